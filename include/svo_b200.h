@@ -1,0 +1,224 @@
+/*
+ * svo_b200.h -- C ABI of the B200 (sm_100a) photometric-alignment library, libsvo_b200.so.
+ *
+ * Drop-in boundary for the hot path of amin-abouee/semi-direct-visual-odometry.  The reference
+ * has no FFI: the path sits behind plain C++ classes.  Every entry point below is what the body
+ * of one of those classes binds (citations relative to the reference tree); the host-side C++
+ * mirror of the classes lives in semi-direct-visual-odometry_b200/host/ and INTEGRATION.md shows
+ * the stub a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every function returns an svo_status (0 = OK, < 0 = error)
+ *     and never throws; svo_last_error() gives the text of the last failure of a context.
+ *   - poses: Sophus::SE3d::params() order  qx qy qz qw tx ty tz, world -> camera
+ *     (include/frame.hpp:198).  K: fx fy cx cy (src/pinhole_camera.cpp:123-139).
+ *   - images: 8-bit gray, row-major.  Pyramids live on the device in "frame slots" of a
+ *     per-context arena; a slot is what a reference Frame's m_imagePyramid is.
+ *   - there is NO CPU fallback: without a CUDA device svo_create fails with SVO_ERR_NO_DEVICE.
+ *   - all work is enqueued on one CUDA stream (svo_config.stream, or a private one).
+ */
+#ifndef SVO_B200_H
+#define SVO_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVO_MAX_LEVELS 8
+
+typedef int32_t svo_status;
+enum {
+    SVO_OK              = 0,
+    SVO_ERR_INVALID     = -1, /* bad argument */
+    SVO_ERR_CUDA        = -2, /* a CUDA call failed; see svo_last_error */
+    SVO_ERR_CAPACITY    = -3, /* batch / feature count above what the context was created for */
+    SVO_ERR_NO_DEVICE   = -4, /* no usable CUDA device: this library has no CPU path */
+    SVO_ERR_UNSUPPORTED = -5  /* e.g. gradientMagnitudeByValue(useBucketing=false), SURVEY 9.7 */
+};
+
+/* optimisation modes: what Optimizer::optimizeLM really does (one damped step),
+ * the same loop with the always-true exit clause removed, and Optimizer::optimizeGN */
+enum { SVO_LM_FAITHFUL = 0, SVO_LM_ITERATED = 1, SVO_GN = 2 };
+
+/* Optimizer::Status, include/optimizer.hpp:21-33 */
+enum {
+    SVO_ST_SUCCESS = 0, SVO_ST_MAX_COFF_DX = 1, SVO_ST_NAN_IN_DX = 2, SVO_ST_SMALL_STEP = 3,
+    SVO_ST_LAMBDA = 4, SVO_ST_NORM_INF_DIFF = 5, SVO_ST_NON_SUFF_POINTS = 6,
+    SVO_ST_INCREASE_CHI2 = 7, SVO_ST_SMALL_CHI2 = 8, SVO_ST_FAILED = 9
+};
+
+typedef struct svo_ctx svo_ctx;
+
+typedef struct {
+    int32_t device;        /* CUDA device ordinal */
+    int32_t width, height; /* camera / level-0 image size (config/config.json:10-11) */
+    int32_t levels;        /* pyramid levels per frame = max_level + 1 (src/system.cpp:36) */
+    int32_t max_frames;    /* frame slots in the device pyramid arena */
+    int32_t max_jobs;      /* sparse-alignment jobs (frame pairs) per batch */
+    int32_t max_features;  /* features per job, n_ref + n_kf */
+    int32_t max_fa_items;  /* FeatureAlignment items per batch */
+    int32_t reserved;
+    void* stream;          /* cudaStream_t to enqueue on; NULL = the context creates one */
+    double K[4];           /* fx fy cx cy */
+} svo_config;
+
+svo_status svo_create(const svo_config* cfg, svo_ctx** out);
+void svo_destroy(svo_ctx* ctx);
+const char* svo_last_error(const svo_ctx* ctx);
+const char* svo_version(void);
+svo_status svo_sync(svo_ctx* ctx);
+/* number of kernels this context has launched so far (bench.py's gpu_launches) */
+int64_t svo_launch_count(const svo_ctx* ctx);
+/* the CUDA stream the context enqueues on (cudaStream_t), so a caller can bracket it with events */
+void* svo_stream(const svo_ctx* ctx);
+/* page-locked host memory: images handed to svo_frames_upload from such a buffer are DMA'd without staging */
+svo_status svo_host_alloc(svo_ctx* ctx, int64_t bytes, void** out);
+svo_status svo_host_free(svo_ctx* ctx, void* p);
+/* level geometry: w_l = (w_{l-1}+1)/2 as cv::pyrDown; pitch is the device row pitch */
+svo_status svo_level_dims(const svo_ctx* ctx, int level, int* w, int* h, int* pitch);
+
+/* ---------------------------------------------------------------------------------------------
+ * ImagePyramid::createImagePyramid (src/image_pyramid.cpp:36-52), called from Frame::Frame
+ * (src/frame.cpp:26).  Builds the image stack AND the gradient stack
+ * (Simd::AbsGradientSaturatedSum at level 0, cv::pyrDown below) for n consecutive slots.
+ * imgs: host pointer, n images of `pitch` bytes per row, `frame_stride` bytes apart.
+ * Asynchronous on the context stream (the host buffer is staged through pinned memory first,
+ * so it may be reused as soon as the call returns).
+ * ------------------------------------------------------------------------------------------- */
+svo_status svo_frames_upload(svo_ctx* ctx, int first_slot, int n, const uint8_t* imgs, int pitch,
+                             int64_t frame_stride);
+/* same, level-0 images already on the device (dptr: device pointer) */
+svo_status svo_frames_upload_device(svo_ctx* ctx, int first_slot, int n, const void* dptr, int pitch,
+                                    int64_t frame_stride);
+/* rebuild the stacks of slots whose level-0 image is already in the arena (asynchronous) */
+svo_status svo_frames_rebuild(svo_ctx* ctx, int first_slot, int n);
+/* ImagePyramid::getImageAtLevel / getGradientAtLevel (src/image_pyramid.cpp:64-100): copies one
+ * level to a continuous host buffer (which: 0 image, 1 gradient).  Synchronous. */
+svo_status svo_frame_download(svo_ctx* ctx, int slot, int level, int which, uint8_t* dst, int dst_pitch);
+
+/* ---------------------------------------------------------------------------------------------
+ * FeatureSelection::gradientMagnitudeByValue(frame, thr, useBucketing = true)
+ * (src/feature_selection.cpp:91-146).  occupancy: m_occupancyGrid as (h/cell+1)*(w/cell+1) bytes,
+ * row-major, nullable.  out: features in cell raster order.  Synchronous.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t x, y;      /* Feature::m_pixelPosition */
+    int32_t magnitude; /* Feature::m_gradientMagnitude */
+} svo_feature_px;
+svo_status svo_select_grid(svo_ctx* ctx, int slot, int cell, uint32_t thr, const uint8_t* occupancy,
+                           svo_feature_px* out, int max_out, int* n_out);
+
+/* ---------------------------------------------------------------------------------------------
+ * ImageAlignment::align(refFrame, curFrame) (src/image_alignment.cpp:25-67), batched over
+ * independent frame pairs ("jobs").
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    double px[2];      /* Feature::m_pixelPosition (level 0) */
+    double bearing[3]; /* Feature::m_bearingVec (unit norm, src/pinhole_camera.cpp:100) */
+    double point[3];   /* Feature::m_point->m_position (world) */
+    int32_t has_point; /* Feature::m_point != nullptr */
+    int32_t reserved;
+} svo_align_feature;
+
+typedef struct {
+    int32_t ref_slot;    /* refFrame->m_imagePyramid */
+    int32_t kf_slot;     /* refFrame->m_lastKeyframe->m_imagePyramid (must exist) */
+    int32_t cur_slot;    /* curFrame->m_imagePyramid */
+    int32_t n_ref;       /* refFrame->numberObservation() */
+    int32_t n_kf;        /* lastKF->numberObservation() */
+    int32_t feat_offset; /* first feature of this job in the feats array: n_ref of ref, then n_kf of lastKF */
+    double T_ref[7];     /* refFrame->m_absPose */
+    double T_kf[7];      /* lastKF->m_absPose */
+    double T_cur[7];     /* curFrame->m_absPose on entry (the prior, src/system.cpp:309) */
+} svo_align_job;
+
+typedef struct {
+    int32_t patch_size; /* m_patchSize, 5 (config/config.json:30); even sizes: SURVEY 9.2 extension */
+    int32_t min_level;  /* 0 */
+    int32_t max_level;  /* 3 */
+    int32_t mode;       /* SVO_LM_FAITHFUL (reference behaviour) | SVO_LM_ITERATED | SVO_GN */
+    int32_t max_iter;   /* Optimizer::m_maxIteration, 20 (src/optimizer.cpp:18) */
+    int32_t reserved;
+} svo_align_params;
+
+typedef struct {
+    double T_cur[7]; /* curFrame->m_absPose after align */
+    double rmse;     /* value align() returns: RMSE of the last level (0 when n_ref == 0) */
+    int32_t status;  /* Optimizer::Status of the last level */
+    int32_t evaluations; /* residual evaluations over all levels */
+    int32_t iterations;  /* solves over all levels */
+    int32_t reserved;
+} svo_align_result;
+
+/* per-level diagnostics; same meaning and layout as orc_level_stats of the oracle */
+typedef struct {
+    double H[36];         /* undamped J^T W J of the first iteration, row-major */
+    double g[6];          /* J^T W r */
+    double dx[6];         /* first solved step */
+    double chi2;          /* sum w r^2 before the first step */
+    double sigma;         /* 1.4826 MAD before the first step */
+    double lambda;        /* damping of the first step (0 for GN) */
+    double pose_after[7]; /* pose at the end of the level */
+    double rmse;
+    int32_t n_px;
+    int32_t status;
+    int32_t iterations;
+    int32_t evaluations;
+} svo_align_level_stats;
+
+/* One call = the whole align: stage -> H2D -> kernel -> D2H -> fetch (synchronous).
+ * results: n_jobs records.  stats: n_jobs * (max_level-min_level+1) records (coarse to fine), nullable. */
+svo_status svo_sparse_align(svo_ctx* ctx, const svo_align_job* jobs, int n_jobs, const svo_align_feature* feats,
+                            int n_feats, const svo_align_params* params, svo_align_result* results,
+                            svo_align_level_stats* stats);
+/* The same, split so a caller can overlap or time the phases; all asynchronous except fetch. */
+svo_status svo_sparse_align_stage(svo_ctx* ctx, const svo_align_job* jobs, int n_jobs, const svo_align_feature* feats,
+                                  int n_feats, const svo_align_params* params, int want_stats);
+svo_status svo_sparse_align_h2d(svo_ctx* ctx);
+svo_status svo_sparse_align_launch(svo_ctx* ctx);
+svo_status svo_sparse_align_d2h(svo_ctx* ctx);
+svo_status svo_sparse_align_fetch(svo_ctx* ctx, svo_align_result* results, svo_align_level_stats* stats);
+
+/* ---------------------------------------------------------------------------------------------
+ * FeatureAlignment::align(refFeature, curFrame, pixelPos) (src/feature_alignment.cpp:25-62),
+ * batched: one item per (feature, frame) call the reference makes serially from
+ * Map::reprojectCell / addCandidateToFrame (src/map.cpp:538,608).  Runs on gradient level 0.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t ref_slot;   /* refFeature->m_frame->m_imagePyramid */
+    int32_t cur_slot;   /* curFrame->m_imagePyramid */
+    double ref_px[2];   /* refFeature->m_pixelPosition */
+    double px[2];       /* pixelPos on entry */
+    double A[4];        /* optional 2x2 row-major affine warp of the template */
+    int32_t use_affine; /* 0 = identity = the reference */
+    int32_t reserved;
+} svo_fa_item;
+
+typedef struct {
+    int32_t patch_size; /* 7 (src/map.cpp:18) */
+    int32_t mode;       /* SVO_LM_FAITHFUL | SVO_LM_ITERATED | SVO_GN */
+    int32_t max_iter;   /* 20 */
+    int32_t reserved;
+} svo_fa_params;
+
+typedef struct {
+    double px[2];  /* pixelPos on return */
+    double rmse;   /* value align() returns (NaN when the start is out of frame, as the reference) */
+    int32_t status;
+    int32_t iterations;
+} svo_fa_result;
+
+svo_status svo_feature_align(svo_ctx* ctx, const svo_fa_item* items, int n, const svo_fa_params* params,
+                             svo_fa_result* results);
+svo_status svo_feature_align_stage(svo_ctx* ctx, const svo_fa_item* items, int n, const svo_fa_params* params);
+svo_status svo_feature_align_h2d(svo_ctx* ctx);
+svo_status svo_feature_align_launch(svo_ctx* ctx);
+svo_status svo_feature_align_d2h(svo_ctx* ctx);
+svo_status svo_feature_align_fetch(svo_ctx* ctx, svo_fa_result* results);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVO_B200_H */

@@ -1,0 +1,151 @@
+/*
+ * svo_oracle.h -- C ABI of the CPU ORACLE (test infrastructure, NOT product code).
+ *
+ * The oracle is a dependency-free, double-precision C++17 restatement of the
+ * photometric-alignment hot path of amin-abouee/semi-direct-visual-odometry
+ * (image pyramid -> grid feature selection -> sparse SE3 image alignment ->
+ * per-feature 2D alignment).  Each function cites the reference file:line it
+ * follows.  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline /
+ * `--impl reference` legs may load it.  The product (libsvo_b200.so) never does.
+ *
+ * PARITY PINNING: the reference's own tests hold no numeric golden vector for
+ * this path and the reference cannot be compiled here
+ * (Eigen, Sophus, OpenCV C++, g2o and libSIMD are absent).  What IS pinned:
+ *   - orc_pyrdown       bit-exact against cv2.pyrDown 4.13 (tests/test_oracle_pyramid.py)
+ *   - orc_project2d     the reference's own KAT, tests/test_camera.cpp:83-96
+ *   - orc_image_jac     against central differences of the projection (python/symbol.py:50-60)
+ *   - orc_se3_exp       against the closed form / scipy Rotation
+ * The alignment numerics (H, g, pose) are therefore "parity unpinned" against a
+ * running reference binary; they are pinned only to this line-by-line restatement.
+ */
+#ifndef SVO_ORACLE_H
+#define SVO_ORACLE_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* optimisation modes */
+enum { ORC_LM_FAITHFUL = 0, ORC_LM_ITERATED = 1, ORC_GN = 2 };
+/* median rule */
+enum { ORC_MEDIAN_EXACT = 0, ORC_MEDIAN_LIBSTDCXX = 1 };
+/* Optimizer::Status, include/optimizer.hpp:21-33 */
+enum {
+    ORC_ST_SUCCESS = 0, ORC_ST_MAX_COFF_DX = 1, ORC_ST_NAN_IN_DX = 2, ORC_ST_SMALL_STEP = 3,
+    ORC_ST_LAMBDA = 4, ORC_ST_NORM_INF_DIFF = 5, ORC_ST_NON_SUFF_POINTS = 6,
+    ORC_ST_INCREASE_CHI2 = 7, ORC_ST_SMALL_CHI2 = 8, ORC_ST_FAILED = 9
+};
+
+/* One feature of the reference frame or of its last keyframe (include/feature.hpp:31-38,
+ * include/point.hpp:28).  Layout is identical to svo_align_feature in include/svo_b200.h. */
+typedef struct {
+    double px[2];      /* Feature::m_pixelPosition, level 0 */
+    double bearing[3]; /* Feature::m_bearingVec (unit norm) */
+    double point[3];   /* Feature::m_point->m_position (world) */
+    int32_t has_point; /* Feature::m_point != nullptr */
+    int32_t reserved;
+} orc_feature;
+
+typedef struct {
+    int32_t patch_size;  /* 5 (config/config.json:30) */
+    int32_t min_level;   /* 0 */
+    int32_t max_level;   /* 3 */
+    int32_t mode;        /* ORC_LM_FAITHFUL | ORC_LM_ITERATED | ORC_GN */
+    int32_t max_iter;    /* Optimizer::m_maxIteration, 20 in the reference */
+    int32_t median_mode; /* ORC_MEDIAN_EXACT | ORC_MEDIAN_LIBSTDCXX */
+} orc_align_params;
+
+/* Per-level record.  H, g, chi2, sigma, n_px, lambda, dx are those of the FIRST
+ * iteration of the level (the only one in LM_FAITHFUL); pose_after, status,
+ * iterations, evaluations describe the end of the level. */
+typedef struct {
+    double H[36];         /* undamped J^T W J, row-major */
+    double g[6];          /* J^T W r */
+    double dx[6];         /* first solved step */
+    double chi2;          /* sum w r^2 before the first step */
+    double sigma;         /* 1.4826 * MAD before the first step */
+    double lambda;        /* damping used in the first step (0 for GN) */
+    double pose_after[7]; /* qx qy qz qw tx ty tz after the level */
+    double rmse;          /* value optimizeLM/GN returns for the level */
+    int32_t n_px;         /* residual rows written in the first evaluation */
+    int32_t status;       /* Optimizer::Status at the end of the level */
+    int32_t iterations;   /* solves performed */
+    int32_t evaluations;  /* residual evaluations performed */
+} orc_level_stats;
+
+/* ---- image pyramid (src/image_pyramid.cpp:36-52) ---- */
+/* Simd::AbsGradientSaturatedSum semantics, 3rd_party/simd/include/Simd/SimdLib.h:856-884 */
+void orc_abs_gradient(const uint8_t* src, int w, int h, int spitch, uint8_t* dst, int dpitch);
+/* cv::pyrDown (5x5 [1 4 6 4 1]^2/256, round half up, BORDER_REFLECT_101), dst = (w+1)/2 x (h+1)/2 */
+void orc_pyrdown(const uint8_t* src, int w, int h, int spitch, uint8_t* dst, int dpitch);
+/* packed pyramid: level l is (w_l x h_l) continuous, levels concatenated; returns bytes needed */
+int64_t orc_pyramid_bytes(int w, int h, int levels);
+/* builds image AND gradient stacks exactly as createImagePyramid does */
+void orc_build_pyramid(const uint8_t* img, int w, int h, int pitch, int levels, uint8_t* img_pyr, uint8_t* grad_pyr);
+
+/* ---- grid feature selection (src/feature_selection.cpp:19-25,91-146) ---- */
+/* occupancy: rows*cols bytes (nullable); out_xym: 3 ints per feature (x, y, magnitude) in cell raster order */
+int orc_grid_select(const uint8_t* grad, int w, int h, int pitch, int cell, uint32_t thr, const uint8_t* occupancy,
+                    int32_t* out_xym, int max_out);
+
+/* ---- numerics (src/algorithm.cpp:834-905, src/pinhole_camera.cpp:50-57) ---- */
+double orc_bilinear_double(const uint8_t* img, int pitch, double x, double y);
+float orc_bilinear_float(const uint8_t* img, int pitch, double x, double y);
+double orc_median(const double* v, int n, int num_valid, int median_mode);
+double orc_sigma(const double* v, int n, int num_valid, int median_mode);
+void orc_project2d(const double K[4], const double p[3], double uv[2]);
+void orc_image_jac(const double p[3], double fx, double fy, double J[12]);
+void orc_se3_exp(const double xi[6], double qt[7]);
+void orc_se3_mul(const double a[7], const double b[7], double out[7]);
+void orc_se3_act(const double T[7], const double p[3], double out[3]);
+void orc_se3_inv(const double T[7], double out[7]);
+int orc_ldlt_solve(const double* A, const double* b, int n, double* x);
+
+/* ---- sparse image alignment (src/image_alignment.cpp:25-67) ---- */
+/* *_pyr: packed image pyramids built by orc_build_pyramid (levels 0..max_level at least).
+ * feats: n_ref features of the reference frame followed by n_kf features of its last keyframe.
+ * T_*: Sophus params order qx qy qz qw tx ty tz, world -> camera.  K: fx fy cx cy.
+ * stats: (max_level - min_level + 1) records, coarse to fine, nullable.
+ * Returns the value ImageAlignment::align returns (RMSE of the last level). */
+double orc_sparse_align(const uint8_t* ref_pyr, const uint8_t* kf_pyr, const uint8_t* cur_pyr, int w, int h,
+                        const orc_feature* feats, int n_ref, int n_kf, const double T_ref[7], const double T_kf[7],
+                        const double K[4], const orc_align_params* params, double T_cur[7], orc_level_stats* stats,
+                        int32_t* status_out);
+
+typedef struct {
+    const uint8_t* ref_pyr;
+    const uint8_t* kf_pyr;
+    const uint8_t* cur_pyr;
+    const orc_feature* feats;
+    int32_t n_ref, n_kf;
+    double T_ref[7], T_kf[7], T_cur[7]; /* T_cur in/out */
+    double rmse;                        /* out */
+    int32_t status;                     /* out */
+    int32_t evaluations;                /* out: residual evaluations over all levels */
+} orc_align_job;
+/* one job per task over n_threads std::threads (CPU baseline for the batched configs) */
+void orc_sparse_align_batch(orc_align_job* jobs, int n_jobs, int w, int h, const double K[4],
+                            const orc_align_params* params, int n_threads);
+
+/* ---- per-feature 2D alignment (src/feature_alignment.cpp:25-62) ---- */
+typedef struct {
+    int32_t patch_size;  /* 7 (src/map.cpp:18) */
+    int32_t mode;        /* ORC_LM_FAITHFUL | ORC_LM_ITERATED | ORC_GN */
+    int32_t max_iter;    /* 20 */
+    int32_t median_mode;
+} orc_fa_params;
+/* ref_grad / cur_grad: gradient level 0 (w x h, pitch w).  A: optional 2x2 row-major affine warp of the
+ * template, NULL = identity = the reference.  px_inout: start / result pixel in cur.
+ * Returns the RMSE FeatureAlignment::align returns. */
+double orc_feature_align(const uint8_t* ref_grad, const uint8_t* cur_grad, int w, int h, const double ref_px[2],
+                         const double* A, double px_inout[2], const orc_fa_params* params, int32_t* status_out,
+                         int32_t* iterations_out);
+
+int orc_hardware_threads(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVO_ORACLE_H */

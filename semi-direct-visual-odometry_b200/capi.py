@@ -1,0 +1,295 @@
+"""ctypes binding of libsvo_b200.so, the C ABI declared in include/svo_b200.h.
+
+This is the Python-side harness over the product library (tests, bench.py, smoke); the
+reference-shaped C++ host classes live in host/.  There is NO CPU fallback: loading fails
+loudly if the library has not been built, and Context() fails if there is no CUDA device.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsvo_b200.so")
+
+OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NO_DEVICE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
+LM_FAITHFUL, LM_ITERATED, GN = 0, 1, 2
+MAX_LEVELS = 8
+
+# every symbol include/svo_b200.h declares (tests check that the library exports all of them)
+SYMBOLS = [
+    "svo_create", "svo_destroy", "svo_last_error", "svo_version", "svo_sync", "svo_launch_count", "svo_stream",
+    "svo_host_alloc", "svo_host_free", "svo_level_dims", "svo_frames_upload", "svo_frames_upload_device",
+    "svo_frames_rebuild", "svo_frame_download", "svo_select_grid", "svo_sparse_align", "svo_sparse_align_stage",
+    "svo_sparse_align_h2d", "svo_sparse_align_launch", "svo_sparse_align_d2h", "svo_sparse_align_fetch",
+    "svo_feature_align", "svo_feature_align_stage", "svo_feature_align_h2d", "svo_feature_align_launch",
+    "svo_feature_align_d2h", "svo_feature_align_fetch",
+]
+
+
+class Config(C.Structure):
+    _fields_ = [("device", C.c_int32), ("width", C.c_int32), ("height", C.c_int32), ("levels", C.c_int32),
+                ("max_frames", C.c_int32), ("max_jobs", C.c_int32), ("max_features", C.c_int32),
+                ("max_fa_items", C.c_int32), ("reserved", C.c_int32), ("stream", C.c_void_p), ("K", C.c_double * 4)]
+
+
+class AlignParams(C.Structure):
+    _fields_ = [("patch_size", C.c_int32), ("min_level", C.c_int32), ("max_level", C.c_int32), ("mode", C.c_int32),
+                ("max_iter", C.c_int32), ("reserved", C.c_int32)]
+
+
+class FaParams(C.Structure):
+    _fields_ = [("patch_size", C.c_int32), ("mode", C.c_int32), ("max_iter", C.c_int32), ("reserved", C.c_int32)]
+
+
+FEATURE_PX_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("magnitude", "<i4")])
+ALIGN_FEATURE_DTYPE = np.dtype([("px", "<f8", 2), ("bearing", "<f8", 3), ("point", "<f8", 3), ("has_point", "<i4"),
+                                ("reserved", "<i4")])
+ALIGN_JOB_DTYPE = np.dtype([("ref_slot", "<i4"), ("kf_slot", "<i4"), ("cur_slot", "<i4"), ("n_ref", "<i4"),
+                            ("n_kf", "<i4"), ("feat_offset", "<i4"), ("T_ref", "<f8", 7), ("T_kf", "<f8", 7),
+                            ("T_cur", "<f8", 7)])
+ALIGN_RESULT_DTYPE = np.dtype([("T_cur", "<f8", 7), ("rmse", "<f8"), ("status", "<i4"), ("evaluations", "<i4"),
+                               ("iterations", "<i4"), ("reserved", "<i4")])
+ALIGN_STATS_DTYPE = np.dtype([("H", "<f8", (6, 6)), ("g", "<f8", 6), ("dx", "<f8", 6), ("chi2", "<f8"), ("sigma", "<f8"),
+                              ("lam", "<f8"), ("pose_after", "<f8", 7), ("rmse", "<f8"), ("n_px", "<i4"),
+                              ("status", "<i4"), ("iterations", "<i4"), ("evaluations", "<i4")])
+FA_ITEM_DTYPE = np.dtype([("ref_slot", "<i4"), ("cur_slot", "<i4"), ("ref_px", "<f8", 2), ("px", "<f8", 2),
+                          ("A", "<f8", 4), ("use_affine", "<i4"), ("reserved", "<i4")])
+FA_RESULT_DTYPE = np.dtype([("px", "<f8", 2), ("rmse", "<f8"), ("status", "<i4"), ("iterations", "<i4")])
+assert ALIGN_FEATURE_DTYPE.itemsize == 72 and ALIGN_JOB_DTYPE.itemsize == 192 and ALIGN_RESULT_DTYPE.itemsize == 80
+assert ALIGN_STATS_DTYPE.itemsize == 488 and FA_ITEM_DTYPE.itemsize == 80 and FA_RESULT_DTYPE.itemsize == 32
+
+_lib = None
+
+
+class SvoError(RuntimeError):
+    def __init__(self, code, text):
+        super().__init__("svo_b200 error %d: %s" % (code, text))
+        self.code = code
+
+
+def load():
+    """dlopen libsvo_b200.so; raises if it has not been built (there is no fallback)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("libsvo_b200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                          "(nvcc, sm_100a).  This package has no CPU or PyTorch fallback.")
+    L = C.CDLL(LIB_PATH)
+    vp, i, i64 = C.c_void_p, C.c_int, C.c_int64
+    L.svo_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
+    L.svo_destroy.argtypes = [vp]
+    L.svo_destroy.restype = None
+    L.svo_last_error.argtypes = [vp]
+    L.svo_last_error.restype = C.c_char_p
+    L.svo_version.restype = C.c_char_p
+    L.svo_sync.argtypes = [vp]
+    L.svo_launch_count.argtypes = [vp]
+    L.svo_launch_count.restype = i64
+    L.svo_stream.argtypes = [vp]
+    L.svo_stream.restype = vp
+    L.svo_host_alloc.argtypes = [vp, i64, C.POINTER(vp)]
+    L.svo_host_free.argtypes = [vp, vp]
+    L.svo_level_dims.argtypes = [vp, i, C.POINTER(i), C.POINTER(i), C.POINTER(i)]
+    L.svo_frames_upload.argtypes = [vp, i, i, vp, i, i64]
+    L.svo_frames_upload_device.argtypes = [vp, i, i, vp, i, i64]
+    L.svo_frames_rebuild.argtypes = [vp, i, i]
+    L.svo_frame_download.argtypes = [vp, i, i, i, vp, i]
+    L.svo_select_grid.argtypes = [vp, i, i, C.c_uint32, vp, vp, i, C.POINTER(i)]
+    L.svo_sparse_align.argtypes = [vp, vp, i, vp, i, C.POINTER(AlignParams), vp, vp]
+    L.svo_sparse_align_stage.argtypes = [vp, vp, i, vp, i, C.POINTER(AlignParams), i]
+    for n in ("h2d", "launch", "d2h"):
+        getattr(L, "svo_sparse_align_" + n).argtypes = [vp]
+        getattr(L, "svo_feature_align_" + n).argtypes = [vp]
+    L.svo_sparse_align_fetch.argtypes = [vp, vp, vp]
+    L.svo_feature_align.argtypes = [vp, vp, i, C.POINTER(FaParams), vp]
+    L.svo_feature_align_stage.argtypes = [vp, vp, i, C.POINTER(FaParams)]
+    L.svo_feature_align_fetch.argtypes = [vp, vp]
+    _lib = L
+    return L
+
+
+def _ptr(a):
+    return a.ctypes.data_as(C.c_void_p) if a is not None else None
+
+
+class PinnedBuffer:
+    """Page-locked host memory from svo_host_alloc, viewed as a numpy uint8 array."""
+
+    def __init__(self, ctx, nbytes):
+        self._ctx = ctx
+        p = C.c_void_p()
+        ctx._check(ctx.L.svo_host_alloc(ctx.h, nbytes, C.byref(p)))
+        self.ptr = p.value
+        self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self.ptr))
+
+    def free(self):
+        if self.ptr:
+            self._ctx.L.svo_host_free(self._ctx.h, self.ptr)
+            self.ptr = None
+            self.array = None
+
+
+class Context:
+    """One svo_ctx: a CUDA stream, a device arena of frame slots (pyramids) and pinned staging."""
+
+    def __init__(self, width, height, K, levels=4, max_frames=4, max_jobs=1, max_features=1024, max_fa_items=2048,
+                 device=0, stream=None):
+        self.L = load()
+        cfg = Config(device, width, height, levels, max_frames, max_jobs, max_features, max_fa_items, 0, stream,
+                     (C.c_double * 4)(*[float(k) for k in K]))
+        h = C.c_void_p()
+        st = self.L.svo_create(C.byref(cfg), C.byref(h))
+        if st != OK:
+            raise SvoError(st, self.L.svo_last_error(None).decode())
+        self.h = h
+        self.width, self.height, self.levels, self.max_frames = width, height, levels, max_frames
+        self.dims = []
+        for l in range(levels):
+            w, hh, p = C.c_int(), C.c_int(), C.c_int()
+            self._check(self.L.svo_level_dims(self.h, l, C.byref(w), C.byref(hh), C.byref(p)))
+            self.dims.append((w.value, hh.value, p.value))
+
+    def _check(self, st):
+        if st != OK:
+            raise SvoError(st, self.L.svo_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.L.svo_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- plumbing ----
+    def sync(self):
+        self._check(self.L.svo_sync(self.h))
+
+    @property
+    def stream(self):
+        return self.L.svo_stream(self.h)
+
+    @property
+    def launches(self):
+        return self.L.svo_launch_count(self.h)
+
+    def pinned(self, nbytes):
+        return PinnedBuffer(self, nbytes)
+
+    # ---- ImagePyramid ----
+    def upload(self, first_slot, imgs):
+        """imgs: (h, w) or (n, h, w) uint8; builds image + gradient stacks of the slots."""
+        a = np.asarray(imgs)
+        assert a.dtype == np.uint8
+        if a.ndim == 2:
+            a = a[None]
+        assert a.shape[1:] == (self.height, self.width), a.shape
+        if not (a.strides[2] == 1 and a.strides[1] >= self.width):
+            a = np.ascontiguousarray(a)
+        self._check(self.L.svo_frames_upload(self.h, first_slot, a.shape[0], a.ctypes.data, a.strides[1], a.strides[0]))
+        return a  # keep alive until the stream has consumed it (pinned path is asynchronous)
+
+    def upload_device(self, first_slot, n, dptr, pitch, frame_stride):
+        self._check(self.L.svo_frames_upload_device(self.h, first_slot, n, dptr, pitch, frame_stride))
+
+    def rebuild(self, first_slot, n):
+        self._check(self.L.svo_frames_rebuild(self.h, first_slot, n))
+
+    def download(self, slot, level, which=0):
+        w, h, _ = self.dims[level]
+        out = np.empty((h, w), np.uint8)
+        self._check(self.L.svo_frame_download(self.h, slot, level, which, out.ctypes.data, w))
+        return out
+
+    # ---- FeatureSelection::gradientMagnitudeByValue ----
+    def select_grid(self, slot, cell=30, thr=50, occupancy=None):
+        rows, cols = self.height // cell + 1, self.width // cell + 1
+        out = np.zeros(rows * cols, FEATURE_PX_DTYPE)
+        occ = None
+        if occupancy is not None:
+            occ = np.ascontiguousarray(np.asarray(occupancy).reshape(-1), dtype=np.uint8)
+            assert occ.size == rows * cols
+        n = C.c_int()
+        self._check(self.L.svo_select_grid(self.h, slot, cell, thr, _ptr(occ), _ptr(out), out.size, C.byref(n)))
+        return out[:n.value].copy()
+
+    # ---- ImageAlignment::align ----
+    def sparse_align(self, jobs, feats, patch_size=5, min_level=0, max_level=3, mode=LM_FAITHFUL, max_iter=20,
+                     want_stats=True):
+        jobs = np.ascontiguousarray(jobs, dtype=ALIGN_JOB_DTYPE).reshape(-1)
+        feats = np.ascontiguousarray(feats, dtype=ALIGN_FEATURE_DTYPE).reshape(-1)
+        prm = AlignParams(patch_size, min_level, max_level, mode, max_iter, 0)
+        res = np.zeros(jobs.size, ALIGN_RESULT_DTYPE)
+        nl = max_level - min_level + 1
+        stats = np.zeros((jobs.size, nl), ALIGN_STATS_DTYPE) if want_stats else None
+        self._check(self.L.svo_sparse_align(self.h, _ptr(jobs), jobs.size, _ptr(feats), feats.size, C.byref(prm),
+                                            _ptr(res), _ptr(stats)))
+        return res, stats
+
+    def sparse_align_stage(self, jobs, feats, patch_size=5, min_level=0, max_level=3, mode=LM_FAITHFUL, max_iter=20,
+                           want_stats=False):
+        jobs = np.ascontiguousarray(jobs, dtype=ALIGN_JOB_DTYPE).reshape(-1)
+        feats = np.ascontiguousarray(feats, dtype=ALIGN_FEATURE_DTYPE).reshape(-1)
+        prm = AlignParams(patch_size, min_level, max_level, mode, max_iter, 0)
+        self._check(self.L.svo_sparse_align_stage(self.h, _ptr(jobs), jobs.size, _ptr(feats), feats.size, C.byref(prm),
+                                                  1 if want_stats else 0))
+        self._staged = (jobs.size, max_level - min_level + 1, want_stats)
+
+    def sparse_align_h2d(self):
+        self._check(self.L.svo_sparse_align_h2d(self.h))
+
+    def sparse_align_launch(self):
+        self._check(self.L.svo_sparse_align_launch(self.h))
+
+    def sparse_align_d2h(self):
+        self._check(self.L.svo_sparse_align_d2h(self.h))
+
+    def sparse_align_fetch(self):
+        n, nl, ws = self._staged
+        res = np.zeros(n, ALIGN_RESULT_DTYPE)
+        stats = np.zeros((n, nl), ALIGN_STATS_DTYPE) if ws else None
+        self._check(self.L.svo_sparse_align_fetch(self.h, _ptr(res), _ptr(stats)))
+        return res, stats
+
+    # ---- FeatureAlignment::align ----
+    def feature_align(self, items, patch_size=7, mode=LM_FAITHFUL, max_iter=20):
+        items = np.ascontiguousarray(items, dtype=FA_ITEM_DTYPE).reshape(-1)
+        prm = FaParams(patch_size, mode, max_iter, 0)
+        res = np.zeros(items.size, FA_RESULT_DTYPE)
+        self._check(self.L.svo_feature_align(self.h, _ptr(items), items.size, C.byref(prm), _ptr(res)))
+        return res
+
+    def feature_align_stage(self, items, patch_size=7, mode=LM_FAITHFUL, max_iter=20):
+        items = np.ascontiguousarray(items, dtype=FA_ITEM_DTYPE).reshape(-1)
+        prm = FaParams(patch_size, mode, max_iter, 0)
+        self._check(self.L.svo_feature_align_stage(self.h, _ptr(items), items.size, C.byref(prm)))
+        self._staged_fa = items.size
+
+    def feature_align_h2d(self):
+        self._check(self.L.svo_feature_align_h2d(self.h))
+
+    def feature_align_launch(self):
+        self._check(self.L.svo_feature_align_launch(self.h))
+
+    def feature_align_d2h(self):
+        self._check(self.L.svo_feature_align_d2h(self.h))
+
+    def feature_align_fetch(self):
+        res = np.zeros(self._staged_fa, FA_RESULT_DTYPE)
+        self._check(self.L.svo_feature_align_fetch(self.h, _ptr(res)))
+        return res
+
+
+def make_jobs(n):
+    return np.zeros(n, ALIGN_JOB_DTYPE)

@@ -1,0 +1,493 @@
+// api.cu -- the C ABI of libsvo_b200.so (include/svo_b200.h): context, pyramid arena, pinned staging and the
+// stage -> H2D -> launch -> D2H -> fetch plumbing around the kernels in pyramid.cu / select.cu /
+// sparse_align.cu / feature_align.cu.  There is no CPU path: without a CUDA device svo_create fails.
+#include <algorithm>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+
+#include "ctx.h"
+
+namespace {
+
+thread_local std::string g_create_error;
+
+inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// staging ring for pageable host images: two halves so the CPU copy of chunk i+1 overlaps the DMA of chunk i
+constexpr int kStageFrames = 16;
+
+void release(svo_ctx* ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->cfg.device);
+    if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    for (int l = 0; l < SVO_MAX_LEVELS; l++) {
+        if (ctx->arena.img[l]) cudaFree(ctx->arena.img[l]);
+        if (ctx->arena.grad[l]) cudaFree(ctx->arena.grad[l]);
+    }
+    for (int i = 0; i < 2; i++) {
+        if (ctx->h_img_stage[i]) cudaFreeHost(ctx->h_img_stage[i]);
+        if (ctx->img_stage_free[i]) cudaEventDestroy(ctx->img_stage_free[i]);
+    }
+    cudaFree(ctx->d_cell_best);
+    cudaFree(ctx->d_occupancy);
+    cudaFree(ctx->d_sel_out);
+    cudaFree(ctx->d_sel_count);
+    cudaFreeHost(ctx->h_sel_out);
+    cudaFreeHost(ctx->h_sel_count);
+    cudaFreeHost(ctx->h_occupancy);
+    cudaFreeHost(ctx->h_jobs);
+    cudaFreeHost(ctx->h_feats);
+    cudaFreeHost(ctx->h_results);
+    cudaFreeHost(ctx->h_stats);
+    cudaFree(ctx->d_jobs);
+    cudaFree(ctx->d_feats);
+    cudaFree(ctx->d_results);
+    cudaFree(ctx->d_stats);
+    cudaFree(ctx->d_scratch_tpl);
+    cudaFree(ctx->d_scratch_jac);
+    cudaFreeHost(ctx->h_fa_items);
+    cudaFreeHost(ctx->h_fa_results);
+    cudaFree(ctx->d_fa_items);
+    cudaFree(ctx->d_fa_results);
+    if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+    delete ctx;
+}
+
+svo_status init(svo_ctx* ctx)
+{
+    const svo_config& c = ctx->cfg;
+    SVO_CUDA(cudaSetDevice(c.device));
+    cudaDeviceProp prop;
+    SVO_CUDA(cudaGetDeviceProperties(&prop, c.device));
+    ctx->sm_count       = prop.multiProcessorCount;
+    ctx->max_smem_optin = (int)prop.sharedMemPerBlockOptin;
+    if (c.stream) {
+        ctx->stream     = (cudaStream_t)c.stream;
+        ctx->own_stream = false;
+    } else {
+        SVO_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+        ctx->own_stream = true;
+    }
+
+    // ---- pyramid arena: [level][slot][h][pitch], pitch a multiple of 16 B, planes 256-B aligned ----
+    PyramidArena& a = ctx->arena;
+    a.levels        = c.levels;
+    int w = c.width, h = c.height;
+    for (int l = 0; l < c.levels; l++) {
+        LevelGeom& g   = a.geom[l];
+        g.w            = w;
+        g.h            = h;
+        g.pitch        = (int)round_up(w, 16);
+        g.plane_stride = round_up((int64_t)g.pitch * h, 256);
+        const size_t bytes = (size_t)g.plane_stride * c.max_frames;
+        SVO_CUDA(cudaMalloc(&a.img[l], bytes));
+        SVO_CUDA(cudaMalloc(&a.grad[l], bytes));
+        SVO_CUDA(cudaMemsetAsync(a.img[l], 0, bytes, ctx->stream));
+        SVO_CUDA(cudaMemsetAsync(a.grad[l], 0, bytes, ctx->stream));
+        w = (w + 1) / 2;  // cv::pyrDown default size, src/image_pyramid.cpp:49-50
+        h = (h + 1) / 2;
+    }
+    ctx->h_img_stage_bytes = (int64_t)a.geom[0].plane_stride * std::min(kStageFrames, c.max_frames);
+    for (int i = 0; i < 2; i++) {
+        SVO_CUDA(cudaHostAlloc(&ctx->h_img_stage[i], ctx->h_img_stage_bytes, cudaHostAllocDefault));
+        SVO_CUDA(cudaEventCreateWithFlags(&ctx->img_stage_free[i], cudaEventDisableTiming));
+    }
+    ctx->stage_next = 0;
+
+    // ---- selection: cells of >= 4 px ----
+    ctx->sel_cap_cells = (c.height / 4 + 1) * (c.width / 4 + 1);
+    SVO_CUDA(cudaMalloc(&ctx->d_cell_best, sizeof(uint32_t) * ctx->sel_cap_cells));
+    SVO_CUDA(cudaMalloc(&ctx->d_occupancy, ctx->sel_cap_cells));
+    SVO_CUDA(cudaMalloc(&ctx->d_sel_out, sizeof(svo_feature_px) * ctx->sel_cap_cells));
+    SVO_CUDA(cudaMalloc(&ctx->d_sel_count, sizeof(int32_t)));
+    SVO_CUDA(cudaHostAlloc(&ctx->h_sel_out, sizeof(svo_feature_px) * ctx->sel_cap_cells, cudaHostAllocDefault));
+    SVO_CUDA(cudaHostAlloc(&ctx->h_sel_count, sizeof(int32_t), cudaHostAllocDefault));
+    SVO_CUDA(cudaHostAlloc(&ctx->h_occupancy, ctx->sel_cap_cells, cudaHostAllocDefault));
+
+    // ---- sparse alignment ----
+    const int64_t nj = std::max(1, c.max_jobs);
+    ctx->feats_cap   = nj * std::max(1, c.max_features);
+    SVO_CUDA(cudaHostAlloc(&ctx->h_jobs, sizeof(svo_align_job) * nj, cudaHostAllocDefault));
+    SVO_CUDA(cudaHostAlloc(&ctx->h_feats, sizeof(svo_align_feature) * ctx->feats_cap, cudaHostAllocDefault));
+    SVO_CUDA(cudaHostAlloc(&ctx->h_results, sizeof(svo_align_result) * nj, cudaHostAllocDefault));
+    SVO_CUDA(cudaHostAlloc(&ctx->h_stats, sizeof(svo_align_level_stats) * nj * c.levels, cudaHostAllocDefault));
+    SVO_CUDA(cudaMalloc(&ctx->d_jobs, sizeof(svo_align_job) * nj));
+    SVO_CUDA(cudaMalloc(&ctx->d_feats, sizeof(svo_align_feature) * ctx->feats_cap));
+    SVO_CUDA(cudaMalloc(&ctx->d_results, sizeof(svo_align_result) * nj));
+    SVO_CUDA(cudaMalloc(&ctx->d_stats, sizeof(svo_align_level_stats) * nj * c.levels));
+    SVO_CUDA(cudaMalloc(&ctx->d_scratch_jac, sizeof(float) * 12 * ctx->feats_cap));
+    ctx->scratch_area = 0;
+
+    // ---- feature alignment ----
+    const int64_t nf = std::max(1, c.max_fa_items);
+    SVO_CUDA(cudaHostAlloc(&ctx->h_fa_items, sizeof(svo_fa_item) * nf, cudaHostAllocDefault));
+    SVO_CUDA(cudaHostAlloc(&ctx->h_fa_results, sizeof(svo_fa_result) * nf, cudaHostAllocDefault));
+    SVO_CUDA(cudaMalloc(&ctx->d_fa_items, sizeof(svo_fa_item) * nf));
+    SVO_CUDA(cudaMalloc(&ctx->d_fa_results, sizeof(svo_fa_result) * nf));
+    SVO_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SVO_OK;
+}
+
+// template scratch grows with the patch area of the request (allocation happens outside any warm loop)
+svo_status ensure_scratch(svo_ctx* ctx, int area)
+{
+    if (area <= ctx->scratch_area) return SVO_OK;
+    SVO_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (ctx->d_scratch_tpl) SVO_CUDA(cudaFree(ctx->d_scratch_tpl));
+    ctx->d_scratch_tpl = nullptr;
+    ctx->scratch_area  = 0;
+    SVO_CUDA(cudaMalloc(&ctx->d_scratch_tpl, sizeof(float) * 3 * (size_t)ctx->feats_cap * area));
+    ctx->scratch_area = area;
+    return SVO_OK;
+}
+
+inline bool bad_slot(const svo_ctx* ctx, int s) { return s < 0 || s >= ctx->cfg.max_frames; }
+
+}  // namespace
+
+extern "C" {
+
+const char* svo_version(void) { return "svo_b200 0.1 (sm_100a)"; }
+
+svo_status svo_create(const svo_config* cfg, svo_ctx** out)
+{
+    if (!cfg || !out) return SVO_ERR_INVALID;
+    *out = nullptr;
+    if (cfg->width < 8 || cfg->height < 8 || cfg->levels < 1 || cfg->levels > SVO_MAX_LEVELS || cfg->max_frames < 1 ||
+        cfg->max_jobs < 0 || cfg->max_features < 0 || cfg->max_fa_items < 0) {
+        g_create_error = "svo_create: invalid configuration";
+        return SVO_ERR_INVALID;
+    }
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || cfg->device < 0 || cfg->device >= n) {
+        cudaGetLastError();
+        g_create_error = "svo_create: no usable CUDA device (this library has no CPU path)";
+        return SVO_ERR_NO_DEVICE;
+    }
+    svo_ctx* ctx = new (std::nothrow) svo_ctx();
+    if (!ctx) return SVO_ERR_INVALID;
+    ctx->cfg = *cfg;
+    const svo_status st = init(ctx);
+    if (st != SVO_OK) {
+        g_create_error = ctx->err;
+        release(ctx);
+        return st;
+    }
+    *out = ctx;
+    return SVO_OK;
+}
+
+void svo_destroy(svo_ctx* ctx) { release(ctx); }
+
+const char* svo_last_error(const svo_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+svo_status svo_sync(svo_ctx* ctx)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    SVO_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SVO_OK;
+}
+
+int64_t svo_launch_count(const svo_ctx* ctx) { return ctx ? ctx->launches : 0; }
+
+void* svo_stream(const svo_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+
+svo_status svo_level_dims(const svo_ctx* ctx, int level, int* w, int* h, int* pitch)
+{
+    if (!ctx || level < 0 || level >= ctx->arena.levels) return SVO_ERR_INVALID;
+    if (w) *w = ctx->arena.geom[level].w;
+    if (h) *h = ctx->arena.geom[level].h;
+    if (pitch) *pitch = ctx->arena.geom[level].pitch;
+    return SVO_OK;
+}
+
+svo_status svo_host_alloc(svo_ctx* ctx, int64_t bytes, void** out)
+{
+    if (!ctx || !out || bytes <= 0) return SVO_ERR_INVALID;
+    SVO_CUDA(cudaSetDevice(ctx->cfg.device));
+    SVO_CUDA(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
+    return SVO_OK;
+}
+
+svo_status svo_host_free(svo_ctx* ctx, void* p)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    if (p) SVO_CUDA(cudaFreeHost(p));
+    return SVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// frames
+// ------------------------------------------------------------------------------------------------
+svo_status svo_frames_upload(svo_ctx* ctx, int first_slot, int n, const uint8_t* imgs, int pitch, int64_t frame_stride)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    if (n == 0) return SVO_OK;
+    const LevelGeom& g = ctx->arena.geom[0];
+    if (!imgs || n < 0 || bad_slot(ctx, first_slot) || bad_slot(ctx, first_slot + n - 1) || pitch < g.w ||
+        (n > 1 && frame_stride < (int64_t)pitch * g.h))
+        SVO_FAIL(SVO_ERR_INVALID, "svo_frames_upload: bad slot range, pitch or stride");
+    SVO_CUDA(cudaSetDevice(ctx->cfg.device));
+    cudaPointerAttributes attr;
+    const bool pinned = cudaPointerGetAttributes(&attr, imgs) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+    cudaGetLastError();
+    if (pinned) {
+        // caller's buffer is page-locked (svo_host_alloc): DMA straight from it
+        for (int i = 0; i < n; i++)
+            SVO_CUDA(cudaMemcpy2DAsync(ctx->arena.img[0] + (int64_t)(first_slot + i) * g.plane_stride, g.pitch,
+                                       imgs + (int64_t)i * frame_stride, pitch, g.w, g.h, cudaMemcpyHostToDevice,
+                                       ctx->stream));
+    } else {
+        const int chunk = (int)(ctx->h_img_stage_bytes / g.plane_stride);
+        for (int i0 = 0; i0 < n; i0 += chunk) {
+            const int m   = std::min(chunk, n - i0);
+            const int buf = ctx->stage_next;
+            ctx->stage_next ^= 1;
+            SVO_CUDA(cudaEventSynchronize(ctx->img_stage_free[buf]));
+            uint8_t* st = ctx->h_img_stage[buf];
+            for (int i = 0; i < m; i++) {
+                const uint8_t* src = imgs + (int64_t)(i0 + i) * frame_stride;
+                uint8_t* dst       = st + (int64_t)i * g.plane_stride;
+                if (pitch == g.pitch)
+                    std::memcpy(dst, src, (size_t)pitch * g.h);
+                else
+                    for (int y = 0; y < g.h; y++) std::memcpy(dst + (int64_t)y * g.pitch, src + (int64_t)y * pitch, g.w);
+            }
+            // staged planes have the device layout: one contiguous copy per chunk
+            SVO_CUDA(cudaMemcpyAsync(ctx->arena.img[0] + (int64_t)(first_slot + i0) * g.plane_stride, st,
+                                     (size_t)m * g.plane_stride, cudaMemcpyHostToDevice, ctx->stream));
+            SVO_CUDA(cudaEventRecord(ctx->img_stage_free[buf], ctx->stream));
+        }
+    }
+    return launch_pyramid_build(ctx, first_slot, n);
+}
+
+svo_status svo_frames_upload_device(svo_ctx* ctx, int first_slot, int n, const void* dptr, int pitch, int64_t frame_stride)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    if (n == 0) return SVO_OK;
+    const LevelGeom& g = ctx->arena.geom[0];
+    if (!dptr || n < 0 || bad_slot(ctx, first_slot) || bad_slot(ctx, first_slot + n - 1) || pitch < g.w)
+        SVO_FAIL(SVO_ERR_INVALID, "svo_frames_upload_device: bad slot range or pitch");
+    SVO_CUDA(cudaSetDevice(ctx->cfg.device));
+    for (int i = 0; i < n; i++)
+        SVO_CUDA(cudaMemcpy2DAsync(ctx->arena.img[0] + (int64_t)(first_slot + i) * g.plane_stride, g.pitch,
+                                   (const uint8_t*)dptr + (int64_t)i * frame_stride, pitch, g.w, g.h,
+                                   cudaMemcpyDeviceToDevice, ctx->stream));
+    return launch_pyramid_build(ctx, first_slot, n);
+}
+
+svo_status svo_frames_rebuild(svo_ctx* ctx, int first_slot, int n)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    if (n == 0) return SVO_OK;
+    if (n < 0 || bad_slot(ctx, first_slot) || bad_slot(ctx, first_slot + n - 1))
+        SVO_FAIL(SVO_ERR_INVALID, "svo_frames_rebuild: bad slot range");
+    SVO_CUDA(cudaSetDevice(ctx->cfg.device));
+    return launch_pyramid_build(ctx, first_slot, n);
+}
+
+svo_status svo_frame_download(svo_ctx* ctx, int slot, int level, int which, uint8_t* dst, int dst_pitch)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    if (!dst || bad_slot(ctx, slot) || level < 0 || level >= ctx->arena.levels || (which != 0 && which != 1))
+        SVO_FAIL(SVO_ERR_INVALID, "svo_frame_download: bad slot / level / which");
+    const LevelGeom& g = ctx->arena.geom[level];
+    if (dst_pitch < g.w) SVO_FAIL(SVO_ERR_INVALID, "svo_frame_download: dst_pitch below the level width");
+    SVO_CUDA(cudaSetDevice(ctx->cfg.device));
+    const uint8_t* src = (which ? ctx->arena.grad[level] : ctx->arena.img[level]) + (int64_t)slot * g.plane_stride;
+    SVO_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, g.pitch, g.w, g.h, cudaMemcpyDeviceToHost, ctx->stream));
+    SVO_CUDA(cudaStreamSynchronize(ctx->stream));
+    return SVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// grid selection
+// ------------------------------------------------------------------------------------------------
+svo_status svo_select_grid(svo_ctx* ctx, int slot, int cell, uint32_t thr, const uint8_t* occupancy, svo_feature_px* out,
+                           int max_out, int* n_out)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    if (!out || !n_out || max_out < 0 || bad_slot(ctx, slot) || cell < 4)
+        SVO_FAIL(SVO_ERR_INVALID, "svo_select_grid: bad arguments (cell must be >= 4)");
+    const LevelGeom& g = ctx->arena.geom[0];
+    const int rows = g.h / cell + 1, cols = g.w / cell + 1;  // src/feature_selection.cpp:19-25
+    if (rows * cols > ctx->sel_cap_cells) SVO_FAIL(SVO_ERR_CAPACITY, "svo_select_grid: too many cells");
+    SVO_CUDA(cudaSetDevice(ctx->cfg.device));
+    if (occupancy) {
+        std::memcpy(ctx->h_occupancy, occupancy, (size_t)rows * cols);
+        SVO_CUDA(cudaMemcpyAsync(ctx->d_occupancy, ctx->h_occupancy, (size_t)rows * cols, cudaMemcpyHostToDevice,
+                                 ctx->stream));
+    }
+    ctx->sel_use_occupancy = occupancy != nullptr;
+    const svo_status st    = launch_grid_select(ctx, slot, cell, thr, rows, cols);
+    if (st != SVO_OK) return st;
+    SVO_CUDA(cudaMemcpyAsync(ctx->h_sel_count, ctx->d_sel_count, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SVO_CUDA(cudaMemcpyAsync(ctx->h_sel_out, ctx->d_sel_out, sizeof(svo_feature_px) * rows * cols, cudaMemcpyDeviceToHost,
+                             ctx->stream));
+    SVO_CUDA(cudaStreamSynchronize(ctx->stream));
+    const int n = *ctx->h_sel_count;
+    *n_out      = n;
+    std::memcpy(out, ctx->h_sel_out, sizeof(svo_feature_px) * std::min(n, max_out));
+    return SVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// sparse image alignment
+// ------------------------------------------------------------------------------------------------
+svo_status svo_sparse_align_stage(svo_ctx* ctx, const svo_align_job* jobs, int n_jobs, const svo_align_feature* feats,
+                                  int n_feats, const svo_align_params* prm, int want_stats)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    if (!jobs || !prm || n_jobs < 0 || n_feats < 0 || (n_feats > 0 && !feats))
+        SVO_FAIL(SVO_ERR_INVALID, "svo_sparse_align: null argument");
+    if (n_jobs > ctx->cfg.max_jobs || n_feats > ctx->feats_cap)
+        SVO_FAIL(SVO_ERR_CAPACITY, "svo_sparse_align: more jobs / features than the context was created for");
+    if (prm->patch_size < 1 || prm->patch_size > 16 || prm->min_level < 0 || prm->max_level < prm->min_level ||
+        prm->max_level >= ctx->arena.levels || prm->mode < SVO_LM_FAITHFUL || prm->mode > SVO_GN)
+        SVO_FAIL(SVO_ERR_INVALID, "svo_sparse_align: bad parameters");
+    for (int j = 0; j < n_jobs; j++) {
+        const svo_align_job& J = jobs[j];
+        if (bad_slot(ctx, J.ref_slot) || bad_slot(ctx, J.kf_slot) || bad_slot(ctx, J.cur_slot))
+            SVO_FAIL(SVO_ERR_INVALID, "svo_sparse_align: frame slot out of range (a last keyframe is required, "
+                                      "src/image_alignment.cpp:30-31)");
+        if (J.n_ref < 0 || J.n_kf < 0 || J.n_ref + J.n_kf > ctx->cfg.max_features)
+            SVO_FAIL(SVO_ERR_CAPACITY, "svo_sparse_align: job has more features than max_features");
+        if (J.feat_offset < 0 || (int64_t)J.feat_offset + J.n_ref + J.n_kf > n_feats)
+            SVO_FAIL(SVO_ERR_INVALID, "svo_sparse_align: feature range outside the feats array");
+    }
+    SVO_CUDA(cudaSetDevice(ctx->cfg.device));
+    const svo_status st = ensure_scratch(ctx, prm->patch_size * prm->patch_size);
+    if (st != SVO_OK) return st;
+    // the pinned buffers may still be read by the previous batch's H2D
+    SVO_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(ctx->h_jobs, jobs, sizeof(svo_align_job) * n_jobs);
+    if (n_feats) std::memcpy(ctx->h_feats, feats, sizeof(svo_align_feature) * n_feats);
+    ctx->staged_jobs       = n_jobs;
+    ctx->staged_feats      = n_feats;
+    ctx->staged_levels     = prm->max_level - prm->min_level + 1;
+    ctx->staged_want_stats = want_stats;
+    ctx->staged_params     = *prm;
+    return SVO_OK;
+}
+
+svo_status svo_sparse_align_h2d(svo_ctx* ctx)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    if (ctx->staged_jobs == 0) return SVO_OK;
+    SVO_CUDA(cudaMemcpyAsync(ctx->d_jobs, ctx->h_jobs, sizeof(svo_align_job) * ctx->staged_jobs, cudaMemcpyHostToDevice,
+                             ctx->stream));
+    if (ctx->staged_feats)
+        SVO_CUDA(cudaMemcpyAsync(ctx->d_feats, ctx->h_feats, sizeof(svo_align_feature) * ctx->staged_feats,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    return SVO_OK;
+}
+
+svo_status svo_sparse_align_launch(svo_ctx* ctx)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    return launch_sparse_align(ctx);
+}
+
+svo_status svo_sparse_align_d2h(svo_ctx* ctx)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    if (ctx->staged_jobs == 0) return SVO_OK;
+    SVO_CUDA(cudaMemcpyAsync(ctx->h_results, ctx->d_results, sizeof(svo_align_result) * ctx->staged_jobs,
+                             cudaMemcpyDeviceToHost, ctx->stream));
+    if (ctx->staged_want_stats)
+        SVO_CUDA(cudaMemcpyAsync(ctx->h_stats, ctx->d_stats,
+                                 sizeof(svo_align_level_stats) * ctx->staged_jobs * ctx->staged_levels,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    return SVO_OK;
+}
+
+svo_status svo_sparse_align_fetch(svo_ctx* ctx, svo_align_result* results, svo_align_level_stats* stats)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    SVO_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (results) std::memcpy(results, ctx->h_results, sizeof(svo_align_result) * ctx->staged_jobs);
+    if (stats) {
+        if (!ctx->staged_want_stats) SVO_FAIL(SVO_ERR_INVALID, "svo_sparse_align_fetch: stats were not requested at stage");
+        std::memcpy(stats, ctx->h_stats, sizeof(svo_align_level_stats) * ctx->staged_jobs * ctx->staged_levels);
+    }
+    return SVO_OK;
+}
+
+svo_status svo_sparse_align(svo_ctx* ctx, const svo_align_job* jobs, int n_jobs, const svo_align_feature* feats, int n_feats,
+                            const svo_align_params* prm, svo_align_result* results, svo_align_level_stats* stats)
+{
+    svo_status st = svo_sparse_align_stage(ctx, jobs, n_jobs, feats, n_feats, prm, stats != nullptr);
+    if (st != SVO_OK) return st;
+    if ((st = svo_sparse_align_h2d(ctx)) != SVO_OK) return st;
+    if ((st = svo_sparse_align_launch(ctx)) != SVO_OK) return st;
+    if ((st = svo_sparse_align_d2h(ctx)) != SVO_OK) return st;
+    return svo_sparse_align_fetch(ctx, results, stats);
+}
+
+// ------------------------------------------------------------------------------------------------
+// feature alignment
+// ------------------------------------------------------------------------------------------------
+svo_status svo_feature_align_stage(svo_ctx* ctx, const svo_fa_item* items, int n, const svo_fa_params* prm)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    if (n < 0 || !prm || (n > 0 && !items)) SVO_FAIL(SVO_ERR_INVALID, "svo_feature_align: null argument");
+    if (n > ctx->cfg.max_fa_items) SVO_FAIL(SVO_ERR_CAPACITY, "svo_feature_align: more items than max_fa_items");
+    if (prm->patch_size < 1 || prm->patch_size > 8 || prm->mode < SVO_LM_FAITHFUL || prm->mode > SVO_GN)
+        SVO_FAIL(SVO_ERR_INVALID, "svo_feature_align: patch_size must be 1..8 and mode valid");
+    for (int i = 0; i < n; i++)
+        if (bad_slot(ctx, items[i].ref_slot) || bad_slot(ctx, items[i].cur_slot))
+            SVO_FAIL(SVO_ERR_INVALID, "svo_feature_align: frame slot out of range");
+    SVO_CUDA(cudaSetDevice(ctx->cfg.device));
+    SVO_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n) std::memcpy(ctx->h_fa_items, items, sizeof(svo_fa_item) * n);
+    ctx->staged_fa        = n;
+    ctx->staged_fa_params = *prm;
+    return SVO_OK;
+}
+
+svo_status svo_feature_align_h2d(svo_ctx* ctx)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    if (ctx->staged_fa)
+        SVO_CUDA(cudaMemcpyAsync(ctx->d_fa_items, ctx->h_fa_items, sizeof(svo_fa_item) * ctx->staged_fa,
+                                 cudaMemcpyHostToDevice, ctx->stream));
+    return SVO_OK;
+}
+
+svo_status svo_feature_align_launch(svo_ctx* ctx)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    return launch_feature_align(ctx);
+}
+
+svo_status svo_feature_align_d2h(svo_ctx* ctx)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    if (ctx->staged_fa)
+        SVO_CUDA(cudaMemcpyAsync(ctx->h_fa_results, ctx->d_fa_results, sizeof(svo_fa_result) * ctx->staged_fa,
+                                 cudaMemcpyDeviceToHost, ctx->stream));
+    return SVO_OK;
+}
+
+svo_status svo_feature_align_fetch(svo_ctx* ctx, svo_fa_result* results)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    SVO_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (results && ctx->staged_fa) std::memcpy(results, ctx->h_fa_results, sizeof(svo_fa_result) * ctx->staged_fa);
+    return SVO_OK;
+}
+
+svo_status svo_feature_align(svo_ctx* ctx, const svo_fa_item* items, int n, const svo_fa_params* prm, svo_fa_result* results)
+{
+    svo_status st = svo_feature_align_stage(ctx, items, n, prm);
+    if (st != SVO_OK) return st;
+    if ((st = svo_feature_align_h2d(ctx)) != SVO_OK) return st;
+    if ((st = svo_feature_align_launch(ctx)) != SVO_OK) return st;
+    if ((st = svo_feature_align_d2h(ctx)) != SVO_OK) return st;
+    return svo_feature_align_fetch(ctx, results);
+}
+
+}  // extern "C"

@@ -1,0 +1,118 @@
+// ctx.h -- internal context of libsvo_b200.so (not part of the C ABI)
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+
+#include "../../include/svo_b200.h"
+
+struct LevelGeom {
+    int w, h, pitch;       // pitch: multiple of 16 B so that TMA descriptors over a plane are legal
+    int64_t plane_stride;  // bytes between the same level of consecutive slots (multiple of 256)
+};
+
+// One arena per stack (image / gradient) and level: [slot][h][pitch] u8.
+struct PyramidArena {
+    int levels;
+    LevelGeom geom[SVO_MAX_LEVELS];
+    uint8_t* img[SVO_MAX_LEVELS];
+    uint8_t* grad[SVO_MAX_LEVELS];
+};
+
+// Device-side view handed to kernels by value.
+struct ArenaView {
+    const uint8_t* img[SVO_MAX_LEVELS];
+    const uint8_t* grad[SVO_MAX_LEVELS];
+    int w[SVO_MAX_LEVELS], h[SVO_MAX_LEVELS], pitch[SVO_MAX_LEVELS];
+    long long plane_stride[SVO_MAX_LEVELS];
+};
+
+struct svo_ctx {
+    svo_config cfg;
+    cudaStream_t stream;
+    bool own_stream;
+    int sm_count;
+    int max_smem_optin;
+    std::string err;
+    int64_t launches;
+
+    PyramidArena arena;
+
+    // pinned staging for image upload
+    uint8_t* h_img_stage[2];     // two halves: CPU copy of chunk i+1 overlaps the DMA of chunk i
+    int64_t h_img_stage_bytes;   // per half
+    cudaEvent_t img_stage_free[2];  // recorded after the last H2D that read the half
+    int stage_next;
+
+    // selection
+    uint32_t* d_cell_best;       // per cell packed (value << 24 | ~index)
+    uint8_t* d_occupancy;        // per cell
+    svo_feature_px* d_sel_out;   // compacted features
+    int32_t* d_sel_count;
+    svo_feature_px* h_sel_out;   // pinned
+    int32_t* h_sel_count;        // pinned
+    uint8_t* h_occupancy;        // pinned
+    int sel_cap_cells;
+    bool sel_use_occupancy;
+
+    // sparse alignment batch
+    svo_align_job* h_jobs;       // pinned
+    svo_align_feature* h_feats;  // pinned
+    svo_align_result* h_results; // pinned
+    svo_align_level_stats* h_stats;  // pinned
+    svo_align_job* d_jobs;
+    svo_align_feature* d_feats;
+    svo_align_result* d_results;
+    svo_align_level_stats* d_stats;
+    float* d_scratch_tpl;        // [job][3][Nmax]  template intensity, gx, gy per patch pixel
+    float* d_scratch_jac;        // [job][F][12]   image Jacobian rows per feature
+    int64_t feats_cap;
+    int scratch_area;            // patch area d_scratch_tpl is sized for
+    int staged_jobs, staged_feats, staged_levels, staged_want_stats;
+    svo_align_params staged_params;
+
+    // feature alignment batch
+    svo_fa_item* h_fa_items;     // pinned
+    svo_fa_result* h_fa_results; // pinned
+    svo_fa_item* d_fa_items;
+    svo_fa_result* d_fa_results;
+    int staged_fa;
+    svo_fa_params staged_fa_params;
+};
+
+#define SVO_CUDA(call)                                                                                   \
+    do {                                                                                                 \
+        cudaError_t e__ = (call);                                                                        \
+        if (e__ != cudaSuccess) {                                                                        \
+            ctx->err = std::string(#call) + ": " + cudaGetErrorString(e__) + " (" + __FILE__ + ":" +     \
+                       std::to_string(__LINE__) + ")";                                                   \
+            return SVO_ERR_CUDA;                                                                         \
+        }                                                                                                \
+    } while (0)
+
+#define SVO_FAIL(code, msg)  \
+    do {                     \
+        ctx->err = (msg);    \
+        return (code);       \
+    } while (0)
+
+inline ArenaView make_view(const PyramidArena& a)
+{
+    ArenaView v{};
+    for (int l = 0; l < a.levels; l++) {
+        v.img[l]          = a.img[l];
+        v.grad[l]         = a.grad[l];
+        v.w[l]            = a.geom[l].w;
+        v.h[l]            = a.geom[l].h;
+        v.pitch[l]        = a.geom[l].pitch;
+        v.plane_stride[l] = a.geom[l].plane_stride;
+    }
+    return v;
+}
+
+// kernel launchers (defined in the .cu files)
+svo_status launch_pyramid_build(svo_ctx* ctx, int first_slot, int n);
+svo_status launch_grid_select(svo_ctx* ctx, int slot, int cell, uint32_t thr, int rows, int cols);
+svo_status launch_sparse_align(svo_ctx* ctx);
+svo_status launch_feature_align(svo_ctx* ctx);
+size_t sparse_align_smem_bytes(int nthreads, int max_features, int patch_area);

@@ -1,0 +1,183 @@
+// math.cuh -- small double-precision device helpers: SE3 (Sophus convention), pivoted LDLT.
+#pragma once
+#include <cuda_runtime.h>
+#include <math.h>
+
+namespace svo {
+
+struct Pose {      // world -> camera, quaternion x y z w + translation
+    double q[4];
+    double t[3];
+};
+
+__device__ __forceinline__ void cross3(const double a[3], const double b[3], double c[3])
+{
+    c[0] = a[1] * b[2] - a[2] * b[1];
+    c[1] = a[2] * b[0] - a[0] * b[2];
+    c[2] = a[0] * b[1] - a[1] * b[0];
+}
+
+// v + w*uv + qv x uv, uv = 2 qv x v
+__device__ __forceinline__ void quat_rotate(const double q[4], const double v[3], double out[3])
+{
+    double uv[3], c2[3];
+    cross3(q, v, uv);
+    uv[0] *= 2.0;
+    uv[1] *= 2.0;
+    uv[2] *= 2.0;
+    cross3(q, uv, c2);
+#pragma unroll
+    for (int i = 0; i < 3; i++) out[i] = v[i] + q[3] * uv[i] + c2[i];
+}
+
+__device__ __forceinline__ void quat_to_R(const double q[4], double R[9])
+{
+    const double x = q[0], y = q[1], z = q[2], w = q[3];
+    R[0] = 1 - 2 * (y * y + z * z);
+    R[1] = 2 * (x * y - z * w);
+    R[2] = 2 * (x * z + y * w);
+    R[3] = 2 * (x * y + z * w);
+    R[4] = 1 - 2 * (x * x + z * z);
+    R[5] = 2 * (y * z - x * w);
+    R[6] = 2 * (x * z - y * w);
+    R[7] = 2 * (y * z + x * w);
+    R[8] = 1 - 2 * (x * x + y * y);
+}
+
+// pose <- pose * exp(-dx);  dx = (upsilon, omega)   [ImageAlignment::update, src/image_alignment.cpp:372-380]
+__device__ inline void pose_update_right_exp_neg(Pose& p, const double dx[6])
+{
+    double ups[3] = {-dx[0], -dx[1], -dx[2]};
+    double om[3]  = {-dx[3], -dx[4], -dx[5]};
+    const double th2 = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
+    const double th  = sqrt(th2);
+    double imag, real, a, b;
+    if (th2 < 1e-20) {
+        const double th4 = th2 * th2;
+        imag = 0.5 - th2 / 48.0 + th4 / 3840.0;
+        real = 1.0 - th2 / 8.0 + th4 / 384.0;
+    } else {
+        double s, c;
+        sincos(0.5 * th, &s, &c);
+        imag = s / th;
+        real = c;
+    }
+    if (th < 1e-10) {
+        a = 0.5;
+        b = 1.0 / 6.0;
+    } else {
+        double s, c;
+        sincos(th, &s, &c);
+        a = (1.0 - c) / th2;
+        b = (th - s) / (th2 * th);
+    }
+    double eq[4] = {imag * om[0], imag * om[1], imag * om[2], real};
+    double c1[3], c2[3], et[3];
+    cross3(om, ups, c1);
+    cross3(om, c1, c2);
+#pragma unroll
+    for (int i = 0; i < 3; i++) et[i] = ups[i] + a * c1[i] + b * c2[i];
+    // translation: t + R(q) * et
+    double rt[3];
+    quat_rotate(p.q, et, rt);
+#pragma unroll
+    for (int i = 0; i < 3; i++) p.t[i] += rt[i];
+    // rotation: q * eq, renormalised
+    const double ax = p.q[0], ay = p.q[1], az = p.q[2], aw = p.q[3];
+    double r[4];
+    r[0] = aw * eq[0] + ax * eq[3] + ay * eq[2] - az * eq[1];
+    r[1] = aw * eq[1] + ay * eq[3] + az * eq[0] - ax * eq[2];
+    r[2] = aw * eq[2] + az * eq[3] + ax * eq[1] - ay * eq[0];
+    r[3] = aw * eq[3] - ax * eq[0] - ay * eq[1] - az * eq[2];
+    const double n = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3]);
+#pragma unroll
+    for (int i = 0; i < 4; i++) p.q[i] = r[i] / n;
+}
+
+// inverse transform of a point: R^T (p - t)
+__device__ __forceinline__ void pose_inv_act(const Pose& T, const double p[3], double out[3])
+{
+    double qi[4] = {-T.q[0], -T.q[1], -T.q[2], T.q[3]};
+    double d[3]  = {p[0] - T.t[0], p[1] - T.t[1], p[2] - T.t[2]};
+    quat_rotate(qi, d, out);
+}
+
+// camera centre in world: -R^T t  (Frame::cameraInWorld, src/frame.cpp:116-120)
+__device__ __forceinline__ void pose_camera_in_world(const Pose& T, double C[3])
+{
+    double qi[4] = {-T.q[0], -T.q[1], -T.q[2], T.q[3]};
+    double r[3];
+    quat_rotate(qi, T.t, r);
+    C[0] = -r[0];
+    C[1] = -r[1];
+    C[2] = -r[2];
+}
+
+// LDLT with symmetric pivoting on the largest |diagonal| and the D^-1 rule of Eigen's solve
+// (pivots not above the smallest normal double give 0).  A: n x n row-major (n <= 6), destroyed.
+template <int N>
+__device__ inline void ldlt_solve(double* A, const double* b, double* x)
+{
+    int perm[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) perm[i] = i;
+    for (int k = 0; k < N; k++) {
+        int piv    = k;
+        double big = fabs(A[k * N + k]);
+        for (int i = k + 1; i < N; i++) {
+            const double v = fabs(A[i * N + i]);
+            if (v > big) {
+                big = v;
+                piv = i;
+            }
+        }
+        if (piv != k) {
+            for (int j = 0; j < N; j++) {
+                const double t = A[k * N + j];
+                A[k * N + j]   = A[piv * N + j];
+                A[piv * N + j] = t;
+            }
+            for (int j = 0; j < N; j++) {
+                const double t = A[j * N + k];
+                A[j * N + k]   = A[j * N + piv];
+                A[j * N + piv] = t;
+            }
+            const int t = perm[k];
+            perm[k]     = perm[piv];
+            perm[piv]   = t;
+        }
+        double dk = A[k * N + k];
+        for (int j = 0; j < k; j++) dk -= A[k * N + j] * A[k * N + j] * A[j * N + j];
+        A[k * N + k] = dk;
+        for (int i = k + 1; i < N; i++) {
+            double s = A[i * N + k];
+            for (int j = 0; j < k; j++) s -= A[i * N + j] * A[k * N + j] * A[j * N + j];
+            A[i * N + k] = (fabs(dk) > 0.0) ? s / dk : s;
+        }
+    }
+    double y[N];
+    for (int i = 0; i < N; i++) y[i] = b[perm[i]];
+    for (int i = 0; i < N; i++)
+        for (int j = 0; j < i; j++) y[i] -= A[i * N + j] * y[j];
+    for (int i = 0; i < N; i++) y[i] = (fabs(A[i * N + i]) > 2.2250738585072014e-308) ? y[i] / A[i * N + i] : 0.0;
+    for (int i = N - 1; i >= 0; i--)
+        for (int j = i + 1; j < N; j++) y[i] -= A[j * N + i] * y[j];
+    for (int i = 0; i < N; i++) x[perm[i]] = y[i];
+}
+
+// Optimizer::updateParameters, Nielsen branch (src/optimizer.cpp:449-466)
+__device__ __forceinline__ bool nielsen_update(double pre, double cur, double& lambda, double& nu)
+{
+    const double rho = pre - cur;
+    if (rho > 0.0) {
+        const double t = 2.0 * rho - 1.0;
+        lambda *= fmax(1.0 / 3.0, 1.0 - t * t * t);
+        nu = 2.0;
+        return true;
+    }
+    lambda *= nu;
+    nu *= 2.0;
+    return false;
+}
+
+}  // namespace svo
