@@ -1,0 +1,363 @@
+#!/usr/bin/env python
+"""bench.py -- sparse image alignment (ImageAlignment::align) throughput on synthetic KITTI-shaped frame pairs.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]            the CUDA path (libsvo_b200.so through the C ABI)
+  python bench.py --impl reference [...]                         the reference's algorithm on the host cores
+                                                                 (the oracle port: the reference itself cannot be
+                                                                 compiled in this image)
+
+Workload (BASELINE.json configs[3]/[4], metric "frame-pairs/sec (sparse align, 500 feat)"): every GPU owns
+`--pairs` (1,024) independent 1241x376 frame pairs with 500 grid-argmax features each, 4-level pyramids, 5x5
+patches, Gauss-Newton with at most 30 iterations per level (weak scaling: 8 GPUs = 8,192 pairs).  A step is one
+pass of the hot path over the whole batch:
+  value  -- pyramids, jobs and features resident in HBM; the step is the alignment launch (+ the final pose gather
+            when N > 1); timed with CUDA events on the launching stream.
+  e2e    -- the same through the C-ABI calls a host makes per frame, from HOST buffers: upload of every pair's new
+            frame from pinned memory + pyramid build + svo_sparse_align (jobs/features H2D, kernel, results D2H).
+Prints ONE JSON line on rank 0.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "frame_pairs_per_sec_sparse_align_500feat"
+UNIT = "pairs/s"
+PATCH, LEVELS = 5, 4
+MODES = {"gn": 2, "lm": 1, "faithful": 0}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--pairs", type=int, default=1024, help="frame pairs per GPU")
+    ap.add_argument("--features", type=int, default=500)
+    ap.add_argument("--mode", default="gn", choices=sorted(MODES))
+    ap.add_argument("--max-iter", type=int, default=30)
+    ap.add_argument("--cpu-sample", type=int, default=256, help="pairs in the CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def workload_name(a):
+    return ("%d independent 1241x376 frame pairs per GPU, %d features (grid argmax, cell %d), %d-level pyramid, "
+            "%dx%d patches, %s <= %d iterations/level" % (a.pairs, a.features, 30 if a.features <= 500 else 20, LEVELS,
+                                                          PATCH, PATCH, a.mode.upper(), a.max_iter))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on all host threads
+# ------------------------------------------------------------------------------------------------------------
+def cpu_pairs_per_sec(batch, a, n_threads, repeats=1):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle as orc
+    n = len(batch["ref"])
+    jobs = []
+    ident = np.array([0, 0, 0, 1, 0, 0, 0], dtype=np.float64)
+    t0 = time.perf_counter()
+    pyr = [(orc.build_pyramid(batch["ref"][i], LEVELS)[0], orc.build_pyramid(batch["cur"][i], LEVELS)[0]) for i in range(n)]
+    t_pyr = time.perf_counter() - t0
+    for i in range(n):
+        o, m = int(batch["feat_offset"][i]), int(batch["n_feat"][i])
+        jobs.append(dict(ref_pyr=pyr[i][0], kf_pyr=pyr[i][0], cur_pyr=pyr[i][1], feats=batch["feats"][o:o + m], n_ref=m,
+                         n_kf=0, T_ref=ident, T_kf=ident, T_cur=ident))
+    best = None
+    evals = 0
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        T, rmse, st, ev = orc.sparse_align_batch(jobs, batch["w"], batch["h"], batch["K"], n_threads, patch_size=PATCH,
+                                                 max_level=LEVELS - 1, mode=MODES[a.mode], max_iter=a.max_iter)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+        evals = int(ev.sum())
+    return n / best, best, evals, t_pyr, T
+
+
+def run_reference(a, rank):
+    if rank != 0:
+        return
+    pkg = importlib.import_module("semi-direct-visual-odometry_b200")
+    threads = os.cpu_count() or 1
+    sample = max(threads, min(a.cpu_sample, a.pairs))
+    batch = pkg.synth.make_batch(sample, a.features)
+    for _ in range(a.warmup):
+        cpu_pairs_per_sec(dict(batch, ref=batch["ref"][:threads], cur=batch["cur"][:threads],
+                               n_feat=batch["n_feat"][:threads], feat_offset=batch["feat_offset"][:threads]), a, threads)
+    t_total, n_total = 0.0, 0
+    for _ in range(a.steps):
+        pps, dt, _, _, _ = cpu_pairs_per_sec(batch, a, threads)
+        t_total += dt
+        n_total += sample
+    value = n_total / t_total
+    desc = "%d of the %d pairs per step, oracle port (g++ -O3), one pair per task on %d threads" % (sample, a.pairs, threads)
+    print(json.dumps({
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
+        "warmup": a.warmup, "ms_per_step": 1e3 * t_total / a.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(a), "sample_pairs_per_step": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }))
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.rows, self.proc = [], None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def stop(self, t0, t1):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for t, line in self.rows:
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                clk, mxv = float(f[0]), float(f[1])
+            except ValueError:
+                continue
+            mx = mxv
+            if t0 <= t <= t1 + 0.1:
+                sm.append(clk)
+                for nme, v in zip(names, f[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+class DevArray:
+    """Minimal __cuda_array_interface__ view of a raw device pointer (for torch.as_tensor)."""
+
+    def __init__(self, ptr, nbytes):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (ptr, False), "version": 2}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# GPU arm
+# ------------------------------------------------------------------------------------------------------------
+def run_b200(a, rank, world):
+    import torch
+    import torch.distributed as dist
+    pkg = importlib.import_module("semi-direct-visual-odometry_b200")
+    capi, synth = pkg.capi, pkg.synth
+    pkg.load()  # fails loudly if the CUDA library is missing: there is no fallback path
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    n = a.pairs
+    batch = synth.make_batch(n, a.features, first_index=rank * n)
+    F = int(batch["n_feat"].max())
+    stream = torch.cuda.Stream()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+
+    with torch.cuda.stream(stream):
+        ctx = pkg.Context(batch["w"], batch["h"], batch["K"], levels=LEVELS, max_frames=2 * n, max_jobs=n,
+                          max_features=F, max_fa_items=16, device=local, stream=stream.cuda_stream)
+        h, w = batch["h"], batch["w"]
+        # pinned host frames: refs [0, n), curs [n, 2n) -- slot i holds frame i
+        pin = ctx.pinned(2 * n * h * w)
+        frames = pin.array.reshape(2 * n, h, w)
+        frames[:n], frames[n:] = batch["ref"], batch["cur"]
+        jobs = capi.make_jobs(n)
+        ident = np.array([0, 0, 0, 1, 0, 0, 0], dtype=np.float64)
+        jobs["ref_slot"], jobs["kf_slot"], jobs["cur_slot"] = np.arange(n), np.arange(n), np.arange(n) + n
+        jobs["n_ref"], jobs["n_kf"], jobs["feat_offset"] = batch["n_feat"], 0, batch["feat_offset"]
+        jobs["T_ref"], jobs["T_kf"], jobs["T_cur"] = ident, ident, ident
+        feats = batch["feats"]
+        kw = dict(patch_size=PATCH, min_level=0, max_level=LEVELS - 1, mode=MODES[a.mode], max_iter=a.max_iter)
+
+        # ---- residency + one stats pass (untimed): algorithmic bytes and a sanity check of the result ----
+        ctx.upload(0, frames)
+        res, stats = ctx.sparse_align(jobs, feats, want_stats=True, **kw)
+        ctx.sync()
+        rot_err = np.array([synth.rotation_angle(res[i]["T_cur"], batch["T_true"][i]) for i in range(n)])
+        tr_err = np.abs(res["T_cur"][:, 4:] - batch["T_true"][:, 4:]).max(axis=1)
+        nvis = stats["n_px"].astype(np.float64) / (PATCH * PATCH)               # visible features per level
+        ev = stats["evaluations"].astype(np.float64)
+        alg_bytes = float((nvis * ((PATCH + 3) ** 2 + ev * (PATCH + 1) ** 2)).sum() + 32.0 * batch["n_feat"].sum()
+                          + 256.0 * LEVELS * n)                                   # SURVEY 8(d) formula, per launch
+        evals_total = int(res["evaluations"].sum())
+
+        gather_buf = None
+        if world > 1:
+            res_dev = torch.as_tensor(DevArray(ctx.results_device_ptr, n * capi.ALIGN_RESULT_DTYPE.itemsize), device="cuda")
+            gather_buf = [torch.empty_like(res_dev) for _ in range(world)] if rank == 0 else None
+
+        def barrier():
+            if world > 1:
+                dist.barrier()
+            torch.cuda.synchronize()
+
+        # ---- value: inputs resident, step = launch (+ final pose gather) ----
+        ctx.sparse_align_stage(jobs, feats, **kw)
+        ctx.sparse_align_h2d()
+
+        def step_value():
+            ctx.sparse_align_launch()
+            if world > 1:
+                dist.gather(res_dev, gather_buf, dst=0)
+
+        for _ in range(a.warmup):
+            step_value()
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        l0 = ctx.launches
+        ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
+        ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(a.steps)]
+        tw0 = time.perf_counter()
+        t_start, t_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t_start.record(stream)
+        for k in range(a.steps):
+            ev0[k].record(stream)
+            ctx.sparse_align_launch()
+            ev1[k].record(stream)
+            if world > 1:
+                dist.gather(res_dev, gather_buf, dst=0)
+        t_end.record(stream)
+        barrier()
+        tw1 = time.perf_counter()
+        launches = ctx.launches - l0
+        ms_total = t_start.elapsed_time(t_end)
+        kern_ms = float(np.mean([ev0[k].elapsed_time(ev1[k]) for k in range(a.steps)]))
+        clocks = sampler.stop(tw0, tw1) if sampler else None
+
+        # ---- single-pair latency (the "us / frame pair" of the metric): one job, resident ----
+        lat_us = None
+        if rank == 0:
+            ctx.sparse_align_stage(jobs[:1], feats[:int(batch["n_feat"][0])], **kw)
+            ctx.sparse_align_h2d()
+            for _ in range(5):
+                ctx.sparse_align_launch()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            e0.record(stream)
+            for _ in range(50):
+                ctx.sparse_align_launch()
+            e1.record(stream)
+            torch.cuda.synchronize()
+            lat_us = 1e3 * e0.elapsed_time(e1) / 50
+
+        # ---- e2e: host buffers through the C ABI, copies inside the timed region ----
+        def step_e2e():
+            ctx.upload(n, frames[n:])                       # every pair's new frame: pinned H2D + pyramid build
+            return ctx.sparse_align(jobs, feats, want_stats=False, **kw)[0]   # jobs/feats H2D, kernel, results D2H
+
+        for _ in range(min(a.warmup, 3)):
+            step_e2e()
+        barrier()
+        e_steps = max(1, min(a.steps, 5))
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record(stream)
+        for _ in range(e_steps):
+            r_e2e = step_e2e()
+        s1.record(stream)
+        barrier()
+        e2e_ms = s0.elapsed_time(s1)
+        h2d = int(n * h * w + jobs.nbytes + feats.nbytes)
+        d2h = int(n * capi.ALIGN_RESULT_DTYPE.itemsize)
+        assert np.array_equal(r_e2e["T_cur"], res["T_cur"]), "e2e result differs from the resident run"
+
+        tmax = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        ms_total, e2e_ms = float(tmax[0]), float(tmax[1])
+        ctx.sync()
+        pin.free()
+        ctx.close()
+
+    if rank == 0:
+        value = world * n * a.steps / (ms_total * 1e-3)
+        e2e_value = world * n * e_steps / (e2e_ms * 1e-3)
+        achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
+        out = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 (FP64 pose/warp/solve, FP32 pixels, FP64 accumulation over features)", "data": "synthetic",
+            "config": {"workload": workload_name(a), "pairs_total": world * n,
+                       "l2": "inputs larger than L2: %.2f GB of pyramids per GPU, every pair reads its own frames"
+                             % (2 * n * 620e3 / 1e9),
+                       "multi_gpu": "contiguous shards of pairs, no collective on the alignment path, one NCCL gather "
+                                    "of 80 B/pair per step" if world > 1 else "single GPU"},
+            "us_per_pair": 1e6 / value,
+            "latency_us_single_pair": lat_us,
+            "evaluations_per_pair": evals_total / n,
+            "accuracy": {"median_rot_err_rad": float(np.median(rot_err)), "median_trans_err_m": float(np.median(tr_err)),
+                         "pairs_within_1e-3rad_1e-2m": float(np.mean((rot_err < 1e-3) & (tr_err < 1e-2)))},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / e_steps, "steps": e_steps,
+                    "what": "svo_frames_upload(cur frames, pinned) + pyramid build + svo_sparse_align (H2D, kernel, D2H)"},
+            "roofline": {"bound": "hbm", "kernel": "k_sparse_align", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+                         "frac": achieved / hbm_peak, "peak_source": peak_src, "traffic": None,
+                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms,
+                         "note": "gather-bound sparse reduction, latency-limited: see DESIGN.md and profiles/"},
+        }
+        if world == 1 and not a.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sample = min(a.cpu_sample, n)
+            sub = {k: (v[:sample] if k in ("ref", "cur", "n_feat", "feat_offset", "T_true") else v) for k, v in batch.items()}
+            pps, dt, cev, t_pyr, Tc = cpu_pairs_per_sec(sub, a, threads)
+            dq = np.abs(Tc - res["T_cur"][:sample])
+            out["cpu_baseline"] = {"value": pps, "unit": UNIT, "cores": threads, "kind": "port",
+                                   "sample": "first %d of the %d pairs, oracle port (g++ -O3), one pair per task on %d "
+                                             "threads, %.2f s; pyramids prebuilt (%.2f s)" % (sample, n, threads, dt, t_pyr),
+                                   "max_pose_param_diff_vs_gpu": float(dq.max())}
+        print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    a = parse()
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if a.impl == "reference":
+        run_reference(a, rank)
+    else:
+        run_b200(a, rank, world)
+
+
+if __name__ == "__main__":
+    main()

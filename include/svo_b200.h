@@ -180,6 +180,9 @@ svo_status svo_sparse_align_h2d(svo_ctx* ctx);
 svo_status svo_sparse_align_launch(svo_ctx* ctx);
 svo_status svo_sparse_align_d2h(svo_ctx* ctx);
 svo_status svo_sparse_align_fetch(svo_ctx* ctx, svo_align_result* results, svo_align_level_stats* stats);
+/* device copy of the last batch's svo_align_result records (valid once the launch has completed on the stream):
+ * what a multi-GPU caller hands to its final pose gather (ncclGather) without a host round trip */
+const void* svo_sparse_align_results_device(const svo_ctx* ctx);
 
 /* ---------------------------------------------------------------------------------------------
  * FeatureAlignment::align(refFeature, curFrame, pixelPos) (src/feature_alignment.cpp:25-62),

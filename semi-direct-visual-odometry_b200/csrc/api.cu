@@ -234,7 +234,12 @@ svo_status svo_frames_upload(svo_ctx* ctx, int first_slot, int n, const uint8_t*
     const bool pinned = cudaPointerGetAttributes(&attr, imgs) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
     if (pinned) {
-        // caller's buffer is page-locked (svo_host_alloc): DMA straight from it
+        // caller's buffer is page-locked (svo_host_alloc): DMA straight from it.  When both sides are dense stacks
+        // of frames the whole batch is ONE 2D copy of n*h rows.
+        if (g.plane_stride == (int64_t)g.pitch * g.h && (n == 1 || frame_stride == (int64_t)pitch * g.h))
+            SVO_CUDA(cudaMemcpy2DAsync(ctx->arena.img[0] + (int64_t)first_slot * g.plane_stride, g.pitch, imgs, pitch, g.w,
+                                       (size_t)g.h * n, cudaMemcpyHostToDevice, ctx->stream));
+        else
         for (int i = 0; i < n; i++)
             SVO_CUDA(cudaMemcpy2DAsync(ctx->arena.img[0] + (int64_t)(first_slot + i) * g.plane_stride, g.pitch,
                                        imgs + (int64_t)i * frame_stride, pitch, g.w, g.h, cudaMemcpyHostToDevice,
@@ -415,6 +420,8 @@ svo_status svo_sparse_align_fetch(svo_ctx* ctx, svo_align_result* results, svo_a
     }
     return SVO_OK;
 }
+
+const void* svo_sparse_align_results_device(const svo_ctx* ctx) { return ctx ? ctx->d_results : nullptr; }
 
 svo_status svo_sparse_align(svo_ctx* ctx, const svo_align_job* jobs, int n_jobs, const svo_align_feature* feats, int n_feats,
                             const svo_align_params* prm, svo_align_result* results, svo_align_level_stats* stats)

@@ -5,6 +5,8 @@ reference frame and, through the exact plane-induced homography of a known motio
 current frame.  Camera: KITTI intrinsics (reference tree: resource/kitti.yaml:7-8) on
 1241x376 (config/config.json:10-11).  Seeds follow SURVEY.md 8(d): base 20261018 + pair index.
 """
+import os
+
 import numpy as np
 
 KITTI_K = (721.5377, 721.5377, 609.5593, 172.8540)
@@ -212,3 +214,60 @@ def make_pair(index=0, n_features=500, cell=30, thr=50, T_ref=None, n_kf=0, base
             fk["has_point"][i] = 1
         out.update(kf=kf, T_kf=T_kf, n_kf=len(fk), feats=np.concatenate([feats_ref, fk]))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# batched workloads (configs 4 and 5): many independent pairs, generated in parallel on the host
+# ---------------------------------------------------------------------------------------------
+GROUP = 32          # pairs that share one (larger) texture, each at its own crop
+GROUP_SPREAD = 256  # the shared texture is this much larger than a frame in both directions
+
+
+def _make_group(args):
+    """Worker: pairs [first, first + count) of a batch.  Every pair sees its own crop of the group texture,
+    its own motion and the grid-argmax features of its own reference frame (cell raster order)."""
+    first, count, n_features, cell, thr, base_seed, w, h, K = args
+    rng = np.random.default_rng(base_seed + first)
+    tex = make_texture(rng, w + GROUP_SPREAD, h + GROUP_SPREAD)
+    out = []
+    for i in range(count):
+        prng = np.random.default_rng(base_seed + first + i)
+        ox, oy = (int(v) for v in prng.integers(0, GROUP_SPREAD, 2))
+        sub = tex[oy:oy + h + 2 * MARGIN, ox:ox + w + 2 * MARGIN]
+        T_cur_ref = random_motion(prng)
+        ref = np.clip(np.rint(sub[MARGIN:MARGIN + h, MARGIN:MARGIN + w]), 0, 255).astype(np.uint8)  # identity view
+        cur = render_plane(sub, K, T_cur_ref, w, h)
+        sel = grid_argmax_np(abs_gradient_np(ref), cell, thr)
+        n = min(n_features, len(sel))
+        feats = make_features(sel[:n, :2].astype(np.float64), K, IDENTITY)
+        out.append((ref, cur, feats, T_cur_ref))
+    return first, out
+
+
+def make_batch(n_pairs, n_features=500, cell=None, thr=50, base_seed=BASE_SEED, first_index=0, workers=None,
+               w=KITTI_W, h=KITTI_H, K=KITTI_K):
+    """n_pairs independent synthetic pairs (T_ref = I, prior = T_ref).  Returns dict of arrays:
+    ref, cur (n, h, w) u8; feats (concatenated records); n_feat (n,), feat_offset (n,); T_true (n, 7)."""
+    import multiprocessing as mp
+    if cell is None:
+        cell = 30 if n_features <= 500 else 20  # SURVEY 8d: cell 30 -> <= 546 features, cell 20 -> <= 1197
+    tasks = [(first_index + g, min(GROUP, n_pairs - g), n_features, cell, thr, base_seed, w, h, tuple(K))
+             for g in range(0, n_pairs, GROUP)]
+    workers = workers or min(len(tasks), os.cpu_count() or 1)
+    if workers > 1:
+        with mp.get_context("fork").Pool(workers) as pool:
+            groups = pool.map(_make_group, tasks)
+    else:
+        groups = [_make_group(t) for t in tasks]
+    ref = np.empty((n_pairs, h, w), np.uint8)
+    cur = np.empty((n_pairs, h, w), np.uint8)
+    T_true = np.empty((n_pairs, 7))
+    feats, n_feat = [], np.zeros(n_pairs, np.int32)
+    for first, items in sorted(groups, key=lambda g: g[0]):
+        for i, (r, c, f, T) in enumerate(items):
+            k = first - first_index + i
+            ref[k], cur[k], T_true[k], n_feat[k] = r, c, T, len(f)
+            feats.append(f)
+    offs = np.concatenate([[0], np.cumsum(n_feat)[:-1]]).astype(np.int32)
+    return dict(ref=ref, cur=cur, feats=np.concatenate(feats), n_feat=n_feat, feat_offset=offs, T_true=T_true,
+                K=np.array(K), w=w, h=h, cell=cell)
