@@ -1,0 +1,3 @@
+// pinhole_camera.hpp -- same include name as the reference; the class lives in svo_host.hpp
+#pragma once
+#include "svo_host.hpp"

@@ -1,0 +1,460 @@
+// svo_host.hpp -- host-side C++ mirror of the reference's hot-path classes over the C ABI of libsvo_b200.so.
+//
+// Same class names, constructor arguments, method names, argument meaning and error behaviour as the reference
+// (citations relative to the reference tree), so System / Map / Estimator code compiles against them unchanged
+// apart from the value types (svo_types.hpp stands in for Eigen / Sophus / cv::Mat, which this image lacks):
+//   ImagePyramid      include/image_pyramid.hpp:23-149, src/image_pyramid.cpp
+//   PinholeCamera     include/pinhole_camera.hpp, src/pinhole_camera.cpp:50-101,123-176 (no-distortion branch)
+//   Point, Feature    include/point.hpp:26-40, include/feature.hpp:27-38, src/feature.cpp:6-45
+//   Frame             include/frame.hpp:82-205, src/frame.cpp
+//   FeatureSelection  include/feature_selection.hpp:35-86, src/feature_selection.cpp:19-25,91-146,269-287
+//   ImageAlignment    include/image_alignment.hpp:15-73, src/image_alignment.cpp:25-67
+//   FeatureAlignment  include/feature_alignment.hpp:15-44, src/feature_alignment.cpp:25-62
+// All arithmetic of the hot path runs on the GPU; these classes only marshal.  No CPU fallback exists.
+#pragma once
+#include <cmath>
+#include <cstdint>
+#include <limits>
+#include <memory>
+#include <stdexcept>
+#include <vector>
+
+#include "svo_device.hpp"
+#include "svo_types.hpp"
+
+namespace svo {
+
+// ------------------------------------------------------------------------------------------------------------
+class PinholeCamera final
+{
+public:
+    explicit PinholeCamera(int32_t width, int32_t height, double fx, double fy, double cx, double cy, double d0 = 0,
+                           double d1 = 0, double d2 = 0, double d3 = 0, double d4 = 0)
+        : m_width(width), m_height(height), m_fx(fx), m_fy(fy), m_cx(cx), m_cy(cy)
+    {
+        // the distortion branch (src/pinhole_camera.cpp:58-72,90-99) is out of scope: KITTI / denso have d = 0
+        if (d0 != 0 || d1 != 0 || d2 != 0 || d3 != 0 || d4 != 0)
+            throw std::invalid_argument("PinholeCamera: lens distortion is not supported on the GPU path");
+    }
+    PinholeCamera(const PinholeCamera&)            = delete;
+    PinholeCamera& operator=(const PinholeCamera&) = delete;
+
+    Vec2 project2d(double x, double y, double z) const { return Vec2(m_fx * (x / z) + m_cx, m_fy * (y / z) + m_cy); }
+    Vec2 project2d(const Vec3& p) const { return project2d(p.x(), p.y(), p.z()); }
+    Vec3 inverseProject2d(double x, double y) const { return Vec3((x - m_cx) / m_fx, (y - m_cy) / m_fy, 1.0).normalized(); }
+    Vec3 inverseProject2d(const Vec2& p) const { return inverseProject2d(p.x(), p.y()); }
+    double fx() const { return m_fx; }
+    double fy() const { return m_fy; }
+    double cx() const { return m_cx; }
+    double cy() const { return m_cy; }
+    int32_t width() const { return m_width; }
+    int32_t height() const { return m_height; }
+    bool isInFrame(const Vec2& p, double boundary = 0.0) const
+    {
+        return p.x() >= boundary && p.y() >= boundary && p.x() < m_width - boundary && p.y() < m_height - boundary;
+    }
+
+private:
+    int32_t m_width, m_height;
+    double m_fx, m_fy, m_cx, m_cy;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// ImagePyramid: the stacks live on the device in one frame slot; cv::Mat-like host copies are fetched lazily.
+class ImagePyramid final
+{
+public:
+    explicit ImagePyramid(std::size_t maxImagePyramid, std::shared_ptr<Device> dev = Device::current())
+        : m_dev(std::move(dev))
+    {
+        m_vecImages.reserve(maxImagePyramid);
+        m_vecGradientImages.reserve(maxImagePyramid);
+    }
+    explicit ImagePyramid(const Mat8& baseImage, std::size_t maxImagePyramid, std::shared_ptr<Device> dev = Device::current())
+        : ImagePyramid(maxImagePyramid, std::move(dev))
+    {
+        createImagePyramid(baseImage, maxImagePyramid);
+    }
+    ImagePyramid(const ImagePyramid&)            = delete;
+    ImagePyramid& operator=(const ImagePyramid&) = delete;
+    ~ImagePyramid() { clear(); }
+
+    // src/image_pyramid.cpp:36-52 -- one upload, abs-gradient + pyrDown kernels for both stacks (asynchronous)
+    void createImagePyramid(const Mat8& baseImage, std::size_t maxPyramidLevel)
+    {
+        if (!m_dev) throw std::runtime_error("ImagePyramid: no svo::Device (construct one and set Device::current())");
+        if ((int)maxPyramidLevel > m_dev->levels()) throw std::invalid_argument("ImagePyramid: more levels than the device arena");
+        clear();
+        m_slot            = m_dev->acquireSlot();
+        m_levels          = maxPyramidLevel;
+        m_baseImageWidth  = baseImage.cols;
+        m_baseImageHeight = baseImage.rows;
+        m_dev->check(svo_frames_upload(m_dev->ctx(), m_slot, 1, baseImage.ptr(), baseImage.cols, 0), "svo_frames_upload");
+        m_vecImages.assign(maxPyramidLevel, Mat8());
+        m_vecGradientImages.assign(maxPyramidLevel, Mat8());
+        m_vecImages[0] = baseImage;  // level 0 shares the caller's buffer, as the reference (no clone)
+    }
+    const Mat8& getImageAtLevel(std::size_t level) const { return fetch(level, 0); }
+    const Mat8& getGradientAtLevel(std::size_t level) const { return fetch(level, 1); }
+    const Mat8& getBaseImage() const { return fetch(0, 0); }
+    const Mat8& getBaseGradientImage() const { return fetch(0, 1); }
+    const std::vector<Mat8>& getAllImages() const
+    {
+        for (std::size_t l = 0; l < m_levels; l++) fetch(l, 0);
+        return m_vecImages;
+    }
+    std::size_t getSizeImagePyramid() const { return m_vecImages.size(); }
+    Size getImageSizeAtLevel(std::size_t level) const
+    {
+        if (level >= m_levels) return Size(0, 0);  // src/image_pyramid.cpp:113-119
+        int w = 0, h = 0;
+        svo_level_dims(m_dev->ctx(), (int)level, &w, &h, nullptr);
+        return Size(w, h);
+    }
+    Size getBaseImageSize() const { return Size((int)m_baseImageWidth, (int)m_baseImageHeight); }
+    void clear()
+    {
+        if (m_slot >= 0 && m_dev) {
+            svo_sync(m_dev->ctx());
+            m_dev->releaseSlot(m_slot);
+        }
+        m_slot   = -1;
+        m_levels = 0;
+        m_vecImages.clear();
+        m_vecGradientImages.clear();
+    }
+    int slot() const { return m_slot; }  // device handle of this pyramid (what the alignment calls take)
+    const std::shared_ptr<Device>& device() const { return m_dev; }
+
+private:
+    const Mat8& fetch(std::size_t level, int which) const
+    {
+        if (level >= m_levels) throw std::out_of_range("ImagePyramid: level out of range");
+        Mat8& m = which ? m_vecGradientImages[level] : m_vecImages[level];
+        if (m.empty()) {
+            const Size s = getImageSizeAtLevel(level);
+            m            = Mat8(s.height, s.width);
+            m_dev->check(svo_frame_download(m_dev->ctx(), m_slot, (int)level, which, m.ptr(), s.width), "svo_frame_download");
+        }
+        return m;
+    }
+    std::shared_ptr<Device> m_dev;
+    int m_slot                    = -1;
+    std::size_t m_levels          = 0;
+    std::size_t m_baseImageWidth  = 0;
+    std::size_t m_baseImageHeight = 0;
+    mutable std::vector<Mat8> m_vecImages;
+    mutable std::vector<Mat8> m_vecGradientImages;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+class Frame;
+class Feature;
+
+class Point final
+{
+public:
+    explicit Point(const Vec3& point3D) : m_id(counter()++), m_position(point3D) {}
+    uint32_t m_id;
+    Vec3 m_position;
+    std::vector<std::shared_ptr<Feature>> m_features;
+
+private:
+    static uint32_t& counter()
+    {
+        static uint32_t c = 0;
+        return c;
+    }
+};
+
+class Frame final
+{
+public:
+    // include/frame.hpp:82-86; throws "Image Corrupted" as src/frame.cpp:20-24
+    explicit Frame(const std::shared_ptr<PinholeCamera>& camera, const Mat8& img, uint32_t maxImagePyramid, uint64_t timestamp,
+                   const std::shared_ptr<Frame> lastKeyframe, std::shared_ptr<Device> dev = Device::current())
+        : m_id(counter()++), m_camera(camera), m_imagePyramid(maxImagePyramid, std::move(dev)), m_keyFrame(false),
+          m_timestamp(timestamp), m_lastKeyframe(lastKeyframe)
+    {
+        if (img.empty() || img.cols != camera->width() || img.rows != camera->height())
+            throw std::runtime_error("Image Corrupted");
+        m_imagePyramid.createImagePyramid(img, maxImagePyramid);
+    }
+    Frame(const Frame&)            = delete;
+    Frame& operator=(const Frame&) = delete;
+
+    void setKeyframe() { m_keyFrame = true; }
+    bool isKeyframe() const { return m_keyFrame; }
+    void addFeature(std::shared_ptr<Feature>& feature) { m_features.emplace_back(feature); }
+    std::size_t numberObservation() const { return m_features.size(); }
+    uint32_t numberObservationWithPoints() const;
+    Vec3 world2camera(const Vec3& p) const { return m_absPose * p; }
+    Vec3 camera2world(const Vec3& p) const { return m_absPose.inverse() * p; }           // src/frame.cpp:94-97
+    Vec2 camera2image(const Vec3& p) const { return m_camera->project2d(p); }            // :99-102
+    Vec2 world2image(const Vec3& p) const { return camera2image(world2camera(p)); }
+    Vec3 image2camera(const Vec2& px, double depth) const { return m_camera->inverseProject2d(px) * depth; }
+    Vec3 image2world(const Vec2& px, double depth) const { return camera2world(image2camera(px, depth)); }
+    Vec3 cameraInWorld() const { return m_absPose.inverse().translation(); }  // -R^T t, src/frame.cpp:116-120
+    bool isVisible(const Vec3& p) const
+    {
+        const Vec3 c = world2camera(p);
+        return c.z() >= 0.0 && m_camera->isInFrame(camera2image(c));
+    }
+
+    uint64_t m_id;
+    std::shared_ptr<PinholeCamera> m_camera;
+    SE3 m_absPose;  // world -> camera, include/frame.hpp:198
+    ImagePyramid m_imagePyramid;
+    std::vector<std::shared_ptr<Feature>> m_features;
+    bool m_keyFrame;
+    uint64_t m_timestamp;
+    std::shared_ptr<Frame> m_lastKeyframe;
+
+private:
+    static uint64_t& counter()
+    {
+        static uint64_t c = 0;
+        return c;
+    }
+};
+
+class Feature final
+{
+public:
+    enum class FeatureType : uint32_t { EDGE, EDGELET, CORNER };
+    // src/feature.cpp:6-45
+    explicit Feature(const std::shared_ptr<Frame>& frame, const Vec2& pixelPosition, uint8_t level,
+                     const FeatureType& type = FeatureType::EDGE)
+        : Feature(frame, pixelPosition, 1.0, 0.0, level, type)
+    {
+    }
+    explicit Feature(const std::shared_ptr<Frame>& frame, const Vec2& pixelPosition, double gradientMagnitude,
+                     double gradientOrientation, uint8_t level, const FeatureType& type = FeatureType::EDGE)
+        : m_id(counter()++), m_frame(frame), m_type(type), m_pixelPosition(pixelPosition),
+          m_homogenous(pixelPosition.x(), pixelPosition.y(), 1.0), m_bearingVec(frame->m_camera->inverseProject2d(pixelPosition)),
+          m_gradientMagnitude(gradientMagnitude), m_gradientOrientation(gradientOrientation), m_level(level), m_point(nullptr)
+    {
+    }
+    void setPoint(std::shared_ptr<Point>& point) { m_point = point; }
+
+    uint64_t m_id;
+    std::shared_ptr<Frame> m_frame;
+    FeatureType m_type;
+    Vec2 m_pixelPosition;
+    Vec3 m_homogenous;
+    Vec3 m_bearingVec;
+    double m_gradientMagnitude;
+    double m_gradientOrientation;
+    uint8_t m_level;
+    std::shared_ptr<Point> m_point;
+
+private:
+    static uint64_t& counter()
+    {
+        static uint64_t c = 0;
+        return c;
+    }
+};
+
+inline uint32_t Frame::numberObservationWithPoints() const
+{
+    uint32_t n = 0;
+    for (const auto& f : m_features) n += f->m_point != nullptr;
+    return n;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+class FeatureSelection final
+{
+public:
+    explicit FeatureSelection(int32_t width, int32_t height, int32_t cellSize)  // src/feature_selection.cpp:19-25
+        : m_cellSize(cellSize), m_gridRows(height / cellSize + 1), m_gridCols(width / cellSize + 1),
+          m_occupancyGrid((size_t)m_gridRows * m_gridCols, false)
+    {
+    }
+    FeatureSelection(const FeatureSelection&)            = delete;
+    FeatureSelection& operator=(const FeatureSelection&) = delete;
+
+    // src/feature_selection.cpp:91-146.  Appends Features to frame->m_features in cell raster order.
+    void gradientMagnitudeByValue(std::shared_ptr<Frame>& frame, uint32_t detectionThreshold, bool useBucketing = true)
+    {
+        if (!useBucketing)  // the reference's non-bucketing branch reads the u8 image as float (:153): rejected, SURVEY 9.7
+            throw std::invalid_argument("gradientMagnitudeByValue(useBucketing=false) is not supported");
+        const auto& dev = frame->m_imagePyramid.device();
+        std::vector<uint8_t> occ(m_occupancyGrid.begin(), m_occupancyGrid.end());
+        std::vector<svo_feature_px> out(occ.size());
+        int n = 0;
+        dev->check(svo_select_grid(dev->ctx(), frame->m_imagePyramid.slot(), m_cellSize, detectionThreshold, occ.data(),
+                                   out.data(), (int)out.size(), &n), "svo_select_grid");
+        for (int i = 0; i < n; i++) {
+            auto f = std::make_shared<Feature>(frame, Vec2(out[i].x, out[i].y), (double)out[i].magnitude, 0.0, 0);
+            frame->addFeature(f);
+        }
+        m_imgGradientMagnitude = frame->m_imagePyramid.getBaseGradientImage();  // computeImageGradient, :250-267
+        resetGridOccupancy();                                                     // :145
+    }
+    void setExistingFeatures(const std::vector<std::shared_ptr<Feature>>& features)  // :269-275
+    {
+        for (const auto& f : features) setCellInGridOccupancy(f->m_pixelPosition);
+    }
+    void setCellInGridOccupancy(const Vec2& px)  // :277-281
+    {
+        m_occupancyGrid[(size_t)((int32_t)(px.y() / m_cellSize) * m_gridCols + (int32_t)(px.x() / m_cellSize))] = true;
+    }
+
+    Mat8 m_imgGradientMagnitude;
+    int32_t m_cellSize;
+    int32_t m_gridRows;
+    int32_t m_gridCols;
+    std::vector<bool> m_occupancyGrid;
+
+private:
+    void resetGridOccupancy() { std::fill(m_occupancyGrid.begin(), m_occupancyGrid.end(), false); }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+class ImageAlignment final
+{
+public:
+    // include/image_alignment.hpp:18; System passes (5, 0, 3, 6), src/system.cpp:26-27
+    explicit ImageAlignment(uint32_t patchSize, int32_t minLevel, int32_t maxLevel, uint32_t numParameters)
+        : m_patchSize(patchSize), m_halfPatchSize(patchSize / 2), m_patchArea(patchSize * patchSize), m_minLevel(minLevel),
+          m_maxLevel(maxLevel)
+    {
+        if (numParameters != 6) throw std::invalid_argument("ImageAlignment optimises an SE3 pose: numParameters must be 6");
+    }
+    ImageAlignment(const ImageAlignment&)            = delete;
+    ImageAlignment& operator=(const ImageAlignment&) = delete;
+
+    // src/image_alignment.cpp:25-67.  Mutates curFrame->m_absPose in place, returns the RMSE of the last level
+    // (0 when refFrame has no features).  refFrame->m_lastKeyframe must be non-null (the reference dereferences it).
+    double align(std::shared_ptr<Frame>& refFrame, std::shared_ptr<Frame>& curFrame)
+    {
+        if (refFrame->numberObservation() == 0) return 0;
+        const auto& lastKF = refFrame->m_lastKeyframe;
+        if (!lastKF) throw std::invalid_argument("ImageAlignment::align: refFrame->m_lastKeyframe is null");
+        const auto& dev = curFrame->m_imagePyramid.device();
+        m_feats.clear();
+        pack(refFrame->m_features);
+        pack(lastKF->m_features);
+        svo_align_job job{};
+        job.ref_slot    = refFrame->m_imagePyramid.slot();
+        job.kf_slot     = lastKF->m_imagePyramid.slot();
+        job.cur_slot    = curFrame->m_imagePyramid.slot();
+        job.n_ref       = (int32_t)refFrame->numberObservation();
+        job.n_kf        = (int32_t)lastKF->numberObservation();
+        job.feat_offset = 0;
+        refFrame->m_absPose.params(job.T_ref);
+        lastKF->m_absPose.params(job.T_kf);
+        curFrame->m_absPose.params(job.T_cur);
+        svo_align_params prm{};
+        prm.patch_size = (int32_t)m_patchSize;
+        prm.min_level  = m_minLevel;
+        prm.max_level  = m_maxLevel;
+        prm.mode       = m_mode;
+        prm.max_iter   = (int32_t)m_maxIteration;
+        svo_align_result res{};
+        m_levelStats.assign((size_t)(m_maxLevel - m_minLevel + 1), svo_align_level_stats{});
+        dev->check(svo_sparse_align(dev->ctx(), &job, 1, m_feats.data(), (int)m_feats.size(), &prm, &res, m_levelStats.data()),
+                   "svo_sparse_align");
+        curFrame->m_absPose = SE3::fromParams(res.T_cur);
+        m_status            = res.status;
+        return res.rmse;
+    }
+
+    int32_t m_mode          = SVO_LM_FAITHFUL;  // what the reference executes (one damped step per level)
+    uint32_t m_maxIteration = 20;               // Optimizer::m_maxIteration, src/optimizer.cpp:18
+    int32_t m_status        = SVO_ST_SUCCESS;   // Optimizer::Status of the last level (dropped by the reference)
+    std::vector<svo_align_level_stats> m_levelStats;
+
+private:
+    void pack(const std::vector<std::shared_ptr<Feature>>& features)
+    {
+        for (const auto& f : features) {
+            svo_align_feature a{};
+            a.px[0] = f->m_pixelPosition.x();
+            a.px[1] = f->m_pixelPosition.y();
+            for (int i = 0; i < 3; i++) a.bearing[i] = f->m_bearingVec[i];
+            a.has_point = f->m_point != nullptr;
+            if (f->m_point)
+                for (int i = 0; i < 3; i++) a.point[i] = f->m_point->m_position[i];
+            m_feats.push_back(a);
+        }
+    }
+    uint32_t m_patchSize;
+    int32_t m_halfPatchSize;
+    int32_t m_patchArea;
+    int32_t m_minLevel;
+    int32_t m_maxLevel;
+    std::vector<svo_align_feature> m_feats;
+};
+
+// ------------------------------------------------------------------------------------------------------------
+class FeatureAlignment final
+{
+public:
+    // include/feature_alignment.hpp:18; Map passes (7, 0, 3), src/map.cpp:18
+    explicit FeatureAlignment(uint32_t patchSize, int32_t level, uint32_t numParameters) : m_patchSize(patchSize), m_level(level)
+    {
+        if (level != 0) throw std::invalid_argument("FeatureAlignment runs on gradient level 0 (src/feature_alignment.cpp:69,118)");
+        if (numParameters != 3) throw std::invalid_argument("FeatureAlignment optimises (x, y, offset): numParameters must be 3");
+    }
+    FeatureAlignment(const FeatureAlignment&)            = delete;
+    FeatureAlignment& operator=(const FeatureAlignment&) = delete;
+
+    // src/feature_alignment.cpp:25-62.  pixelPos is in/out; returns the pre-step RMSE (NaN when the start is out of frame).
+    double align(const std::shared_ptr<Feature>& refFeature, const std::shared_ptr<Frame>& curFrame, Vec2& pixelPos)
+    {
+        Item it{refFeature, curFrame, pixelPos};
+        std::vector<double> err;
+        std::vector<Vec2> px{pixelPos};
+        alignBatch({it}, px, err);
+        pixelPos = px[0];
+        return err[0];
+    }
+
+    // The serial per-candidate loop of Map::reprojectCell / addCandidateToFrame (src/map.cpp:538,608) as ONE launch.
+    struct Item {
+        std::shared_ptr<Feature> refFeature;
+        std::shared_ptr<Frame> curFrame;
+        Vec2 pixelPos;
+    };
+    void alignBatch(const std::vector<Item>& items, std::vector<Vec2>& pixelPosOut, std::vector<double>& errorOut)
+    {
+        pixelPosOut.resize(items.size());
+        errorOut.resize(items.size());
+        if (items.empty()) return;
+        const auto& dev = items[0].curFrame->m_imagePyramid.device();
+        std::vector<svo_fa_item> in(items.size());
+        for (size_t i = 0; i < items.size(); i++) {
+            svo_fa_item a{};
+            a.ref_slot  = items[i].refFeature->m_frame->m_imagePyramid.slot();
+            a.cur_slot  = items[i].curFrame->m_imagePyramid.slot();
+            a.ref_px[0] = items[i].refFeature->m_pixelPosition.x();
+            a.ref_px[1] = items[i].refFeature->m_pixelPosition.y();
+            a.px[0]     = items[i].pixelPos.x();
+            a.px[1]     = items[i].pixelPos.y();
+            a.A[0] = a.A[3] = 1.0;
+            in[i]           = a;
+        }
+        svo_fa_params prm{};
+        prm.patch_size = (int32_t)m_patchSize;
+        prm.mode       = m_mode;
+        prm.max_iter   = (int32_t)m_maxIteration;
+        std::vector<svo_fa_result> res(items.size());
+        dev->check(svo_feature_align(dev->ctx(), in.data(), (int)in.size(), &prm, res.data()), "svo_feature_align");
+        for (size_t i = 0; i < items.size(); i++) {
+            pixelPosOut[i] = Vec2(res[i].px[0], res[i].px[1]);
+            errorOut[i]    = res[i].rmse;
+        }
+    }
+
+    int32_t m_mode          = SVO_LM_FAITHFUL;
+    uint32_t m_maxIteration = 20;
+
+private:
+    uint32_t m_patchSize;
+    int32_t m_level;
+};
+
+}  // namespace svo

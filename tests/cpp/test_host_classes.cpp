@@ -1,0 +1,201 @@
+// test_host_classes.cpp -- exercises the reference-shaped host classes (host/svo_host.hpp) end to end on the GPU and
+// checks them against the CPU oracle.  Shaped after the reference's own tests (tests/test_image_pyramid.cpp:20-60:
+// level count, sizes, base image identity) plus the numeric checks the reference never had.
+// usage: test_host_classes <ref.u8> <cur.u8> <w> <h> <Tcur_true 7 doubles...>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <iostream>
+
+#include "svo_host.hpp"
+#include "svo_oracle.h"
+
+using namespace svo;
+
+static int g_fail = 0;
+#define CHECK(cond)                                                        \
+    do {                                                                   \
+        if (!(cond)) {                                                     \
+            std::printf("CHECK FAILED %s:%d: %s\n", __FILE__, __LINE__, #cond); \
+            g_fail++;                                                      \
+        }                                                                  \
+    } while (0)
+
+static Mat8 readImage(const char* path, int w, int h)
+{
+    Mat8 m(h, w);
+    std::ifstream f(path, std::ios::binary);
+    f.read(reinterpret_cast<char*>(m.ptr()), (std::streamsize)w * h);
+    if (!f) {
+        std::printf("cannot read %s\n", path);
+        std::exit(2);
+    }
+    return m;
+}
+
+int main(int argc, char** argv)
+{
+    if (argc < 5) return 2;
+    const int w = std::atoi(argv[3]), h = std::atoi(argv[4]);
+    const Mat8 refImg = readImage(argv[1], w, h), curImg = readImage(argv[2], w, h);
+    const double K[4] = {721.5377, 721.5377, 609.5593, 172.8540};  // resource/kitti.yaml:7-8
+
+    Device::current() = std::make_shared<Device>(w, h, K, /*levels*/ 4, /*maxFrames*/ 8);
+    auto camera       = std::make_shared<PinholeCamera>(w, h, K[0], K[1], K[2], K[3], 0, 0, 0, 0, 0);
+
+    // ---- ImagePyramid (tests/test_image_pyramid.cpp) ----
+    {
+        ImagePyramid pyr(4);
+        CHECK(pyr.getSizeImagePyramid() == 0);
+        pyr.createImagePyramid(refImg, 4);
+        CHECK(pyr.getSizeImagePyramid() == 4);
+        CHECK(pyr.getBaseImage().ptr() == refImg.ptr());  // level 0 shares the input buffer
+        CHECK(pyr.getBaseImageSize().width == w && pyr.getBaseImageSize().height == h);
+        CHECK(pyr.getImageSizeAtLevel(1).width == (w + 1) / 2 && pyr.getImageSizeAtLevel(1).height == (h + 1) / 2);
+        CHECK(pyr.getImageSizeAtLevel(7).width == 0);
+        std::vector<uint8_t> ip(orc_pyramid_bytes(w, h, 4)), gp(ip.size());
+        orc_build_pyramid(refImg.ptr(), w, h, w, 4, ip.data(), gp.data());
+        size_t off = 0;
+        for (int l = 0; l < 4; l++) {
+            const Mat8& a = pyr.getImageAtLevel(l);
+            const Mat8& g = pyr.getGradientAtLevel(l);
+            CHECK(std::memcmp(a.ptr(), ip.data() + off, (size_t)a.rows * a.cols) == 0);
+            CHECK(std::memcmp(g.ptr(), gp.data() + off, (size_t)g.rows * g.cols) == 0);
+            off += (size_t)a.rows * a.cols;
+        }
+    }
+    // ---- Frame: corrupted image throws (src/frame.cpp:20-24) ----
+    {
+        bool threw = false;
+        try {
+            Frame bad(camera, Mat8(10, 10), 4, 0, nullptr);
+        } catch (const std::runtime_error& e) {
+            threw = std::string(e.what()) == "Image Corrupted";
+        }
+        CHECK(threw);
+    }
+
+    auto kf  = std::make_shared<Frame>(camera, refImg, 4, 0, nullptr);  // an empty last keyframe
+    auto ref = std::make_shared<Frame>(camera, refImg, 4, 1, kf);
+    auto cur = std::make_shared<Frame>(camera, curImg, 4, 2, kf);
+
+    // ---- FeatureSelection::gradientMagnitudeByValue ----
+    FeatureSelection selector(w, h, 30);
+    CHECK(selector.m_gridRows == h / 30 + 1 && selector.m_gridCols == w / 30 + 1);
+    selector.setCellInGridOccupancy(Vec2(45.0, 40.0));  // cell (1, 1) is taken
+    selector.gradientMagnitudeByValue(ref, 50, true);
+    {
+        std::vector<uint8_t> occ((size_t)selector.m_gridRows * selector.m_gridCols, 0);
+        occ[(size_t)1 * selector.m_gridCols + 1] = 1;
+        std::vector<int32_t> want(3 * occ.size());
+        const Mat8& g = ref->m_imagePyramid.getBaseGradientImage();
+        const int n   = orc_grid_select(g.ptr(), w, h, w, 30, 50, occ.data(), want.data(), (int)occ.size());
+        CHECK((int)ref->numberObservation() == n);
+        for (int i = 0; i < n && i < (int)ref->numberObservation(); i++) {
+            const auto& f = ref->m_features[i];
+            CHECK(f->m_pixelPosition.x() == want[3 * i] && f->m_pixelPosition.y() == want[3 * i + 1] &&
+                  f->m_gradientMagnitude == want[3 * i + 2]);
+            CHECK(std::fabs(f->m_bearingVec.norm() - 1.0) < 1e-12);
+        }
+        bool occupancyReset = true;
+        for (bool b : selector.m_occupancyGrid) occupancyReset &= !b;
+        CHECK(occupancyReset);  // src/feature_selection.cpp:145
+        bool threw = false;
+        try {
+            selector.gradientMagnitudeByValue(ref, 50, false);
+        } catch (const std::invalid_argument&) {
+            threw = true;
+        }
+        CHECK(threw);
+    }
+    // 3D points on the plane z = 15 m (the scene the images were rendered from); every 7th feature has no point
+    for (size_t i = 0; i < ref->m_features.size(); i++) {
+        if (i % 7 == 3) continue;
+        auto& f      = ref->m_features[i];
+        const Vec3 b = f->m_bearingVec;
+        auto p       = std::make_shared<Point>(ref->camera2world(b * (15.0 / b.z())));
+        f->setPoint(p);
+    }
+
+    // ---- ImageAlignment::align, faithful mode == the reference's behaviour ----
+    std::vector<orc_feature> of;
+    for (const auto& f : ref->m_features) {
+        orc_feature a{};
+        a.px[0] = f->m_pixelPosition.x();
+        a.px[1] = f->m_pixelPosition.y();
+        for (int i = 0; i < 3; i++) a.bearing[i] = f->m_bearingVec[i];
+        a.has_point = f->m_point != nullptr;
+        if (f->m_point)
+            for (int i = 0; i < 3; i++) a.point[i] = f->m_point->m_position[i];
+        of.push_back(a);
+    }
+    std::vector<uint8_t> rp(orc_pyramid_bytes(w, h, 4)), rg(rp.size()), cp(rp.size()), cg(rp.size());
+    orc_build_pyramid(refImg.ptr(), w, h, w, 4, rp.data(), rg.data());
+    orc_build_pyramid(curImg.ptr(), w, h, w, 4, cp.data(), cg.data());
+    const double I7[7] = {0, 0, 0, 1, 0, 0, 0};
+    for (int mode = 0; mode < 3; mode++) {
+        ImageAlignment aligner(5, 0, 3, 6);
+        aligner.m_mode         = mode;
+        aligner.m_maxIteration = 30;
+        cur->m_absPose         = ref->m_absPose;  // prior
+        const double err       = aligner.align(ref, cur);
+        orc_align_params prm{5, 0, 3, mode, 30, ORC_MEDIAN_EXACT};
+        double T[7];
+        std::memcpy(T, I7, sizeof(T));
+        int32_t st         = 0;
+        const double oerr  = orc_sparse_align(rp.data(), rp.data(), cp.data(), w, h, of.data(), (int)of.size(), 0, I7, I7, K, &prm,
+                                              T, nullptr, &st);
+        double got[7];
+        cur->m_absPose.params(got);
+        double dq = 0, dt = 0;
+        for (int i = 0; i < 4; i++) dq = std::fmax(dq, std::fabs(got[i] - T[i]));
+        for (int i = 4; i < 7; i++) dt = std::fmax(dt, std::fabs(got[i] - T[i]));
+        std::printf("ImageAlignment mode %d: rmse gpu %.6f oracle %.6f  |dq| %.2e |dt| %.2e status %d/%d\n", mode, err, oerr, dq,
+                    dt, aligner.m_status, st);
+        CHECK(dq < 5e-6 && dt < 1e-4);  // 1e-5 rad = 5e-6 in quaternion units
+        CHECK(std::fabs(err - oerr) <= 1e-4 * oerr);
+        if (mode == 0) CHECK(aligner.m_status == st);
+        if (mode != 0 && argc >= 12) {  // iterated modes recover the rendered motion
+            double e = 0;
+            for (int i = 4; i < 7; i++) e = std::fmax(e, std::fabs(got[i] - std::atof(argv[5 + i])));
+            CHECK(e < 5e-3);
+        }
+    }
+    {
+        auto empty = std::make_shared<Frame>(camera, refImg, 4, 3, kf);
+        ImageAlignment aligner(5, 0, 3, 6);
+        CHECK(aligner.align(empty, cur) == 0.0);  // src/image_alignment.cpp:27-28
+    }
+
+    // ---- FeatureAlignment::align (single calls and the batched form agree with the oracle) ----
+    {
+        FeatureAlignment fa(7, 0, 3);
+        std::vector<FeatureAlignment::Item> items;
+        for (size_t i = 50; i < 90 && i < ref->m_features.size(); i++)
+            items.push_back({ref->m_features[i], cur, Vec2(ref->m_features[i]->m_pixelPosition.x() + 0.7,
+                                                           ref->m_features[i]->m_pixelPosition.y() - 0.4)});
+        std::vector<Vec2> px;
+        std::vector<double> err;
+        fa.alignBatch(items, px, err);
+        for (size_t i = 0; i < items.size(); i++) {
+            const auto& f       = items[i].refFeature;
+            const double rpx[2] = {f->m_pixelPosition.x(), f->m_pixelPosition.y()};
+            double p[2]         = {items[i].pixelPos.x(), items[i].pixelPos.y()};
+            orc_fa_params prm{7, ORC_LM_FAITHFUL, 20, ORC_MEDIAN_EXACT};
+            int32_t st = 0, it = 0;
+            const double oerr = orc_feature_align(rg.data(), cg.data(), w, h, rpx, nullptr, p, &prm, &st, &it);
+            CHECK(std::fabs(px[i].x() - p[0]) < 1e-7 && std::fabs(px[i].y() - p[1]) < 1e-7);
+            CHECK((std::isnan(oerr) && std::isnan(err[i])) || std::fabs(err[i] - oerr) < 1e-7);
+            if (i == 0) {
+                Vec2 single = items[i].pixelPos;
+                const double e1 = fa.align(f, cur, single);
+                CHECK(single.x() == px[i].x() && single.y() == px[i].y() && (e1 == err[i] || (std::isnan(e1) && std::isnan(err[i]))));
+            }
+        }
+    }
+    Device::current().reset();
+    std::printf(g_fail ? "FAILED (%d checks)\n" : "ALL HOST-CLASS CHECKS PASSED\n", g_fail);
+    return g_fail ? 1 : 0;
+}
