@@ -47,6 +47,7 @@ void release(svo_ctx* ctx)
     cudaFree(ctx->d_stats);
     cudaFree(ctx->d_scratch_tpl);
     cudaFree(ctx->d_scratch_jac);
+    cudaFree(ctx->d_scratch2);
     cudaFreeHost(ctx->h_fa_items);
     cudaFreeHost(ctx->h_fa_results);
     cudaFree(ctx->d_fa_items);

@@ -68,6 +68,8 @@ struct svo_ctx {
     float* d_scratch_jac;        // [job][F][12]   image Jacobian rows per feature
     int64_t feats_cap;
     int scratch_area;            // patch area d_scratch_tpl is sized for
+    float* d_scratch2;           // fast path: per job world points + per level template blocks
+    size_t scratch2_bytes;
     int staged_jobs, staged_feats, staged_levels, staged_want_stats;
     svo_align_params staged_params;
 
@@ -116,3 +118,5 @@ svo_status launch_grid_select(svo_ctx* ctx, int slot, int cell, uint32_t thr, in
 svo_status launch_sparse_align(svo_ctx* ctx);
 svo_status launch_feature_align(svo_ctx* ctx);
 size_t sparse_align_smem_bytes(int nthreads, int max_features, int patch_area);
+bool sparse_align_v2_supported(const svo_ctx* ctx, int maxF);
+svo_status launch_sparse_align_v2(svo_ctx* ctx, int maxF);

@@ -16,13 +16,13 @@
 //               in FP64 on thread 0; the accept/reject logic of the reference stays on the device.
 // Tensor cores are not used: the path is a gather plus a 28-scalar reduction.
 #include <float.h>
+#include <stdlib.h>
 
 #include "ctx.h"
 #include "math.cuh"
+#include "align_common.cuh"
 
 namespace {
-
-using svo::Pose;
 
 constexpr int GEO_INVALID = -32768;
 constexpr unsigned FULL   = 0xffffffffu;
@@ -44,23 +44,6 @@ struct AlignArgs {
 struct __align__(16) Geo {  // per feature, per evaluation
     int uI, vI;
     float fu, fv;
-};
-
-struct Ctrl {
-    Pose pose, pre_pose;
-    double R[9], t[3];
-    double E[28];     // last evaluation: H (21, upper triangle row-major), g (6), chi2
-    double curE[28];  // accepted evaluation (LM)
-    double preChi2;
-    double sigma;
-    double first_sigma;
-    double lambda, nu;
-    double dx[6];
-    double rmse;
-    int n_eval, cur_n, nvis;
-    int status, it, done, success;
-    int evals_total, iters_total, evals_level, iters_level;
-    int first;
 };
 
 __device__ __forceinline__ uint32_t f2key(float f)
@@ -198,28 +181,6 @@ struct InvSigned {
 struct InvAbs {
     __device__ __forceinline__ float operator()(uint32_t k) const { return __uint_as_float(k); }
 };
-
-__constant__ int c_pairA[21] = {0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 4, 4, 5};
-__constant__ int c_pairB[21] = {0, 1, 2, 3, 4, 5, 1, 2, 3, 4, 5, 2, 3, 4, 5, 3, 4, 5, 4, 5, 5};
-
-__device__ __forceinline__ void set_Rt(Ctrl* c)
-{
-    svo::quat_to_R(c->pose.q, c->R);
-    c->t[0] = c->pose.t[0];
-    c->t[1] = c->pose.t[1];
-    c->t[2] = c->pose.t[2];
-}
-
-__device__ void expand_H(const double* E, double* H, double* g)
-{
-    int k = 0;
-    for (int a = 0; a < 6; a++)
-        for (int b = a; b < 6; b++, k++) {
-            H[a * 6 + b] = E[k];
-            H[b * 6 + a] = E[k];
-        }
-    for (int a = 0; a < 6; a++) g[a] = E[21 + a];
-}
 
 template <int NT>
 __global__ void __launch_bounds__(NT, 1) k_sparse_align(const AlignArgs a)
@@ -761,6 +722,12 @@ svo_status launch_sparse_align(svo_ctx* ctx)
     // feature capacity of this launch: the largest job, rounded up (keeps shared memory small for small jobs)
     int maxF = 1;
     for (int j = 0; j < nJobs; j++) maxF = std::max(maxF, ctx->h_jobs[j].n_ref + ctx->h_jobs[j].n_kf);
+    // fast path (sparse_align_v2.cu): patch 4 / 5, <= 512 features per pair.  SVO_ALIGN_GENERIC=1 forces the generic
+    // kernel below (A/B measurements); both are CUDA paths -- there is no CPU fallback anywhere.
+    {
+        const char* e = getenv("SVO_ALIGN_GENERIC");
+        if (!(e && e[0] == '1') && sparse_align_v2_supported(ctx, maxF)) return launch_sparse_align_v2(ctx, maxF);
+    }
     maxF = (maxF + 15) & ~15;
     if ((int64_t)maxF * area >= 65536) SVO_FAIL(SVO_ERR_CAPACITY, "features * patch area must stay below 65536");
 

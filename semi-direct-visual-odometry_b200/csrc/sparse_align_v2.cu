@@ -1,0 +1,887 @@
+// sparse_align_v2.cu -- fast path of ImageAlignment::align (src/image_alignment.cpp:25-67) for patch sizes 4 / 5 and
+// at most 512 features per frame pair.  Two kernels:
+//
+// k_align_precompute<P>  (computeJacobian, :69-192, for ALL levels at once; one thread per job x level x feature)
+//     FP64: world point p_W = T_frame^-1 (bearing |P - C|), visibility at the level, the 2x6 image Jacobian rows A, B
+//     (computeImageJac, :194-248) and the (P+2)^2 grid of bilinear template samples around the feature, from which
+//     T (centre P x P), gx and gy (central differences) follow.  Written feature-minor to an HBM scratch so that the
+//     iterate kernel reads a level with ONE bulk async copy.
+//
+// k_align_iterate<P>     (optimizeLM / optimizeGN, src/optimizer.cpp:41-370, over all levels; one CTA per pair,
+//                         persistent: never returns to the host between iterations)
+//     thread f owns feature f.  Per evaluation (computeResiduals, :251-370 + tukeyWeighting + normal equations):
+//       warp      p_cur = R p_W + t, project, scale (FP64)
+//       sample    the (P+1)^2 footprint of the current image lives in REGISTERS (8-byte row windows) and is re-fetched
+//                 from L2 only when the feature's integer position leaves the window; bilinear in FP32
+//       residual  r = I - T, kept in registers as fixed point q = rint(r 2^16) (|r| <= 255 is exact in 25 bits)
+//       sigma     1.4826 MAD by two exact order statistics: block-wide MSD radix select on the fixed-point keys
+//                 (6+6 bit passes on thread-private shared-memory counters, 9+6 bit passes on shared atomics)
+//       reduce    per-feature patch sums sxx sxy syy bx by chi2 -> 28 entries of J^T W J, J^T W r, chi2 through the
+//                 factorisation J_row = gx A + gy B; transposed warp-shuffle reduction, FP64 across warps
+//       solve     damping, pivoted LDLT 6x6, pose <- pose exp(-dx) in FP64 on one thread; accept / reject on device
+#include <float.h>
+
+#include "align_common.cuh"
+
+namespace {
+
+constexpr int NT       = 512;
+constexpr int NW       = NT / 32;
+constexpr unsigned FULL = 0xffffffffu;
+
+template <int P>
+struct PatchGeo {
+    static constexpr int PB   = -(P / 2);  // first offset; odd P: -half..half, even P: -P/2..P/2-1
+    static constexpr int AREA = P * P;
+    static constexpr int FW   = P + 1;     // footprint of the bilinear taps of a patch
+    static constexpr int GW   = P + 2;     // template grid: patch plus one ring for the central differences
+    static constexpr int GA   = GW * GW;
+    static constexpr int ROWW = GA + 12 + 1;  // scratch words per feature and level: grid, A, B, flag
+};
+
+struct V2Args {
+    ArenaView view;
+    const svo_align_job* jobs;
+    const svo_align_feature* feats;
+    svo_align_result* results;
+    svo_align_level_stats* stats;  // nullable
+    float* scratch;                // [job][ pW: 3*Fpad doubles | level blocks: ROWW*Fpad floats each ]
+    long long job_stride;          // floats per job in scratch
+    int Fpad;                      // features per job rounded up (multiple of 32, <= NT)
+    svo_align_params prm;
+    double K[4];
+};
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ------------------------------------------------------------------------------------------------------------
+// precompute
+// ------------------------------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(128) k_align_precompute(const V2Args a)
+{
+    using G = PatchGeo<P>;
+    const int nLevels = a.prm.max_level - a.prm.min_level + 1;
+    const int f       = blockIdx.x * blockDim.x + threadIdx.x;
+    const int si      = blockIdx.y;  // 0 = coarsest
+    const int job     = blockIdx.z;
+    if (f >= a.Fpad) return;
+    const int level        = a.prm.max_level - si;
+    const svo_align_job* J = a.jobs + job;
+    const int nRef = J->n_ref, F = J->n_ref + J->n_kf;
+    float* base    = a.scratch + (long long)job * a.job_stride;
+    double* pWout  = reinterpret_cast<double*>(base);
+    float* blk     = base + 6 * a.Fpad + (long long)si * G::ROWW * a.Fpad;
+    uint32_t flag  = 0;
+    if (f < F) {
+        const svo_align_feature* ft = a.feats + J->feat_offset + f;
+        if (ft->has_point) {
+            // p_W = T_frame^-1 (bearing * |P - C_frame|)   src/image_alignment.cpp:153-155
+            const double* Tp = f < nRef ? J->T_ref : J->T_kf;
+            Pose Tf;
+#pragma unroll
+            for (int i = 0; i < 4; i++) Tf.q[i] = Tp[i];
+#pragma unroll
+            for (int i = 0; i < 3; i++) Tf.t[i] = Tp[4 + i];
+            double C[3];
+            svo::pose_camera_in_world(Tf, C);
+            const double d0 = ft->point[0] - C[0], d1 = ft->point[1] - C[1], d2 = ft->point[2] - C[2];
+            const double depthNorm = sqrt(d0 * d0 + d1 * d1 + d2 * d2);
+            const double pC[3]     = {ft->bearing[0] * depthNorm, ft->bearing[1] * depthNorm, ft->bearing[2] * depthNorm};
+            double pW[3];
+            svo::pose_inv_act(Tf, pC, pW);
+            if (si == 0) {
+                pWout[0 * a.Fpad + f] = pW[0];
+                pWout[1 * a.Fpad + f] = pW[1];
+                pWout[2 * a.Fpad + f] = pW[2];
+            }
+            const int lw = a.view.w[level], lh = a.view.h[level], lpitch = a.view.pitch[level];
+            const double denom = (double)(1 << level);
+            const double scale = 1.0 / denom;
+            const int border   = P / 2 + 2;
+            const double u = ft->px[0] * scale, v = ft->px[1] * scale;
+            const double uf = floor(u), vf = floor(v);
+            const int uI = (int)uf, vI = (int)vf;
+            if (!((uI - border) < 0 || (vI - border) < 0 || (uI + border) >= lw || (vI + border) >= lh)) {
+                flag = 1;
+                // computeImageJac at the WORLD point, scaled focal lengths
+                const double fx = a.K[0] / denom, fy = a.K[1] / denom;
+                const double x = pW[0], y = pW[1], z = pW[2];
+                const double x2 = x * x, y2 = y * y, z2 = z * z;
+                float* jf = blk + (long long)G::GA * a.Fpad + f;
+                jf[0 * a.Fpad]  = (float)(fx / z);
+                jf[1 * a.Fpad]  = 0.f;
+                jf[2 * a.Fpad]  = (float)(-(fx * x) / z2);
+                jf[3 * a.Fpad]  = (float)(-(fx * x * y) / z2);
+                jf[4 * a.Fpad]  = (float)((fx * x2) / z2 + fx);
+                jf[5 * a.Fpad]  = (float)(-(fx * y) / z);
+                jf[6 * a.Fpad]  = 0.f;
+                jf[7 * a.Fpad]  = (float)(fy / z);
+                jf[8 * a.Fpad]  = (float)(-(fy * y) / z2);
+                jf[9 * a.Fpad]  = (float)(-(fy * y2) / z2 - fy);
+                jf[10 * a.Fpad] = (float)((fy * x * y) / z2);
+                jf[11 * a.Fpad] = (float)((fy * x) / z);
+                // template grid: bilinear samples at (u + gx - 1 + PB, v + gy - 1 + PB), gx, gy in [0, GW)
+                const uint8_t* img = a.view.img[level] +
+                                     (long long)(f < nRef ? J->ref_slot : J->kf_slot) * a.view.plane_stride[level] +
+                                     (long long)(vI + G::PB - 1) * lpitch + (uI + G::PB - 1);
+                const double fu = u - uf, fv = v - vf, wu0 = 1.0 - fu, wv0 = 1.0 - fv;
+                double prev[G::GW];  // horizontal interpolants of the previous source row
+#pragma unroll
+                for (int ry = 0; ry <= G::GW; ry++) {
+                    double cur[G::GW];
+                    double left = (double)__ldg(img + (long long)ry * lpitch);
+#pragma unroll
+                    for (int cx = 0; cx < G::GW; cx++) {
+                        const double right = (double)__ldg(img + (long long)ry * lpitch + cx + 1);
+                        cur[cx]            = wu0 * left + fu * right;  // src/algorithm.cpp:901-902
+                        left               = right;
+                    }
+                    if (ry > 0) {
+#pragma unroll
+                        for (int cx = 0; cx < G::GW; cx++)
+                            blk[(long long)((ry - 1) * G::GW + cx) * a.Fpad + f] = (float)(wv0 * prev[cx] + fv * cur[cx]);  // :903
+                    }
+#pragma unroll
+                    for (int cx = 0; cx < G::GW; cx++) prev[cx] = cur[cx];
+                }
+            }
+        }
+    }
+    reinterpret_cast<uint32_t*>(blk)[(long long)(G::GA + 12) * a.Fpad + f] = flag;
+}
+
+// ------------------------------------------------------------------------------------------------------------
+// block-wide exact selection on 27-bit keys held in registers
+// ------------------------------------------------------------------------------------------------------------
+struct SelSmem {
+    uint32_t* priv;    // [16][NT] thread-private packed 8-bit counters (64 bins), zero between uses
+    uint32_t* bins;    // [512] shared counters for the atomic passes, zero between uses
+    uint32_t* tot;     // [64] bin totals of a private pass
+    uint32_t* wtot;    // [NW]
+    uint32_t* sel;     // [2] chosen digit, remaining rank
+};
+
+// one pass over 6 bits with thread-private counters.  keys: AREA values; live: participates at all
+template <int AREA, class KeyFn>
+__device__ __forceinline__ void select_pass_private(const int (&q)[AREA], bool live, KeyFn key, uint32_t& prefix, uint32_t& mask,
+                                                    int& k, int shift, const SelSmem& s)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (live) {
+#pragma unroll
+        for (int i = 0; i < AREA; i++) {
+            const uint32_t kk = key(q[i]);
+            if ((kk & mask) == prefix) {
+                const uint32_t d = (kk >> shift) & 63u;
+                s.priv[(d >> 2) * NT + tid] += 1u << ((d & 3u) * 8u);
+            }
+        }
+    }
+    __syncthreads();
+    {   // warp w reduces word row w (bins 4w .. 4w+3) over all NT columns
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int j = 0; j < NT / 32; j++) {
+            const uint32_t wv                 = s.priv[warp * NT + lane + 32 * j];
+            s.priv[warp * NT + lane + 32 * j] = 0;
+            lo += wv & 0x00ff00ffu;
+            hi += (wv >> 8) & 0x00ff00ffu;
+        }
+        lo = __reduce_add_sync(FULL, lo);
+        hi = __reduce_add_sync(FULL, hi);
+        if (lane == 0) {
+            s.tot[warp * 4 + 0] = lo & 0xffffu;
+            s.tot[warp * 4 + 1] = hi & 0xffffu;
+            s.tot[warp * 4 + 2] = lo >> 16;
+            s.tot[warp * 4 + 3] = hi >> 16;
+        }
+    }
+    __syncthreads();
+    if (warp == 0) {
+        const uint32_t c0 = s.tot[2 * lane], c1 = s.tot[2 * lane + 1];
+        const uint32_t sum = c0 + c1;
+        uint32_t incl      = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t v = __shfl_up_sync(FULL, incl, o);
+            if (lane >= o) incl += v;
+        }
+        const uint32_t excl = incl - sum;
+        const uint32_t kk   = (uint32_t)k;
+        if (kk >= excl && kk < excl + c0) {
+            s.sel[0] = 2 * lane;
+            s.sel[1] = kk - excl;
+        } else if (kk >= excl + c0 && kk < incl) {
+            s.sel[0] = 2 * lane + 1;
+            s.sel[1] = kk - excl - c0;
+        }
+    }
+    __syncthreads();
+    prefix |= s.sel[0] << shift;
+    mask |= 63u << shift;
+    k = (int)s.sel[1];
+}
+
+// one pass over `bits` (<= 9) bits with shared atomic counters (few keys match the prefix by now)
+template <int AREA, class KeyFn>
+__device__ __forceinline__ void select_pass_atomic(const int (&q)[AREA], bool live, KeyFn key, uint32_t& prefix, uint32_t& mask,
+                                                   int& k, int shift, int bits, const SelSmem& s)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t dm = (1u << bits) - 1u;
+    if (live) {
+#pragma unroll
+        for (int i = 0; i < AREA; i++) {
+            const uint32_t kk = key(q[i]);
+            if ((kk & mask) == prefix) atomicAdd(&s.bins[(kk >> shift) & dm], 1u);
+        }
+    }
+    __syncthreads();
+    const uint32_t c = s.bins[tid];  // NT == 512 bins
+    s.bins[tid]      = 0;
+    uint32_t incl    = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    if (lane == 31) s.wtot[warp] = incl;
+    __syncthreads();
+    uint32_t base = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) base += (w < warp) ? s.wtot[w] : 0u;
+    const uint32_t excl = base + incl - c;
+    const uint32_t kk   = (uint32_t)k;
+    if (kk >= excl && kk < excl + c) {
+        s.sel[0] = tid;
+        s.sel[1] = kk - excl;
+    }
+    __syncthreads();
+    prefix |= s.sel[0] << shift;
+    mask |= dm << shift;
+    k = (int)s.sel[1];
+}
+
+// k-th smallest key (0-based) over all live threads' keys; *rank_in_key = k minus the number of strictly smaller keys
+template <int AREA, class KeyFn>
+__device__ __forceinline__ uint32_t block_select27(const int (&q)[AREA], bool live, KeyFn key, int k, const SelSmem& s,
+                                                   int* rank_in_key)
+{
+    uint32_t prefix = 0, mask = 0;
+    select_pass_private<AREA>(q, live, key, prefix, mask, k, 21, s);
+    select_pass_private<AREA>(q, live, key, prefix, mask, k, 15, s);
+    select_pass_atomic<AREA>(q, live, key, prefix, mask, k, 6, 9, s);
+    select_pass_atomic<AREA>(q, live, key, prefix, mask, k, 0, 6, s);
+    *rank_in_key = k;
+    return prefix;
+}
+
+// largest key strictly below bound (0 if none)
+template <int AREA, class KeyFn>
+__device__ __forceinline__ uint32_t block_max_below27(const int (&q)[AREA], bool live, KeyFn key, uint32_t bound, const SelSmem& s)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t m = 0;
+    if (live) {
+#pragma unroll
+        for (int i = 0; i < AREA; i++) {
+            const uint32_t kk = key(q[i]);
+            if (kk < bound) m = max(m, kk);
+        }
+    }
+    m = __reduce_max_sync(FULL, m);
+    if (lane == 0) s.wtot[warp] = m;
+    __syncthreads();
+    uint32_t out = 0;
+#pragma unroll
+    for (int w = 0; w < NW; w++) out = max(out, s.wtot[w]);
+    __syncthreads();  // wtot is reused by the next pass
+    return out;
+}
+
+struct KeySignedQ {  // order-preserving map of q in [-2^25, 2^25) to 27 bits
+    __device__ __forceinline__ uint32_t operator()(int q) const { return (uint32_t)(q + (1 << 25)); }
+};
+struct KeyAbsDev2 {  // |2 q - med2|, deviations in half fixed-point units
+    int med2;
+    __device__ __forceinline__ uint32_t operator()(int q) const { return (uint32_t)min(abs(2 * q - med2), (1 << 27) - 1); }
+};
+
+// ------------------------------------------------------------------------------------------------------------
+// iterate
+// ------------------------------------------------------------------------------------------------------------
+template <int P>
+__host__ __device__ constexpr size_t v2_smem_bytes(int Fpad)
+{
+    using G = PatchGeo<P>;
+    size_t b = 0;
+    b += (size_t)G::ROWW * Fpad * 4;  // level block (grid, jac, flags): one bulk copy
+    b += (size_t)3 * Fpad * 8;        // pW
+    b += (size_t)16 * NT * 4;         // private counters
+    b += 512 * 4 + 64 * 4 + NW * 4 + 16;  // bins, tot, wtot, sel
+    b += (size_t)NW * 32 * 8;         // red
+    b += sizeof(Ctrl) + 64;
+    return b + 1024;                  // alignment slack
+}
+
+template <int P>
+__global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
+{
+    using G = PatchGeo<P>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int job = blockIdx.x;
+    const svo_align_job* J = a.jobs + job;
+    const int F       = J->n_ref + J->n_kf;
+    const int Fpad    = a.Fpad;
+    const int nLevels = a.prm.max_level - a.prm.min_level + 1;
+
+    // ---- shared memory carve-up ----
+    unsigned char* sp = smem_raw;
+    float* blk        = reinterpret_cast<float*>(sp);  // [ROWW][Fpad]
+    sp += (size_t)G::ROWW * Fpad * 4;
+    double* pWs = reinterpret_cast<double*>(sp);  // [3][Fpad]
+    sp += (size_t)3 * Fpad * 8;
+    SelSmem sel;
+    sel.priv = reinterpret_cast<uint32_t*>(sp);
+    sp += (size_t)16 * NT * 4;
+    sel.bins = reinterpret_cast<uint32_t*>(sp);
+    sp += 512 * 4;
+    sel.tot = reinterpret_cast<uint32_t*>(sp);
+    sp += 64 * 4;
+    sel.wtot = reinterpret_cast<uint32_t*>(sp);
+    sp += NW * 4;
+    sel.sel = reinterpret_cast<uint32_t*>(sp);
+    sp += 16;
+    sp          = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sp) + 15) & ~uintptr_t(15));
+    double* red = reinterpret_cast<double*>(sp);  // [NW][32]
+    sp += (size_t)NW * 32 * 8;
+    unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sp);
+    sp += 16;
+    Ctrl* ctrl = reinterpret_cast<Ctrl*>(sp);
+
+    const float* gridS    = blk;
+    const float* jacS     = blk + (size_t)G::GA * Fpad;
+    const uint32_t* flagS = reinterpret_cast<const uint32_t*>(blk + (size_t)(G::GA + 12) * Fpad);
+
+    if (J->n_ref == 0) {  // src/image_alignment.cpp:27-28
+        if (tid == 0) {
+            svo_align_result res;
+            for (int i = 0; i < 7; i++) res.T_cur[i] = J->T_cur[i];
+            res.rmse        = 0.0;
+            res.status      = SVO_ST_SUCCESS;
+            res.evaluations = 0;
+            res.iterations  = 0;
+            res.reserved    = 0;
+            a.results[job]  = res;
+        }
+        return;
+    }
+
+    const float* scr = a.scratch + (long long)job * a.job_stride;
+    for (int i = tid; i < 16 * NT; i += NT) sel.priv[i] = 0;
+    sel.bins[tid] = 0;
+    if (tid == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(1));
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+        for (int i = 0; i < 4; i++) ctrl->pose.q[i] = J->T_cur[i];
+#pragma unroll
+        for (int i = 0; i < 3; i++) ctrl->pose.t[i] = J->T_cur[4 + i];
+        set_Rt(ctrl);
+        ctrl->evals_total = 0;
+        ctrl->iters_total = 0;
+        ctrl->status      = SVO_ST_FAILED;
+        ctrl->rmse        = 0.0;
+    }
+    __syncthreads();
+    uint32_t mphase = 0;
+    // world points (level independent): bulk copy HBM -> shared
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)(3 * Fpad * 8);
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                         smem_u32(pWs)),
+                     "l"(scr), "r"(bytes), "r"(smem_u32(mbar))
+                     : "memory");
+    }
+    {
+        uint32_t done = 0;
+        while (!done)
+            asm volatile("{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                         : "=r"(done)
+                         : "r"(smem_u32(mbar)), "r"(mphase)
+                         : "memory");
+        mphase ^= 1;
+    }
+    const int f = tid;
+    double pwx = 0, pwy = 0, pwz = 1;
+    if (f < F) {
+        pwx = pWs[f];
+        pwy = pWs[Fpad + f];
+        pwz = pWs[2 * Fpad + f];
+    }
+    const double fx0 = a.K[0], fy0 = a.K[1], cx0 = a.K[2], cy0 = a.K[3];
+    const int border = P / 2 + 2;
+
+#pragma unroll 1
+    for (int level = a.prm.max_level, si = 0; level >= a.prm.min_level; level--, si++) {
+        const int lw = a.view.w[level], lh = a.view.h[level], lpitch = a.view.pitch[level];
+        const double scale    = 1.0 / (double)(1 << level);
+        const uint8_t* curImg = a.view.img[level] + (long long)J->cur_slot * a.view.plane_stride[level];
+
+        // ---- the level's template block: one bulk async copy HBM -> shared ----
+        __syncthreads();  // everyone is done with the previous level's block
+        if (tid == 0) {
+            const uint32_t bytes = (uint32_t)(G::ROWW * Fpad * 4);
+            const float* src     = scr + 6 * Fpad + (long long)si * G::ROWW * Fpad;
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+            asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                             smem_u32(blk)),
+                         "l"(src), "r"(bytes), "r"(smem_u32(mbar))
+                         : "memory");
+            ctrl->lambda      = 1e-2;
+            ctrl->nu          = 2.0;
+            ctrl->it          = 0;
+            ctrl->done        = 0;
+            ctrl->success     = 1;
+            ctrl->status      = SVO_ST_FAILED;
+            ctrl->first       = 1;
+            ctrl->evals_level = 0;
+            ctrl->iters_level = 0;
+            ctrl->preChi2     = DBL_MAX;
+            ctrl->pre_pose    = ctrl->pose;
+        }
+        {
+            uint32_t done = 0;
+            while (!done)
+                asm volatile(
+                    "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+                    : "=r"(done)
+                    : "r"(smem_u32(mbar)), "r"(mphase)
+                    : "memory");
+            mphase ^= 1;
+        }
+        __syncthreads();  // ctrl init visible
+        const bool refvis = f < F && flagS[f] != 0;
+
+        // current-image window of this feature: FW rows x 8 bytes starting at column wx, row wy
+        uint32_t winLo[G::FW], winHi[G::FW];
+        int wx = 0, wy = 0;
+        bool winValid = false;
+
+        // ================= evaluate (computeResiduals + tukeyWeighting + normal equations) =================
+        auto evaluate = [&]() {
+            // --- warp the feature (FP64) ---
+            bool vis = false;
+            int uI = 0, vI = 0;
+            float fu = 0.f, fv = 0.f;
+            if (refvis) {
+                const double* R = ctrl->R;
+                const double cxp = R[0] * pwx + R[1] * pwy + R[2] * pwz + ctrl->t[0];
+                const double cyp = R[3] * pwx + R[4] * pwy + R[5] * pwz + ctrl->t[1];
+                const double czp = R[6] * pwx + R[7] * pwy + R[8] * pwz + ctrl->t[2];
+                // PinholeCamera::project2d, src/pinhole_camera.cpp:55-56 (no z > 0 test)
+                const double u = (fx0 * (cxp / czp) + cx0) * scale;
+                const double v = (fy0 * (cyp / czp) + cy0) * scale;
+                if (isfinite(u) && isfinite(v) && fabs(u) < 1e6 && fabs(v) < 1e6) {
+                    const double uf = floor(u), vf = floor(v);
+                    uI = (int)uf;
+                    vI = (int)vf;
+                    if (!((uI - border) < 0 || (vI - border) < 0 || (uI + border) >= lw || (vI + border) >= lh)) {
+                        vis = true;
+                        fu  = (float)(u - uf);
+                        fv  = (float)(v - vf);
+                    }
+                }
+            }
+            // --- refresh the register window if the footprint left it ---
+            int q[G::AREA];
+            if (vis) {
+                const int x0 = uI + G::PB, y0 = vI + G::PB;  // footprint origin
+                if (!winValid || y0 != wy || x0 < wx || x0 + G::FW > wx + 8) {
+                    wx       = x0 - 1;
+                    wy       = y0;
+                    winValid = true;
+#pragma unroll
+                    for (int r = 0; r < G::FW; r++) {
+                        const uint8_t* p   = curImg + (long long)(wy + r) * lpitch + wx;
+                        const uintptr_t ad = reinterpret_cast<uintptr_t>(p);
+                        const uint2* p8    = reinterpret_cast<const uint2*>(ad & ~uintptr_t(7));
+                        const uint32_t sh  = (uint32_t)(ad & 7u);
+                        const uint2 w0     = __ldg(p8);
+                        uint2 w1           = make_uint2(0u, 0u);
+                        if (sh) w1 = __ldg(p8 + 1);  // never touched when aligned: may lie past the plane
+                        // bytes sh .. sh+7 of the 16-byte pair
+                        const uint32_t s4 = sh & 3u;
+                        uint32_t a0 = w0.x, a1 = w0.y, a2 = w1.x, a3 = w1.y;
+                        if (sh & 4u) {
+                            a0 = a1;
+                            a1 = a2;
+                            a2 = a3;
+                        }
+                        winLo[r] = __funnelshift_r(a0, a1, s4 * 8u);
+                        winHi[r] = __funnelshift_r(a1, a2, s4 * 8u);
+                    }
+                }
+                // --- bilinear taps (FP32) and residuals ---
+                const uint32_t off = (uint32_t)(x0 - wx);  // 0 .. 8 - FW
+                const float wu0 = 1.f - fu, wv0 = 1.f - fv;
+                float prevRow[P];
+#pragma unroll
+                for (int r = 0; r < G::FW; r++) {
+                    // FW bytes of the row starting at byte `off`
+                    const uint32_t lo = __funnelshift_r(winLo[r], winHi[r], off * 8u);
+                    const uint32_t hi = winHi[r] >> (off * 8u);
+                    float px[G::FW];
+#pragma unroll
+                    for (int c = 0; c < G::FW; c++) {
+                        const uint32_t b = c < 4 ? (lo >> (8 * c)) & 0xffu : (hi >> (8 * (c - 4))) & 0xffu;
+                        px[c]            = (float)b;
+                    }
+                    float curRow[P];
+#pragma unroll
+                    for (int c = 0; c < P; c++) curRow[c] = wu0 * px[c] + fu * px[c + 1];
+                    if (r > 0) {
+#pragma unroll
+                        for (int c = 0; c < P; c++) {
+                            const float val = wv0 * prevRow[c] + fv * curRow[c];
+                            const float T   = gridS[(size_t)((r - 1 + 1) * G::GW + (c + 1)) * Fpad + f];
+                            q[(r - 1) * P + c] = __float2int_rn((val - T) * 65536.f);
+                        }
+                    }
+#pragma unroll
+                    for (int c = 0; c < P; c++) prevRow[c] = curRow[c];
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < G::AREA; i++) q[i] = 0;
+            }
+            const int nvis     = __syncthreads_count(vis);
+            const int numValid = nvis * G::AREA;
+            const int N        = F * G::AREA;
+
+            // --- sigma = 1.4826 MAD, src/optimizer.cpp:485-507, src/algorithm.cpp:834-872 (MEDIAN_EXACT) ---
+            double sigma;
+            if (nvis == 0) {
+                sigma = DBL_EPSILON;  // the reference gets MAD = 0 from all-sentinel input
+            } else {
+                const int mid = numValid / 2;
+                int rk;
+                // element `mid` of the sorted N-vector (invalid rows sort last, so it is a valid one)
+                const uint32_t kHi = block_select27<G::AREA>(q, vis, KeySignedQ{}, mid, sel, &rk);
+                uint32_t kLo       = kHi;
+                if (!(N & 1) && mid > 0 && rk == 0) kLo = block_max_below27<G::AREA>(q, vis, KeySignedQ{}, kHi, sel);
+                const int med2 = ((N & 1) || mid == 0) ? 2 * ((int)kHi - (1 << 25)) : ((int)kHi - (1 << 25)) + ((int)kLo - (1 << 25));
+                KeyAbsDev2 kd{med2};
+                const uint32_t dHi = block_select27<G::AREA>(q, vis, kd, mid, sel, &rk);
+                uint32_t dLo       = dHi;
+                if (!(N & 1) && mid > 0 && rk == 0) dLo = block_max_below27<G::AREA>(q, vis, kd, dHi, sel);
+                // deviations are in units of 2^-17
+                const double mad = ((N & 1) || mid == 0) ? (double)dHi : 0.5 * ((double)dHi + (double)dLo);
+                sigma            = 1.482602218505602 * mad * (1.0 / 131072.0);
+                if (sigma <= DBL_EPSILON) sigma = DBL_EPSILON;
+            }
+            const double cD = 4.6851 * sigma;
+            const float cF  = (float)cD;
+            const float ic2 = (float)(1.0 / (cD * cD));
+
+            // --- per-feature patch sums (FP32) and the feature's 28 contributions ---
+            float val[32];
+#pragma unroll
+            for (int i = 0; i < 32; i++) val[i] = 0.f;
+            if (vis) {
+                float sxx = 0.f, sxy = 0.f, syy = 0.f, bx = 0.f, by = 0.f, ch = 0.f;
+#pragma unroll
+                for (int y = 0; y < P; y++) {
+#pragma unroll
+                    for (int x = 0; x < P; x++) {
+                        const float rr = (float)q[y * P + x] * (1.f / 65536.f);
+                        const float gl = gridS[(size_t)((y + 1) * G::GW + x) * Fpad + f];
+                        const float gr = gridS[(size_t)((y + 1) * G::GW + x + 2) * Fpad + f];
+                        const float gu = gridS[(size_t)(y * G::GW + x + 1) * Fpad + f];
+                        const float gd = gridS[(size_t)((y + 2) * G::GW + x + 1) * Fpad + f];
+                        const float gx = 0.5f * (gr - gl), gy = 0.5f * (gd - gu);
+                        float w        = 0.f;
+                        if (fabsf(rr) <= cF) {
+                            const float t = 1.f - rr * rr * ic2;
+                            w             = t * t;
+                        }
+                        const float wgx = w * gx, wgy = w * gy, wr = w * rr;
+                        sxx += wgx * gx;
+                        sxy += wgx * gy;
+                        syy += wgy * gy;
+                        bx += wr * gx;
+                        by += wr * gy;
+                        ch += wr * rr;
+                    }
+                }
+                float A[6], B[6];
+#pragma unroll
+                for (int i = 0; i < 6; i++) {
+                    A[i] = jacS[(size_t)i * Fpad + f];
+                    B[i] = jacS[(size_t)(6 + i) * Fpad + f];
+                }
+                int k = 0;
+#pragma unroll
+                for (int i = 0; i < 6; i++)
+#pragma unroll
+                    for (int j = i; j < 6; j++, k++) val[k] = sxx * (A[i] * A[j]) + sxy * (A[i] * B[j] + B[i] * A[j]) + syy * (B[i] * B[j]);
+#pragma unroll
+                for (int i = 0; i < 6; i++) val[21 + i] = bx * A[i] + by * B[i];
+                val[27] = ch;
+            }
+            // --- transposed warp reduction: afterwards lane i holds the warp total of val[i] ---
+#pragma unroll
+            for (int s = 16; s >= 1; s >>= 1) {
+                const bool up = (lane & s) != 0;
+#pragma unroll
+                for (int j = 0; j < s; j++) {
+                    const float send = up ? val[j] : val[j + s];
+                    const float keep = up ? val[j + s] : val[j];
+                    val[j]           = keep + __shfl_xor_sync(FULL, send, s);
+                }
+            }
+            red[warp * 32 + lane] = (double)val[0];
+            __syncthreads();
+            if (tid < 28) {
+                double s = 0.0;
+#pragma unroll
+                for (int w = 0; w < NW; w++) s += red[w * 32 + tid];
+                ctrl->E[tid] = s;
+            }
+            if (tid == 32) {
+                ctrl->sigma  = sigma;
+                ctrl->n_eval = numValid;
+                ctrl->evals_level++;
+            }
+            __syncthreads();
+        };
+
+        // record the first iteration of the level for the stats record
+        auto record_first = [&](const double* H, const double* g, double chi2, double lambda, int n) {
+            if (!ctrl->first) return;
+            ctrl->first = 0;
+            if (a.stats) {
+                svo_align_level_stats* s = a.stats + (size_t)job * nLevels + si;
+                for (int i = 0; i < 36; i++) s->H[i] = H[i];
+                for (int i = 0; i < 6; i++) s->g[i] = g[i];
+                s->chi2   = chi2;
+                s->sigma  = ctrl->first_sigma;
+                s->lambda = lambda;
+                s->n_px   = n;
+            }
+        };
+
+        // One evaluate() call site for all three modes (keeps the per-thread register state in registers): the
+        // control flow of optimizeGN (src/optimizer.cpp:41-159) and optimizeLM (:161-370) runs as a state machine
+        // on thread 0 after every evaluation.
+        const bool gn       = a.prm.mode == SVO_GN;
+        const bool faithful = a.prm.mode == SVO_LM_FAITHFUL;
+        const int maxIter   = a.prm.max_iter > 0 ? a.prm.max_iter : 20;
+        bool lmFirst        = true;  // thread 0 only
+#pragma unroll 1
+        while (true) {
+            evaluate();
+            if (tid == 0) {
+                double H[36], g[6], dx[6];
+                if (gn) {
+                    expand_H(ctrl->E, H, g);
+                    const double chi2 = ctrl->E[27];
+                    if (ctrl->first) ctrl->first_sigma = ctrl->sigma;
+                    const bool wasFirst = ctrl->first;
+                    record_first(H, g, chi2, 0.0, ctrl->n_eval);
+                    svo::ldlt_solve<6>(H, g, dx);
+                    if (wasFirst && a.stats)
+                        for (int i = 0; i < 6; i++) a.stats[(size_t)job * nLevels + si].dx[i] = dx[i];
+                    ctrl->iters_level++;
+                    double mx = dx[0];
+                    bool nan  = false;
+                    for (int i = 0; i < 6; i++) {
+                        mx = fmax(mx, dx[i]);
+                        nan |= isnan(dx[i]);
+                    }
+                    if (mx > 1e3) {
+                        ctrl->status = SVO_ST_MAX_COFF_DX;
+                        ctrl->done   = 1;
+                    } else if (nan) {
+                        ctrl->status = SVO_ST_NAN_IN_DX;
+                        ctrl->done   = 1;
+                    } else if (chi2 > ctrl->preChi2) {
+                        ctrl->status = SVO_ST_INCREASE_CHI2;
+                        ctrl->pose   = ctrl->pre_pose;  // rollback, :113-118
+                        ctrl->done   = 1;
+                    } else {
+                        ctrl->pre_pose = ctrl->pose;
+                        ctrl->preChi2  = chi2;
+                        double step    = 0;
+                        for (int i = 0; i < 6; i++) step += dx[i] * dx[i];
+                        svo::pose_update_right_exp_neg(ctrl->pose, dx);
+                        if (step < 1e-16 || chi2 < 1e-1) {
+                            int st = ctrl->status;
+                            st     = step < 1e-16 ? SVO_ST_SMALL_STEP : st;
+                            st     = chi2 < 1e-1 ? SVO_ST_SMALL_CHI2 : st;
+                            ctrl->status = st;
+                            ctrl->done   = 1;
+                        } else {
+                            ctrl->status = SVO_ST_SUCCESS;
+                            ctrl->it++;
+                            if (ctrl->it >= maxIter) ctrl->done = 1;
+                        }
+                    }
+                    ctrl->rmse = sqrt(chi2 / (double)ctrl->n_eval);
+                } else {
+                    if (lmFirst) {  // the evaluation before the loop, :199-206
+                        lmFirst = false;
+                        for (int i = 0; i < 28; i++) ctrl->curE[i] = ctrl->E[i];
+                        ctrl->cur_n       = ctrl->n_eval;
+                        ctrl->first_sigma = ctrl->sigma;
+                    } else {  // the re-evaluation after a step, :338-360
+                        const bool ok = svo::nielsen_update(ctrl->preChi2, ctrl->E[27], ctrl->lambda, ctrl->nu);
+                        ctrl->success = ok;
+                        if (ok) {
+                            for (int i = 0; i < 28; i++) ctrl->curE[i] = ctrl->E[i];
+                            ctrl->cur_n = ctrl->n_eval;
+                        } else {
+                            ctrl->pose = ctrl->pre_pose;  // rollback
+                        }
+                        ctrl->it++;
+                        if (ctrl->it >= maxIter) ctrl->done = 1;
+                    }
+                    if (!ctrl->done) {
+                        if (ctrl->success) {  // :224-233 snapshot
+                            ctrl->pre_pose = ctrl->pose;
+                            ctrl->preChi2  = ctrl->curE[27];
+                            ctrl->status   = SVO_ST_SUCCESS;
+                        }
+                        expand_H(ctrl->curE, H, g);
+                        if (ctrl->it == 0) {
+                            double mx = H[0];
+                            for (int i = 1; i < 6; i++) mx = fmax(mx, H[i * 6 + i]);
+                            ctrl->lambda *= mx;  // :296-299
+                        }
+                        const double lambda = ctrl->lambda;
+                        const bool wasFirst = ctrl->first;
+                        record_first(H, g, ctrl->curE[27], lambda, ctrl->cur_n);
+                        for (int i = 0; i < 6; i++) H[i * 6 + i] += lambda;
+                        svo::ldlt_solve<6>(H, g, dx);
+                        if (wasFirst && a.stats)
+                            for (int i = 0; i < 6; i++) a.stats[(size_t)job * nLevels + si].dx[i] = dx[i];
+                        svo::pose_update_right_exp_neg(ctrl->pose, dx);  // :310 applied before any check
+                        ctrl->iters_level++;
+                        double mx = dx[0], step = 0;
+                        bool nan = false;
+                        for (int i = 0; i < 6; i++) {
+                            mx = fmax(mx, dx[i]);
+                            nan |= isnan(dx[i]);
+                            step += dx[i] * dx[i];
+                        }
+                        if (mx > 1e3) {
+                            ctrl->status = SVO_ST_MAX_COFF_DX;
+                            ctrl->done   = 1;
+                        } else if (nan) {
+                            ctrl->status = SVO_ST_NAN_IN_DX;
+                            ctrl->done   = 1;
+                        } else if (step < 1e-16 || lambda >= 1e14 || lambda <= 1e-14 || faithful) {
+                            // :328 -- in the reference the clause `normDiffPose < m_normInfDiff` is always true
+                            int st = ctrl->status;
+                            st     = step < 1e-16 ? SVO_ST_SMALL_STEP : st;
+                            st     = fabs(lambda) >= 1e14 ? SVO_ST_LAMBDA : st;
+                            ctrl->status = st;
+                            ctrl->done   = 1;
+                        }
+                    }
+                    if (ctrl->done) ctrl->rmse = sqrt(ctrl->curE[27] / (double)ctrl->cur_n);
+                }
+                set_Rt(ctrl);
+            }
+            __syncthreads();
+            if (ctrl->done) break;
+        }
+        if (tid == 0) {
+            ctrl->evals_total += ctrl->evals_level;
+            ctrl->iters_total += ctrl->iters_level;
+            if (a.stats) {
+                svo_align_level_stats* s = a.stats + (size_t)job * nLevels + si;
+                for (int i = 0; i < 4; i++) s->pose_after[i] = ctrl->pose.q[i];
+                for (int i = 0; i < 3; i++) s->pose_after[4 + i] = ctrl->pose.t[i];
+                s->rmse        = ctrl->rmse;
+                s->status      = ctrl->status;
+                s->iterations  = ctrl->iters_level;
+                s->evaluations = ctrl->evals_level;
+            }
+        }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        svo_align_result res;
+        for (int i = 0; i < 4; i++) res.T_cur[i] = ctrl->pose.q[i];
+        for (int i = 0; i < 3; i++) res.T_cur[4 + i] = ctrl->pose.t[i];
+        res.rmse        = ctrl->rmse;
+        res.status      = ctrl->status;
+        res.evaluations = ctrl->evals_total;
+        res.iterations  = ctrl->iters_total;
+        res.reserved    = 0;
+        a.results[job]  = res;
+    }
+}
+
+template <int P>
+svo_status launch_v2(svo_ctx* ctx, int maxF)
+{
+    using G                     = PatchGeo<P>;
+    const svo_align_params& prm = ctx->staged_params;
+    const int nJobs             = ctx->staged_jobs;
+    const int nLevels           = prm.max_level - prm.min_level + 1;
+    const int Fpad              = (maxF + 31) & ~31;
+    const long long job_stride  = 6LL * Fpad + (long long)nLevels * G::ROWW * Fpad;  // floats
+    const size_t need           = (size_t)job_stride * 4 * nJobs;
+    if (need > ctx->scratch2_bytes) {
+        SVO_CUDA(cudaStreamSynchronize(ctx->stream));
+        if (ctx->d_scratch2) SVO_CUDA(cudaFree(ctx->d_scratch2));
+        ctx->d_scratch2     = nullptr;
+        ctx->scratch2_bytes = 0;
+        SVO_CUDA(cudaMalloc(&ctx->d_scratch2, need));
+        ctx->scratch2_bytes = need;
+    }
+    V2Args args;
+    args.view       = make_view(ctx->arena);
+    args.jobs       = ctx->d_jobs;
+    args.feats      = ctx->d_feats;
+    args.results    = ctx->d_results;
+    args.stats      = ctx->staged_want_stats ? ctx->d_stats : nullptr;
+    args.scratch    = ctx->d_scratch2;
+    args.job_stride = job_stride;
+    args.Fpad       = Fpad;
+    args.prm        = prm;
+    for (int i = 0; i < 4; i++) args.K[i] = ctx->cfg.K[i];
+
+    dim3 pgrid((Fpad + 127) / 128, nLevels, nJobs);
+    k_align_precompute<P><<<pgrid, 128, 0, ctx->stream>>>(args);
+    const size_t smem = v2_smem_bytes<P>(Fpad);
+    SVO_CUDA(cudaFuncSetAttribute(k_align_iterate<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_align_iterate<P><<<nJobs, NT, smem, ctx->stream>>>(args);
+    ctx->launches += 2;
+    SVO_CUDA(cudaGetLastError());
+    return SVO_OK;
+}
+
+}  // namespace
+
+// returns true when the fast path handles this batch
+bool sparse_align_v2_supported(const svo_ctx* ctx, int maxF)
+{
+    const svo_align_params& prm = ctx->staged_params;
+    if (prm.patch_size != 4 && prm.patch_size != 5) return false;
+    if (maxF > NT) return false;
+    const int Fpad    = (maxF + 31) & ~31;
+    const size_t smem = prm.patch_size == 5 ? v2_smem_bytes<5>(Fpad) : v2_smem_bytes<4>(Fpad);
+    return smem <= (size_t)ctx->max_smem_optin;
+}
+
+svo_status launch_sparse_align_v2(svo_ctx* ctx, int maxF)
+{
+    return ctx->staged_params.patch_size == 5 ? launch_v2<5>(ctx, maxF) : launch_v2<4>(ctx, maxF);
+}

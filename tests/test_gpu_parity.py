@@ -133,9 +133,19 @@ def _check_levels(stats, lv, synth, faithful):
             assert g["status"] == o["status"] and g["iterations"] == o["iterations"]
 
 
+@pytest.fixture(params=["fast", "generic"])
+def align_path(request, monkeypatch):
+    """Both CUDA implementations of the alignment: the fast path (patch 4/5, <= 512 features) and the generic kernel."""
+    if request.param == "generic":
+        monkeypatch.setenv("SVO_ALIGN_GENERIC", "1")
+    else:
+        monkeypatch.delenv("SVO_ALIGN_GENERIC", raising=False)
+    return request.param
+
+
 @pytest.mark.parametrize("n_features,n_kf,tref", [(499, 0, False), (500, 0, False), (501, 200, False), (300, 100, True),
                                                    (37, 0, False)])
-def test_sparse_align_faithful_parity(pkg, orc, synth, pair_cache, n_features, n_kf, tref):
+def test_sparse_align_faithful_parity(pkg, orc, synth, pair_cache, align_path, n_features, n_kf, tref):
     """LM_FAITHFUL = what the reference does: one damped step per level.  Odd N (499 x 25) is the
     case where the reference's median is well defined; even N checks MEDIAN_EXACT."""
     kw = {}
@@ -160,7 +170,7 @@ def test_sparse_align_faithful_parity(pkg, orc, synth, pair_cache, n_features, n
 
 @pytest.mark.parametrize("mode", ["LM_ITERATED", "GN"])
 @pytest.mark.parametrize("patch", [5, 4])
-def test_sparse_align_iterated_parity(pkg, orc, synth, pair_cache, mode, patch):
+def test_sparse_align_iterated_parity(pkg, orc, synth, pair_cache, align_path, mode, patch):
     pair = pair_cache(2, 500)
     pyr = _pyrs(orc, pair)
     m = getattr(orc, mode)
@@ -189,7 +199,7 @@ def test_sparse_align_identity_motion(pkg, orc, synth, pair_cache):
     assert res[0]["rmse"] < 1e-6
 
 
-def test_sparse_align_edge_cases(pkg, orc, synth, pair_cache):
+def test_sparse_align_edge_cases(pkg, orc, synth, pair_cache, align_path):
     pair = pair_cache(1, 60)
     pyr = _pyrs(orc, pair)
     feats = pair["feats"].copy()
@@ -282,3 +292,23 @@ def test_feature_align_parity(pkg, orc, synth, pair_cache, mode, patch, affine):
             assert ok, (i, r, px, st, it)
     # iterated modes: FP64 both sides, identical algorithm -> identical trajectories, allow a stray tie-break
     assert nbad <= n // 100, nbad
+
+
+def test_sparse_align_generic_sizes(pkg, orc, synth, pair_cache):
+    """Shapes only the generic kernel takes: 7x7 patches, and more than 512 features per pair (config 4: 1,000)."""
+    pair = pair_cache(5, 300)
+    pyr = _pyrs(orc, pair)
+    rmse, T, status, lv = _oracle_align(orc, pair, pyr, orc.LM_FAITHFUL, patch=7)
+    with _ctx(pkg, pair) as ctx:
+        ctx.upload(0, np.stack([pair["ref"], pair["cur"]]))
+        res, stats = ctx.sparse_align(_job(pkg, pair), pair["feats"], mode=pkg.capi.LM_FAITHFUL, patch_size=7)
+    _check_levels(stats[0], lv, synth, True)
+    big = pair_cache(6, 1000, cell=20)
+    assert big["n_ref"] > 900
+    pyr = _pyrs(orc, big)
+    rmse, T, status, lv = _oracle_align(orc, big, pyr, orc.GN, max_iter=30)
+    with _ctx(pkg, big) as ctx:
+        ctx.upload(0, np.stack([big["ref"], big["cur"]]))
+        res, stats = ctx.sparse_align(_job(pkg, big), big["feats"], mode=pkg.capi.GN, max_iter=30)
+    _check_levels(stats[0][:1], lv[:1], synth, False)
+    assert synth.rotation_angle(res[0]["T_cur"], T) < ROT_TOL and np.abs(res[0]["T_cur"][4:] - T[4:]).max() < TRANS_TOL
