@@ -127,6 +127,11 @@ class PinnedBuffer:
         self.ptr = p.value
         self.array = np.ctypeslib.as_array((C.c_uint8 * nbytes).from_address(self.ptr))
 
+    def view(self, dtype, count, offset=0):
+        """A structured-array view (no copy) of `count` records at byte `offset`."""
+        dt = np.dtype(dtype)
+        return self.array[offset:offset + count * dt.itemsize].view(dt)
+
     def free(self):
         if self.ptr:
             self._ctx.L.svo_host_free(self._ctx.h, self.ptr)

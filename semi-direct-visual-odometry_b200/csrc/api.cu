@@ -15,7 +15,7 @@ thread_local std::string g_create_error;
 inline int64_t round_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 // staging ring for pageable host images: two halves so the CPU copy of chunk i+1 overlaps the DMA of chunk i
-constexpr int kStageFrames = 16;
+constexpr int kStageFrames = 32;
 
 void release(svo_ctx* ctx)
 {
@@ -26,10 +26,14 @@ void release(svo_ctx* ctx)
         if (ctx->arena.img[l]) cudaFree(ctx->arena.img[l]);
         if (ctx->arena.grad[l]) cudaFree(ctx->arena.grad[l]);
     }
+    if (ctx->copy_stream) cudaStreamSynchronize(ctx->copy_stream);
     for (int i = 0; i < 2; i++) {
         if (ctx->h_img_stage[i]) cudaFreeHost(ctx->h_img_stage[i]);
-        if (ctx->img_stage_free[i]) cudaEventDestroy(ctx->img_stage_free[i]);
+        if (ctx->d_img_stage[i]) cudaFree(ctx->d_img_stage[i]);
+        if (ctx->ev_h2d[i]) cudaEventDestroy(ctx->ev_h2d[i]);
+        if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]);
     }
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     cudaFree(ctx->d_cell_best);
     cudaFree(ctx->d_occupancy);
     cudaFree(ctx->d_sel_out);
@@ -90,10 +94,14 @@ svo_status init(svo_ctx* ctx)
         w = (w + 1) / 2;  // cv::pyrDown default size, src/image_pyramid.cpp:49-50
         h = (h + 1) / 2;
     }
-    ctx->h_img_stage_bytes = (int64_t)a.geom[0].plane_stride * std::min(kStageFrames, c.max_frames);
+    SVO_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    ctx->stage_frames = std::min(kStageFrames, c.max_frames);
+    const size_t stage_bytes = (size_t)c.width * c.height * ctx->stage_frames + 64;
     for (int i = 0; i < 2; i++) {
-        SVO_CUDA(cudaHostAlloc(&ctx->h_img_stage[i], ctx->h_img_stage_bytes, cudaHostAllocDefault));
-        SVO_CUDA(cudaEventCreateWithFlags(&ctx->img_stage_free[i], cudaEventDisableTiming));
+        SVO_CUDA(cudaHostAlloc(&ctx->h_img_stage[i], stage_bytes, cudaHostAllocDefault));
+        SVO_CUDA(cudaMalloc(&ctx->d_img_stage[i], stage_bytes));
+        SVO_CUDA(cudaEventCreateWithFlags(&ctx->ev_h2d[i], cudaEventDisableTiming));
+        SVO_CUDA(cudaEventCreateWithFlags(&ctx->ev_consumed[i], cudaEventDisableTiming));
     }
     ctx->stage_next = 0;
 
@@ -234,40 +242,44 @@ svo_status svo_frames_upload(svo_ctx* ctx, int first_slot, int n, const uint8_t*
     cudaPointerAttributes attr;
     const bool pinned = cudaPointerGetAttributes(&attr, imgs) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
-    if (pinned) {
-        // caller's buffer is page-locked (svo_host_alloc): DMA straight from it.  When both sides are dense stacks
-        // of frames the whole batch is ONE 2D copy of n*h rows.
-        if (g.plane_stride == (int64_t)g.pitch * g.h && (n == 1 || frame_stride == (int64_t)pitch * g.h))
-            SVO_CUDA(cudaMemcpy2DAsync(ctx->arena.img[0] + (int64_t)first_slot * g.plane_stride, g.pitch, imgs, pitch, g.w,
-                                       (size_t)g.h * n, cudaMemcpyHostToDevice, ctx->stream));
-        else
-        for (int i = 0; i < n; i++)
-            SVO_CUDA(cudaMemcpy2DAsync(ctx->arena.img[0] + (int64_t)(first_slot + i) * g.plane_stride, g.pitch,
-                                       imgs + (int64_t)i * frame_stride, pitch, g.w, g.h, cudaMemcpyHostToDevice,
-                                       ctx->stream));
-    } else {
-        const int chunk = (int)(ctx->h_img_stage_bytes / g.plane_stride);
-        for (int i0 = 0; i0 < n; i0 += chunk) {
-            const int m   = std::min(chunk, n - i0);
-            const int buf = ctx->stage_next;
-            ctx->stage_next ^= 1;
-            SVO_CUDA(cudaEventSynchronize(ctx->img_stage_free[buf]));
+    const bool dense       = pitch == g.w && (n == 1 || frame_stride == (int64_t)g.w * g.h);
+    const int64_t frame_sz = (int64_t)g.w * g.h;
+    // Chunked pipeline: the DMA of chunk i+1 (copy stream) overlaps k_repack + the pyramid kernels of chunk i (main
+    // stream).  PCIe moves DENSE bytes in one 1-D transfer per chunk; the pitched arena layout is made on the device.
+    for (int i0 = 0; i0 < n; i0 += ctx->stage_frames) {
+        const int m   = std::min(ctx->stage_frames, n - i0);
+        const int buf = ctx->stage_next;
+        ctx->stage_next ^= 1;
+        const uint8_t* src = imgs + (int64_t)i0 * frame_stride;
+        SVO_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_consumed[buf], 0));  // device buffer free again
+        if (pinned && dense) {
+            SVO_CUDA(cudaMemcpyAsync(ctx->d_img_stage[buf], src, (size_t)m * frame_sz, cudaMemcpyHostToDevice, ctx->copy_stream));
+        } else if (pinned) {
+            for (int i = 0; i < m; i++)
+                SVO_CUDA(cudaMemcpy2DAsync(ctx->d_img_stage[buf] + (int64_t)i * frame_sz, g.w, src + (int64_t)i * frame_stride, pitch,
+                                           g.w, g.h, cudaMemcpyHostToDevice, ctx->copy_stream));
+        } else {
+            SVO_CUDA(cudaEventSynchronize(ctx->ev_h2d[buf]));  // the pinned half is no longer being read
             uint8_t* st = ctx->h_img_stage[buf];
             for (int i = 0; i < m; i++) {
-                const uint8_t* src = imgs + (int64_t)(i0 + i) * frame_stride;
-                uint8_t* dst       = st + (int64_t)i * g.plane_stride;
-                if (pitch == g.pitch)
-                    std::memcpy(dst, src, (size_t)pitch * g.h);
+                const uint8_t* fs = src + (int64_t)i * frame_stride;
+                uint8_t* fd       = st + (int64_t)i * frame_sz;
+                if (pitch == g.w)
+                    std::memcpy(fd, fs, (size_t)frame_sz);
                 else
-                    for (int y = 0; y < g.h; y++) std::memcpy(dst + (int64_t)y * g.pitch, src + (int64_t)y * pitch, g.w);
+                    for (int y = 0; y < g.h; y++) std::memcpy(fd + (int64_t)y * g.w, fs + (int64_t)y * pitch, g.w);
             }
-            // staged planes have the device layout: one contiguous copy per chunk
-            SVO_CUDA(cudaMemcpyAsync(ctx->arena.img[0] + (int64_t)(first_slot + i0) * g.plane_stride, st,
-                                     (size_t)m * g.plane_stride, cudaMemcpyHostToDevice, ctx->stream));
-            SVO_CUDA(cudaEventRecord(ctx->img_stage_free[buf], ctx->stream));
+            SVO_CUDA(cudaMemcpyAsync(ctx->d_img_stage[buf], st, (size_t)m * frame_sz, cudaMemcpyHostToDevice, ctx->copy_stream));
         }
+        SVO_CUDA(cudaEventRecord(ctx->ev_h2d[buf], ctx->copy_stream));
+        SVO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[buf], 0));
+        svo_status st = launch_repack(ctx, ctx->d_img_stage[buf], g.w, frame_sz, first_slot + i0, m);
+        if (st != SVO_OK) return st;
+        SVO_CUDA(cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));
+        st = launch_pyramid_build(ctx, first_slot + i0, m);
+        if (st != SVO_OK) return st;
     }
-    return launch_pyramid_build(ctx, first_slot, n);
+    return SVO_OK;
 }
 
 svo_status svo_frames_upload_device(svo_ctx* ctx, int first_slot, int n, const void* dptr, int pitch, int64_t frame_stride)
@@ -278,10 +290,10 @@ svo_status svo_frames_upload_device(svo_ctx* ctx, int first_slot, int n, const v
     if (!dptr || n < 0 || bad_slot(ctx, first_slot) || bad_slot(ctx, first_slot + n - 1) || pitch < g.w)
         SVO_FAIL(SVO_ERR_INVALID, "svo_frames_upload_device: bad slot range or pitch");
     SVO_CUDA(cudaSetDevice(ctx->cfg.device));
-    for (int i = 0; i < n; i++)
-        SVO_CUDA(cudaMemcpy2DAsync(ctx->arena.img[0] + (int64_t)(first_slot + i) * g.plane_stride, g.pitch,
-                                   (const uint8_t*)dptr + (int64_t)i * frame_stride, pitch, g.w, g.h,
-                                   cudaMemcpyDeviceToDevice, ctx->stream));
+    {
+        const svo_status st = launch_repack(ctx, (const uint8_t*)dptr, pitch, frame_stride, first_slot, n);
+        if (st != SVO_OK) return st;
+    }
     return launch_pyramid_build(ctx, first_slot, n);
 }
 
@@ -369,8 +381,24 @@ svo_status svo_sparse_align_stage(svo_ctx* ctx, const svo_align_job* jobs, int n
     if (st != SVO_OK) return st;
     // the pinned buffers may still be read by the previous batch's H2D
     SVO_CUDA(cudaStreamSynchronize(ctx->stream));
-    std::memcpy(ctx->h_jobs, jobs, sizeof(svo_align_job) * n_jobs);
-    if (n_feats) std::memcpy(ctx->h_feats, feats, sizeof(svo_align_feature) * n_feats);
+    // page-locked caller buffers (svo_host_alloc) are DMA'd in place -- they must stay untouched until the fetch;
+    // pageable ones are copied to the context's pinned mirrors first
+    auto is_pinned = [](const void* p) {
+        cudaPointerAttributes at;
+        const bool ok = cudaPointerGetAttributes(&at, p) == cudaSuccess && at.type == cudaMemoryTypeHost;
+        cudaGetLastError();
+        return ok;
+    };
+    ctx->src_jobs  = jobs;
+    ctx->src_feats = feats;
+    if (!is_pinned(jobs)) {
+        std::memcpy(ctx->h_jobs, jobs, sizeof(svo_align_job) * n_jobs);
+        ctx->src_jobs = ctx->h_jobs;
+    }
+    if (n_feats && !is_pinned(feats)) {
+        std::memcpy(ctx->h_feats, feats, sizeof(svo_align_feature) * n_feats);
+        ctx->src_feats = ctx->h_feats;
+    }
     ctx->staged_jobs       = n_jobs;
     ctx->staged_feats      = n_feats;
     ctx->staged_levels     = prm->max_level - prm->min_level + 1;
@@ -383,10 +411,10 @@ svo_status svo_sparse_align_h2d(svo_ctx* ctx)
 {
     if (!ctx) return SVO_ERR_INVALID;
     if (ctx->staged_jobs == 0) return SVO_OK;
-    SVO_CUDA(cudaMemcpyAsync(ctx->d_jobs, ctx->h_jobs, sizeof(svo_align_job) * ctx->staged_jobs, cudaMemcpyHostToDevice,
+    SVO_CUDA(cudaMemcpyAsync(ctx->d_jobs, ctx->src_jobs, sizeof(svo_align_job) * ctx->staged_jobs, cudaMemcpyHostToDevice,
                              ctx->stream));
     if (ctx->staged_feats)
-        SVO_CUDA(cudaMemcpyAsync(ctx->d_feats, ctx->h_feats, sizeof(svo_align_feature) * ctx->staged_feats,
+        SVO_CUDA(cudaMemcpyAsync(ctx->d_feats, ctx->src_feats, sizeof(svo_align_feature) * ctx->staged_feats,
                                  cudaMemcpyHostToDevice, ctx->stream));
     return SVO_OK;
 }

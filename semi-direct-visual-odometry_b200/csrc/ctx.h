@@ -39,9 +39,15 @@ struct svo_ctx {
     PyramidArena arena;
 
     // pinned staging for image upload
-    uint8_t* h_img_stage[2];     // two halves: CPU copy of chunk i+1 overlaps the DMA of chunk i
-    int64_t h_img_stage_bytes;   // per half
-    cudaEvent_t img_stage_free[2];  // recorded after the last H2D that read the half
+    // frame ingest pipeline: host -> (pinned staging, pageable sources only) -> dense device staging on the copy
+    // stream -> k_repack + pyramid kernels on the main stream; two buffers so the DMA of chunk i+1 overlaps the
+    // kernels of chunk i
+    cudaStream_t copy_stream;
+    uint8_t* h_img_stage[2];     // pinned, dense frames
+    uint8_t* d_img_stage[2];     // device, dense frames (+ slack)
+    int stage_frames;            // frames per buffer
+    cudaEvent_t ev_h2d[2];       // copy stream: chunk landed in d_img_stage[b]
+    cudaEvent_t ev_consumed[2];  // main stream: k_repack has read d_img_stage[b]
     int stage_next;
 
     // selection
@@ -71,6 +77,8 @@ struct svo_ctx {
     float* d_scratch2;           // fast path: per job world points + per level template blocks
     size_t scratch2_bytes;
     int staged_jobs, staged_feats, staged_levels, staged_want_stats;
+    const svo_align_job* src_jobs;      // where the H2D of the staged batch reads from (pinned user memory or h_jobs)
+    const svo_align_feature* src_feats;
     svo_align_params staged_params;
 
     // feature alignment batch
@@ -114,6 +122,7 @@ inline ArenaView make_view(const PyramidArena& a)
 
 // kernel launchers (defined in the .cu files)
 svo_status launch_pyramid_build(svo_ctx* ctx, int first_slot, int n);
+svo_status launch_repack(svo_ctx* ctx, const uint8_t* dsrc, long long src_pitch, long long src_frame_stride, int first_slot, int n);
 svo_status launch_grid_select(svo_ctx* ctx, int slot, int cell, uint32_t thr, int rows, int cols);
 svo_status launch_sparse_align(svo_ctx* ctx);
 svo_status launch_feature_align(svo_ctx* ctx);

@@ -46,6 +46,38 @@ __global__ void __launch_bounds__(128) k_abs_gradient(const uint8_t* __restrict_
     *reinterpret_cast<uint32_t*>(d + (long long)y * pitch + x0) = out;
 }
 
+// Dense (arbitrary pitch / alignment) source frames -> level 0 of the arena (16-B aligned pitched rows).
+// One thread = 16 output bytes: five aligned 32-bit source words, funnel-shifted into place, one 128-bit store.
+// grid: (ceil(pitch/16/128), h, n_frames)
+__global__ void __launch_bounds__(128) k_repack(const uint8_t* __restrict__ src, long long src_pitch, long long src_frame_stride,
+                                                uint8_t* __restrict__ dst, int w, int h, int pitch, long long plane_stride)
+{
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * 16;
+    const int y  = blockIdx.y;
+    if (x0 >= pitch) return;
+    const uint8_t* s    = src + (long long)blockIdx.z * src_frame_stride + (long long)y * src_pitch + x0;
+    const uintptr_t ad  = reinterpret_cast<uintptr_t>(s);
+    const uint32_t* s4  = reinterpret_cast<const uint32_t*>(ad & ~uintptr_t(3));
+    const int off       = (int)(ad & 3u);
+    const uint32_t sh   = (uint32_t)off * 8u;
+    const int valid     = min(16, w - x0);  // bytes of this segment inside the image (<= 0: pure padding)
+    const int need      = valid > 0 ? off + valid : 0;
+    uint32_t v[5];
+#pragma unroll
+    for (int i = 0; i < 5; i++) v[i] = (i * 4 < need) ? __ldg(s4 + i) : 0u;  // never read a word without a needed byte
+    uint32_t o[4];
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        o[i] = __funnelshift_r(v[i], v[i + 1], sh);
+        const int rem = valid - 4 * i;  // valid bytes in this word
+        if (rem <= 0)
+            o[i] = 0u;
+        else if (rem < 4)
+            o[i] &= (1u << (8 * rem)) - 1u;
+    }
+    *reinterpret_cast<uint4*>(dst + (long long)blockIdx.z * plane_stride + (long long)y * pitch + x0) = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 __device__ __forceinline__ int reflect101(int i, int n)
 {
     if (n == 1) return 0;
@@ -123,6 +155,17 @@ svo_status launch_pyramid_build(svo_ctx* ctx, int first_slot, int n)
                                                  s.plane_stride, d.w, d.h, d.pitch, d.plane_stride);
         ctx->launches++;
     }
+    SVO_CUDA(cudaGetLastError());
+    return SVO_OK;
+}
+
+svo_status launch_repack(svo_ctx* ctx, const uint8_t* dsrc, long long src_pitch, long long src_frame_stride, int first_slot, int n)
+{
+    const LevelGeom& g = ctx->arena.geom[0];
+    dim3 grid((g.pitch / 16 + 127) / 128, g.h, n);
+    k_repack<<<grid, 128, 0, ctx->stream>>>(dsrc, src_pitch, src_frame_stride, ctx->arena.img[0] + (int64_t)first_slot * g.plane_stride,
+                                            g.w, g.h, g.pitch, g.plane_stride);
+    ctx->launches++;
     SVO_CUDA(cudaGetLastError());
     return SVO_OK;
 }

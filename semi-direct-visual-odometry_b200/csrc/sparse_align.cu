@@ -721,7 +721,7 @@ svo_status launch_sparse_align(svo_ctx* ctx)
     if (nJobs == 0) return SVO_OK;
     // feature capacity of this launch: the largest job, rounded up (keeps shared memory small for small jobs)
     int maxF = 1;
-    for (int j = 0; j < nJobs; j++) maxF = std::max(maxF, ctx->h_jobs[j].n_ref + ctx->h_jobs[j].n_kf);
+    for (int j = 0; j < nJobs; j++) maxF = std::max(maxF, ctx->src_jobs[j].n_ref + ctx->src_jobs[j].n_kf);
     // fast path (sparse_align_v2.cu): patch 4 / 5, <= 512 features per pair.  SVO_ALIGN_GENERIC=1 forces the generic
     // kernel below (A/B measurements); both are CUDA paths -- there is no CPU fallback anywhere.
     {
