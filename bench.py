@@ -222,6 +222,9 @@ def run_b200(a, rank, world):
         alg_bytes = float((nvis * ((PATCH + 3) ** 2 + ev * (PATCH + 1) ** 2)).sum() + 32.0 * batch["n_feat"].sum()
                           + 256.0 * LEVELS * n)                                   # SURVEY 8(d) formula, per launch
         evals_total = int(res["evaluations"].sum())
+        tiers = res["reserved"].astype(np.int64)  # fast-path diagnostics: selections served hot | cold << 8 | generic << 16
+        sel_tiers = {"hot": int((tiers & 0xff).sum()), "cold": int(((tiers >> 8) & 0xff).sum()),
+                     "generic": int(((tiers >> 16) & 0xff).sum())}
 
         gather_buf = None
         if world > 1:
@@ -327,6 +330,7 @@ def run_b200(a, rank, world):
             "us_per_pair": 1e6 / value,
             "latency_us_single_pair": lat_us,
             "evaluations_per_pair": evals_total / n,
+            "sigma_selections": sel_tiers,
             "accuracy": {"median_rot_err_rad": float(np.median(rot_err)), "median_trans_err_m": float(np.median(tr_err)),
                          "pairs_within_1e-3rad_1e-2m": float(np.mean((rot_err < 1e-3) & (tr_err < 1e-2)))},
             "gpu_launches": int(launches),

@@ -183,6 +183,9 @@ svo_status svo_sparse_align_fetch(svo_ctx* ctx, svo_align_result* results, svo_a
 /* device copy of the last batch's svo_align_result records (valid once the launch has completed on the stream):
  * what a multi-GPU caller hands to its final pose gather (ncclGather) without a host round trip */
 const void* svo_sparse_align_results_device(const svo_ctx* ctx);
+/* diagnostics: per level (8 slots each, coarse to fine) SM-clock cycles job 0 of the last fast-path launch spent in
+ * [0] warp+sample [1] median select [2] MAD select [3] weights+sums [4] reductions [5] solve [6] #evaluations */
+svo_status svo_debug_cycles(svo_ctx* ctx, int64_t* out64);
 
 /* ---------------------------------------------------------------------------------------------
  * FeatureAlignment::align(refFeature, curFrame, pixelPos) (src/feature_alignment.cpp:25-62),

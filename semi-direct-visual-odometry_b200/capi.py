@@ -22,7 +22,7 @@ SYMBOLS = [
     "svo_host_alloc", "svo_host_free", "svo_level_dims", "svo_frames_upload", "svo_frames_upload_device",
     "svo_frames_rebuild", "svo_frame_download", "svo_select_grid", "svo_sparse_align", "svo_sparse_align_stage",
     "svo_sparse_align_h2d", "svo_sparse_align_launch", "svo_sparse_align_d2h", "svo_sparse_align_fetch",
-    "svo_sparse_align_results_device",
+    "svo_sparse_align_results_device", "svo_debug_cycles",
     "svo_feature_align", "svo_feature_align_stage", "svo_feature_align_h2d", "svo_feature_align_launch",
     "svo_feature_align_d2h", "svo_feature_align_fetch",
 ]
@@ -105,6 +105,7 @@ def load():
         getattr(L, "svo_feature_align_" + n).argtypes = [vp]
     L.svo_sparse_align_fetch.argtypes = [vp, vp, vp]
     L.svo_sparse_align_results_device.argtypes = [vp]
+    L.svo_debug_cycles.argtypes = [vp, vp]
     L.svo_sparse_align_results_device.restype = vp
     L.svo_feature_align.argtypes = [vp, vp, i, C.POINTER(FaParams), vp]
     L.svo_feature_align_stage.argtypes = [vp, vp, i, C.POINTER(FaParams)]
@@ -269,6 +270,11 @@ class Context:
         stats = np.zeros((n, nl), ALIGN_STATS_DTYPE) if ws else None
         self._check(self.L.svo_sparse_align_fetch(self.h, _ptr(res), _ptr(stats)))
         return res, stats
+
+    def debug_cycles(self):
+        out = np.zeros((8, 8), np.int64)
+        self._check(self.L.svo_debug_cycles(self.h, _ptr(out)))
+        return out
 
     @property
     def results_device_ptr(self):

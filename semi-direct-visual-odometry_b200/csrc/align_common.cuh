@@ -35,16 +35,28 @@ __device__ __forceinline__ void set_Rt(Ctrl* c)
     c->t[2] = c->pose.t[2];
 }
 
-__device__ void expand_H(const double* E, double* H, double* g)
+__device__ __forceinline__ void expand_H(const double* E, double* H, double* g)
 {
     int k = 0;
+#pragma unroll
     for (int a = 0; a < 6; a++)
+#pragma unroll
         for (int b = a; b < 6; b++, k++) {
             H[a * 6 + b] = E[k];
             H[b * 6 + a] = E[k];
         }
+#pragma unroll
     for (int a = 0; a < 6; a++) g[a] = E[21 + a];
 }
 
+// dx = (H + diag_add I)^-1 g with H, g packed in E (21 + 6): register-resident fast path, pivoted LDLT fallback
+__device__ __forceinline__ void solve6(const double* E, double diag_add, double* dx)
+{
+    if (svo::ldlt6_nopivot(E, diag_add, E + 21, dx)) return;
+    double H[36], g[6];
+    expand_H(E, H, g);
+    for (int i = 0; i < 6; i++) H[i * 6 + i] += diag_add;
+    svo::ldlt_solve<6>(H, g, dx);
+}
 
 }  // namespace

@@ -52,6 +52,7 @@ void release(svo_ctx* ctx)
     cudaFree(ctx->d_scratch_tpl);
     cudaFree(ctx->d_scratch_jac);
     cudaFree(ctx->d_scratch2);
+    cudaFree(ctx->d_dbg);
     cudaFreeHost(ctx->h_fa_items);
     cudaFreeHost(ctx->h_fa_results);
     cudaFree(ctx->d_fa_items);
@@ -128,6 +129,8 @@ svo_status init(svo_ctx* ctx)
     SVO_CUDA(cudaMalloc(&ctx->d_stats, sizeof(svo_align_level_stats) * nj * c.levels));
     SVO_CUDA(cudaMalloc(&ctx->d_scratch_jac, sizeof(float) * 12 * ctx->feats_cap));
     ctx->scratch_area = 0;
+    SVO_CUDA(cudaMalloc(&ctx->d_dbg, 64 * sizeof(long long)));
+    SVO_CUDA(cudaMemsetAsync(ctx->d_dbg, 0, 64 * sizeof(long long), ctx->stream));
 
     // ---- feature alignment ----
     const int64_t nf = std::max(1, c.max_fa_items);
@@ -447,6 +450,14 @@ svo_status svo_sparse_align_fetch(svo_ctx* ctx, svo_align_result* results, svo_a
         if (!ctx->staged_want_stats) SVO_FAIL(SVO_ERR_INVALID, "svo_sparse_align_fetch: stats were not requested at stage");
         std::memcpy(stats, ctx->h_stats, sizeof(svo_align_level_stats) * ctx->staged_jobs * ctx->staged_levels);
     }
+    return SVO_OK;
+}
+
+svo_status svo_debug_cycles(svo_ctx* ctx, int64_t* out64)
+{
+    if (!ctx || !out64) return SVO_ERR_INVALID;
+    SVO_CUDA(cudaStreamSynchronize(ctx->stream));
+    SVO_CUDA(cudaMemcpy(out64, ctx->d_dbg, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
     return SVO_OK;
 }
 

@@ -74,6 +74,7 @@ struct svo_ctx {
     float* d_scratch_jac;        // [job][F][12]   image Jacobian rows per feature
     int64_t feats_cap;
     int scratch_area;            // patch area d_scratch_tpl is sized for
+    long long* d_dbg;            // 64 per-phase cycle counters of job 0 (diagnostics)
     float* d_scratch2;           // fast path: per job world points + per level template blocks
     size_t scratch2_bytes;
     int staged_jobs, staged_feats, staged_levels, staged_want_stats;

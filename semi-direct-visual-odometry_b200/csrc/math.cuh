@@ -165,6 +165,71 @@ __device__ inline void ldlt_solve(double* A, const double* b, double* x)
     for (int i = 0; i < N; i++) x[perm[i]] = y[i];
 }
 
+// Fast path of the 6x6 solve: LDL^T without pivoting, fully unrolled so the whole factorisation lives in registers.
+// E: upper triangle of the symmetric matrix, row-major (21 values); diag_add is added to the diagonal (LM damping).
+// Returns false when a pivot is not safely positive (semi-definite / degenerate systems): the caller then falls back
+// to ldlt_solve, which reproduces Eigen's pivoted LDLT including its zero-pivot rule.  For the well-conditioned SPD
+// systems of the alignment both agree to rounding.
+__device__ __forceinline__ bool ldlt6_nopivot(const double* E, double diag_add, const double* b, double* x)
+{
+    double A[6][6];
+    {
+        int k = 0;
+#pragma unroll
+        for (int i = 0; i < 6; i++)
+#pragma unroll
+            for (int j = i; j < 6; j++, k++) A[j][i] = E[k];  // lower triangle
+    }
+    double scale = 0.0;
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        A[i][i] += diag_add;
+        scale = fmax(scale, fabs(A[i][i]));
+    }
+    const double tiny = scale * 1e-13;
+    double D[6], invD[6];
+    bool ok = scale > 0.0 && isfinite(scale);
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        double v[6];
+        double d = A[j][j];
+#pragma unroll
+        for (int i = 0; i < j; i++) {
+            v[i] = A[j][i] * D[i];
+            d -= A[j][i] * v[i];
+        }
+        D[j]    = d;
+        ok      = ok && (d > tiny);
+        invD[j] = 1.0 / d;
+#pragma unroll
+        for (int r = j + 1; r < 6; r++) {
+            double sacc = A[r][j];
+#pragma unroll
+            for (int i = 0; i < j; i++) sacc -= A[r][i] * v[i];
+            A[r][j] = sacc * invD[j];
+        }
+    }
+    if (!ok) return false;
+    double y[6];
+#pragma unroll
+    for (int i = 0; i < 6; i++) {
+        double sacc = b[i];
+#pragma unroll
+        for (int j = 0; j < i; j++) sacc -= A[i][j] * y[j];
+        y[i] = sacc;
+    }
+#pragma unroll
+    for (int i = 0; i < 6; i++) y[i] *= invD[i];
+#pragma unroll
+    for (int i = 5; i >= 0; i--) {
+        double sacc = y[i];
+#pragma unroll
+        for (int j = i + 1; j < 6; j++) sacc -= A[j][i] * x[j];
+        x[i] = sacc;
+    }
+    return true;
+}
+
 // Optimizer::updateParameters, Nielsen branch (src/optimizer.cpp:449-466)
 __device__ __forceinline__ bool nielsen_update(double pre, double cur, double& lambda, double& nu)
 {

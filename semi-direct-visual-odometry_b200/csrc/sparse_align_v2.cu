@@ -50,6 +50,7 @@ struct V2Args {
     int Fpad;                      // features per job rounded up (multiple of 32, <= NT)
     svo_align_params prm;
     double K[4];
+    long long* dbg;                // nullable: per-phase cycle counters of job 0 (svo_debug_cycles)
 };
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -158,8 +159,8 @@ struct SelSmem {
     uint32_t* priv;    // [16][NT] thread-private packed 8-bit counters (64 bins), zero between uses
     uint32_t* bins;    // [512] shared counters for the atomic passes, zero between uses
     uint32_t* tot;     // [64] bin totals of a private pass
-    uint32_t* wtot;    // [NW]
-    uint32_t* sel;     // [2] chosen digit, remaining rank
+    uint32_t* wtot;    // [4][NW] per-warp partials (count inside, count below, max below, last non-empty bin)
+    uint32_t* sel;     // [4] chosen digit, remaining rank, predecessor bin
 };
 
 // one pass over 6 bits with thread-private counters.  keys: AREA values; live: participates at all
@@ -300,6 +301,308 @@ __device__ __forceinline__ uint32_t block_max_below27(const int (&q)[AREA], bool
     return out;
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// tiered selection.  The generic 4-pass select above sweeps all 25 keys of every thread 4-5 times with ~10 integer
+// instructions per key and pass; the integer pipes issue at half rate, which made sigma half of the kernel.  Two
+// cheaper tiers come first:
+//   hot   the target of the previous evaluation (median or MAD key) brackets this one: ONE sweep counts the keys
+//         below the bracket and histograms (512 shared atomic counters) the few that fall inside; a second sweep
+//         resolves the chosen bin to a single key.  Keys outside the bracket cost 4-5 instructions and no memory.
+//   cold  one sweep with thread-private counters over 64 coarse bins (1 intensity unit for the median, 1/2 for the
+//         MAD) finds the coarse bin, then the hot machinery runs on exactly that bin.
+//   generic  targets outside the coarse range fall back to block_select27.
+// All tiers are exact on the fixed-point keys; only the work differs.
+// ------------------------------------------------------------------------------------------------------------
+struct Bracket {   // uniform per CTA (every thread holds the same values)
+    uint32_t center;
+    int shift;     // log2 of the bin width of the first sweep; bracket = center -/+ (256 << shift)
+    bool valid;
+};
+
+// Sweep A of a bracketed select: 512 bins of width 2^shift starting at lo; counts the keys below lo.  Straight-line
+// per key except for the (rare) shared atomic.  Returns 0 and (bin, rank inside the bin, last non-empty bin before
+// it or 0xffffffff) on a hit, -1 / +1 when the k-th key lies below / above the bracket.
+template <int AREA, class KeyFn>
+__device__ __forceinline__ int bracket_sweep_a(const int (&q)[AREA], bool live, KeyFn key, uint32_t lo, int shift, int k,
+                                               const SelSmem& s, uint32_t* binOut, int* rankOut, uint32_t* predBin)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    uint32_t below = 0;
+    if (live) {
+#pragma unroll
+        for (int i = 0; i < AREA; i++) {
+            const uint32_t t = key(q[i]) - lo;  // keys below lo wrap to >= 2^31 (keys are < 2^27)
+            below += t >> 31;
+            if ((t >> shift) < 512u) atomicAdd(&s.bins[t >> shift], 1u);
+        }
+    }
+    below = __reduce_add_sync(FULL, below);
+    if (lane == 0) s.wtot[NW + warp] = below;
+    __syncthreads();
+    const uint32_t c = s.bins[tid];
+    s.bins[tid]      = 0;
+    uint32_t incl    = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const uint32_t nz = __ballot_sync(FULL, c != 0);
+    if (lane == 31) {
+        s.wtot[warp]          = incl;
+        s.wtot[3 * NW + warp] = nz ? (uint32_t)(warp * 32 + 31 - __clz(nz)) : 0xffffffffu;  // last non-empty bin of the warp
+    }
+    __syncthreads();
+    const uint32_t wi = lane < NW ? s.wtot[lane] : 0u;
+    const uint32_t wb = lane < NW ? s.wtot[NW + lane] : 0u;
+    const uint32_t inside   = __reduce_add_sync(FULL, wi);
+    const uint32_t base     = __reduce_add_sync(FULL, lane < warp ? wi : 0u);
+    const uint32_t totBelow = __reduce_add_sync(FULL, wb);
+    const int kin = k - (int)totBelow;
+    if (kin < 0) return -1;
+    if (kin >= (int)inside) return 1;
+    const uint32_t excl = base + incl - c;
+    if ((uint32_t)kin >= excl && (uint32_t)kin < excl + c) {
+        s.sel[0] = tid;
+        s.sel[1] = (uint32_t)kin - excl;
+        const uint32_t lower = nz & ((1u << lane) - 1u);
+        uint32_t pb          = 0xffffffffu;
+        if (lower) {
+            pb = (uint32_t)(warp * 32 + 31 - __clz(lower));
+        } else {
+            for (int w = warp - 1; w >= 0; w--) {
+                const uint32_t lb = s.wtot[3 * NW + w];
+                if (lb != 0xffffffffu) {
+                    pb = lb;
+                    break;
+                }
+            }
+        }
+        s.sel[2] = pb;
+    }
+    __syncthreads();
+    *binOut  = s.sel[0];
+    *rankOut = (int)s.sel[1];
+    *predBin = s.sel[2];
+    return 0;
+}
+
+// Sweep B: the chosen bin [lo2, lo2 + W), W <= 128, resolved to single keys.  The 512 unit bins start up to 287 keys
+// BELOW lo2, so that the predecessor of the target (needed for the even-count median rule) is normally inside the
+// window too.  rankA = rank of the target among the keys >= lo2.  Returns the key, its rank among equal keys and the
+// predecessor key (hasPred false: the predecessor lies below the window).
+template <int AREA, class KeyFn>
+__device__ __forceinline__ void bracket_sweep_b(const int (&q)[AREA], bool live, KeyFn key, uint32_t lo2, int rankA, const SelSmem& s,
+                                                uint32_t* keyOut, int* rankOut, uint32_t* predOut, bool* hasPred)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t ws  = lo2 >= 256u ? ((lo2 - 256u) & ~31u) : 0u;  // window start
+    const uint32_t off = lo2 - ws;                                   // 0 .. 287
+    if (live) {
+#pragma unroll
+        for (int i = 0; i < AREA; i++) {
+            const uint32_t t = key(q[i]) - ws;
+            if (t < 512u) atomicAdd(&s.bins[t], 1u);
+        }
+    }
+    __syncthreads();
+    const uint32_t c = s.bins[tid];
+    s.bins[tid]      = 0;
+    uint32_t incl    = c;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const uint32_t nz = __ballot_sync(FULL, c != 0);
+    if (lane == 31) {
+        s.wtot[warp]          = incl;
+        s.wtot[3 * NW + warp] = nz ? (uint32_t)(warp * 32 + 31 - __clz(nz)) : 0xffffffffu;
+    }
+    if ((uint32_t)tid == off) s.sel[3] = incl - c;  // keys of this warp's bins before lo2
+    __syncthreads();
+    const uint32_t wi   = lane < NW ? s.wtot[lane] : 0u;
+    const uint32_t base = __reduce_add_sync(FULL, lane < warp ? wi : 0u);
+    const uint32_t P    = __reduce_add_sync(FULL, (uint32_t)lane < (off >> 5) ? wi : 0u) + s.sel[3];  // keys in [ws, lo2)
+    const uint32_t kin  = P + (uint32_t)rankA;
+    const uint32_t excl = base + incl - c;
+    if (kin >= excl && kin < excl + c) {
+        s.sel[0] = tid;
+        s.sel[1] = kin - excl;
+        const uint32_t lower = nz & ((1u << lane) - 1u);
+        uint32_t pb          = 0xffffffffu;
+        if (lower) {
+            pb = (uint32_t)(warp * 32 + 31 - __clz(lower));
+        } else {
+            for (int w = warp - 1; w >= 0; w--) {
+                const uint32_t lb = s.wtot[3 * NW + w];
+                if (lb != 0xffffffffu) {
+                    pb = lb;
+                    break;
+                }
+            }
+        }
+        s.sel[2] = pb;
+    }
+    __syncthreads();
+    *keyOut  = ws + s.sel[0];
+    *rankOut = (int)s.sel[1];
+    *hasPred = s.sel[1] > 0 || s.sel[2] != 0xffffffffu;
+    *predOut = s.sel[1] > 0 ? ws + s.sel[0] : ws + s.sel[2];
+}
+
+// Bracketed exact select: sweep A with bins of 2^shift from lo, then (shift > 0) sweep B over the chosen bin.  On a
+// hit: *keyOut = the k-th smallest key, *predOut = the (k-1)-th smallest (valid when needPred and k > 0).
+template <int AREA, class KeyFn>
+__device__ __forceinline__ int bracket_select(const int (&q)[AREA], bool live, KeyFn key, uint32_t lo, int shift, int k, bool needPred,
+                                              const SelSmem& s, uint32_t* keyOut, uint32_t* predOut)
+{
+    uint32_t bin, pbin;
+    int rank;
+    const int rc = bracket_sweep_a<AREA>(q, live, key, lo, shift, k, s, &bin, &rank, &pbin);
+    if (rc != 0) return rc;
+    bool hasPred;
+    if (shift == 0) {
+        *keyOut  = lo + bin;
+        hasPred  = rank > 0 || pbin != 0xffffffffu;
+        *predOut = rank > 0 ? lo + bin : lo + pbin;
+    } else {
+        int rank2;
+        bracket_sweep_b<AREA>(q, live, key, lo + (bin << shift), rank, s, keyOut, &rank2, predOut, &hasPred);
+    }
+    if (needPred && !hasPred) *predOut = block_max_below27<AREA>(q, live, key, *keyOut, s);  // rare: predecessor far below
+    return 0;
+}
+
+// cold tier, first pass: every key goes into one of 64 coarse bins (thread-private counters, no prefix test, so the
+// per-key code is straight-line).  Returns the bin of the k-th key.
+template <int AREA, class CoarseFn>
+__device__ __forceinline__ uint32_t coarse_pass_private(const int (&q)[AREA], bool live, CoarseFn coarse, int k, const SelSmem& s,
+                                                        uint32_t* belowBin)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (live) {
+#pragma unroll
+        for (int i = 0; i < AREA; i++) {
+            const uint32_t d = coarse(q[i]);
+            s.priv[(d >> 2) * NT + tid] += 1u << ((d & 3u) * 8u);
+        }
+    }
+    __syncthreads();
+    {
+        uint32_t lo = 0, hi = 0;
+#pragma unroll
+        for (int j = 0; j < NT / 32; j++) {
+            const uint32_t wv                 = s.priv[warp * NT + lane + 32 * j];
+            s.priv[warp * NT + lane + 32 * j] = 0;
+            lo += wv & 0x00ff00ffu;
+            hi += (wv >> 8) & 0x00ff00ffu;
+        }
+        lo = __reduce_add_sync(FULL, lo);
+        hi = __reduce_add_sync(FULL, hi);
+        if (lane == 0) {
+            s.tot[warp * 4 + 0] = lo & 0xffffu;
+            s.tot[warp * 4 + 1] = hi & 0xffffu;
+            s.tot[warp * 4 + 2] = lo >> 16;
+            s.tot[warp * 4 + 3] = hi >> 16;
+        }
+    }
+    __syncthreads();
+    // every warp scans the 64 totals redundantly: no third barrier
+    const uint32_t c0 = s.tot[2 * lane], c1 = s.tot[2 * lane + 1];
+    const uint32_t sum = c0 + c1;
+    uint32_t incl      = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t v = __shfl_up_sync(FULL, incl, o);
+        if (lane >= o) incl += v;
+    }
+    const uint32_t excl = incl - sum;
+    const uint32_t kk   = (uint32_t)k;
+    uint32_t mine       = 0xffffffffu;
+    if (kk >= excl && kk < excl + c0)
+        mine = 2 * lane;
+    else if (kk >= excl + c0 && kk < incl)
+        mine = 2 * lane + 1;
+    const uint32_t bin = __reduce_min_sync(FULL, mine);
+    *belowBin          = __shfl_sync(FULL, (bin & 1u) ? excl + c0 : excl, (int)((bin >> 1) & 31u));  // keys in lower bins
+    return bin;
+}
+
+// coarse digit for the cold tier: 64 bins of 2^16 key units starting at (base << 16), clamped
+struct CoarseKey {
+    int base;
+    __device__ __forceinline__ uint32_t operator()(uint32_t kk) const { return (uint32_t)min(max((int)(kk >> 16) - base, 0), 63); }
+};
+template <class KeyFn>
+struct CoarseOf {
+    KeyFn key;
+    CoarseKey ck;
+    __device__ __forceinline__ uint32_t operator()(int q) const { return ck(key(q)); }
+};
+
+// k-th smallest key with its predecessor, through the tiers.  tierStat: bit 0 hot hit, bit 1 cold, bit 2 generic.
+template <int AREA, class KeyFn>
+__device__ __forceinline__ uint32_t tiered_select(const int (&q)[AREA], bool live, KeyFn key, int coarseBase, int k, bool needPred,
+                                                  Bracket& br, const SelSmem& s, uint32_t* predOut, int* tierStat, long long* prof)
+{
+    long long t0 = clock64();
+    uint32_t kOut = 0, pred = 0;
+    bool done = false;
+    if (br.valid) {
+        const uint32_t half = 256u << br.shift;
+        const uint32_t lo   = br.center > half ? br.center - half : 0u;
+        if (bracket_select<AREA>(q, live, key, lo, br.shift, k, needPred, s, &kOut, &pred) == 0) {
+            done      = true;
+            *tierStat = 1;
+        }
+        const long long t1 = clock64();
+        prof[done ? 0 : 1] += t1 - t0;  // hot hit / hot miss
+        prof[done ? 4 : 5] += 1;
+        t0 = t1;
+    }
+    if (!done) {
+        CoarseOf<KeyFn> ck{key, CoarseKey{coarseBase}};
+        uint32_t belowBins;
+        const uint32_t b = coarse_pass_private<AREA>(q, live, ck, k, s, &belowBins);
+        if (b != 0 && b != 63) {
+            // second private pass: 64 sub-bins of 2^10 key units inside the coarse bin (keys of other coarse bins do
+            // not match the prefix test), leaving a few dozen keys for the atomic sweeps
+            uint32_t prefix2 = ((uint32_t)((int)b + coarseBase)) << 16, mask2 = 0xffff0000u;
+            int kk = k - (int)belowBins;  // select_pass_private works on the rank among the keys matching the prefix
+            select_pass_private<AREA>(q, live, key, prefix2, mask2, kk, 10, s);
+            const uint32_t lo = prefix2;  // now includes the 6 sub-bin bits
+            const long long t1 = clock64();
+            prof[2] += t1 - t0;  // two private passes
+            bracket_select<AREA>(q, live, key, lo, 1, k, needPred, s, &kOut, &pred);
+            prof[3] += clock64() - t1;  // bracket select after the private passes
+            prof[6] += 1;
+            *tierStat = 2;
+        } else {
+            int rank;
+            kOut = block_select27<AREA>(q, live, key, k, s, &rank);
+            pred = kOut;
+            if (needPred && rank == 0) pred = block_max_below27<AREA>(q, live, key, kOut, s);
+            *tierStat = 4;
+        }
+    }
+    // next bracket: centred on this result, wide enough for 4x the last movement
+    const uint32_t moved = br.valid ? (kOut > br.center ? kOut - br.center : br.center - kOut) : 0xffffffffu;
+    // (shared atomics cost ~2 cycles per key inside the bracket, so brackets wider than +/- 2^13 key units = 1/8
+    // intensity unit are not worth it: those evaluations go through the cold tier)
+    int sh = 4;
+    if (br.valid) {
+        const uint32_t want = 4u * min(moved, 1u << 20) + 64u;  // half-width
+        sh = 0;
+        while ((256u << sh) < want && sh < 6) sh++;
+    }
+    br.valid  = sh <= 5;
+    br.shift  = min(sh, 5);
+    br.center = kOut;
+    *predOut  = pred;
+    return kOut;
+}
+
 struct KeySignedQ {  // order-preserving map of q in [-2^25, 2^25) to 27 bits
     __device__ __forceinline__ uint32_t operator()(int q) const { return (uint32_t)(q + (1 << 25)); }
 };
@@ -319,7 +622,7 @@ __host__ __device__ constexpr size_t v2_smem_bytes(int Fpad)
     b += (size_t)G::ROWW * Fpad * 4;  // level block (grid, jac, flags): one bulk copy
     b += (size_t)3 * Fpad * 8;        // pW
     b += (size_t)16 * NT * 4;         // private counters
-    b += 512 * 4 + 64 * 4 + NW * 4 + 16;  // bins, tot, wtot, sel
+    b += 512 * 4 + 64 * 4 + 4 * NW * 4 + 16;  // bins, tot, wtot, sel
     b += (size_t)NW * 32 * 8;         // red
     b += sizeof(Ctrl) + 64;
     return b + 1024;                  // alignment slack
@@ -351,7 +654,7 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
     sel.tot = reinterpret_cast<uint32_t*>(sp);
     sp += 64 * 4;
     sel.wtot = reinterpret_cast<uint32_t*>(sp);
-    sp += NW * 4;
+    sp += 4 * NW * 4;
     sel.sel = reinterpret_cast<uint32_t*>(sp);
     sp += 16;
     sp          = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sp) + 15) & ~uintptr_t(15));
@@ -424,6 +727,8 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
     }
     const double fx0 = a.K[0], fy0 = a.K[1], cx0 = a.K[2], cy0 = a.K[3];
     const int border = P / 2 + 2;
+    int dbgEval = 0;
+    uint32_t tierCount = 0;  // diagnostics: hot | cold << 8 | generic << 16 selections
 
 #pragma unroll 1
     for (int level = a.prm.max_level, si = 0; level >= a.prm.min_level; level--, si++) {
@@ -471,9 +776,13 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
         uint32_t winLo[G::FW], winHi[G::FW];
         int wx = 0, wy = 0;
         bool winValid = false;
+        Bracket brMed{0u, 4, false}, brMad{0u, 4, false};  // selection brackets carried between evaluations
 
         // ================= evaluate (computeResiduals + tukeyWeighting + normal equations) =================
+        long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        long long sprof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
         auto evaluate = [&]() {
+            const long long c0 = clock64();
             // --- warp the feature (FP64) ---
             bool vis = false;
             int uI = 0, vI = 0;
@@ -560,30 +869,39 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
                 for (int i = 0; i < G::AREA; i++) q[i] = 0;
             }
             const int nvis     = __syncthreads_count(vis);
+            const long long c1 = clock64();
             const int numValid = nvis * G::AREA;
             const int N        = F * G::AREA;
 
             // --- sigma = 1.4826 MAD, src/optimizer.cpp:485-507, src/algorithm.cpp:834-872 (MEDIAN_EXACT) ---
             double sigma;
+            long long cMid = c1;
             if (nvis == 0) {
                 sigma = DBL_EPSILON;  // the reference gets MAD = 0 from all-sentinel input
             } else {
-                const int mid = numValid / 2;
-                int rk;
+                const int mid      = numValid / 2;
+                const bool evenAvg = !(N & 1) && mid > 0;  // mean of elements mid-1 and mid
                 // element `mid` of the sorted N-vector (invalid rows sort last, so it is a valid one)
-                const uint32_t kHi = block_select27<G::AREA>(q, vis, KeySignedQ{}, mid, sel, &rk);
-                uint32_t kLo       = kHi;
-                if (!(N & 1) && mid > 0 && rk == 0) kLo = block_max_below27<G::AREA>(q, vis, KeySignedQ{}, kHi, sel);
-                const int med2 = ((N & 1) || mid == 0) ? 2 * ((int)kHi - (1 << 25)) : ((int)kHi - (1 << 25)) + ((int)kLo - (1 << 25));
+                uint32_t kLo, dLo;
+                int tier;
+                const uint32_t kHi = tiered_select<G::AREA>(q, vis, KeySignedQ{}, 512 - 32, mid, evenAvg, brMed, sel, &kLo, &tier, sprof);
+                tierCount += tier == 1 ? 1 : (tier == 2 ? 0x100 : 0x10000);
+                if (!evenAvg) kLo = kHi;
+                const int med2 = ((int)kHi - (1 << 25)) + ((int)kLo - (1 << 25));
                 KeyAbsDev2 kd{med2};
-                const uint32_t dHi = block_select27<G::AREA>(q, vis, kd, mid, sel, &rk);
-                uint32_t dLo       = dHi;
-                if (!(N & 1) && mid > 0 && rk == 0) dLo = block_max_below27<G::AREA>(q, vis, kd, dHi, sel);
+                cMid = clock64();
+                const uint32_t dHi = tiered_select<G::AREA>(q, vis, kd, 0, mid, evenAvg, brMad, sel, &dLo, &tier, sprof);
+                tierCount += tier == 1 ? 1 : (tier == 2 ? 0x100 : 0x10000);
+                if (!evenAvg) dLo = dHi;
+                if (a.dbg && job == 0 && tid == 64 && dbgEval < 24)
+                    a.dbg[32 + dbgEval] = ((long long)dHi << 32) | (uint32_t)((int)kHi - (1 << 25));
+                dbgEval++;
                 // deviations are in units of 2^-17
-                const double mad = ((N & 1) || mid == 0) ? (double)dHi : 0.5 * ((double)dHi + (double)dLo);
+                const double mad = 0.5 * ((double)dHi + (double)dLo);
                 sigma            = 1.482602218505602 * mad * (1.0 / 131072.0);
                 if (sigma <= DBL_EPSILON) sigma = DBL_EPSILON;
             }
+            const long long c2 = clock64();
             const double cD = 4.6851 * sigma;
             const float cF  = (float)cD;
             const float ic2 = (float)(1.0 / (cD * cD));
@@ -633,6 +951,7 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
                 for (int i = 0; i < 6; i++) val[21 + i] = bx * A[i] + by * B[i];
                 val[27] = ch;
             }
+            const long long c3 = clock64();
             // --- transposed warp reduction: afterwards lane i holds the warp total of val[i] ---
 #pragma unroll
             for (int s = 16; s >= 1; s >>= 1) {
@@ -658,14 +977,23 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
                 ctrl->evals_level++;
             }
             __syncthreads();
+            const long long c4 = clock64();
+            tph[0] += c1 - c0;    // warp + window + bilinear + residual
+            tph[1] += cMid - c1;  // median select
+            tph[2] += c2 - cMid;  // MAD select
+            tph[3] += c3 - c2;    // weights + patch sums + expansion
+            tph[4] += c4 - c3;    // reductions
+            tph[6] += 1;
         };
 
         // record the first iteration of the level for the stats record
-        auto record_first = [&](const double* H, const double* g, double chi2, double lambda, int n) {
+        auto record_first = [&](const double* E, double chi2, double lambda, int n) {
             if (!ctrl->first) return;
             ctrl->first = 0;
             if (a.stats) {
                 svo_align_level_stats* s = a.stats + (size_t)job * nLevels + si;
+                double H[36], g[6];
+                expand_H(E, H, g);
                 for (int i = 0; i < 36; i++) s->H[i] = H[i];
                 for (int i = 0; i < 6; i++) s->g[i] = g[i];
                 s->chi2   = chi2;
@@ -685,15 +1013,15 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
 #pragma unroll 1
         while (true) {
             evaluate();
+            const long long cs0 = clock64();
             if (tid == 0) {
-                double H[36], g[6], dx[6];
+                double dx[6];
                 if (gn) {
-                    expand_H(ctrl->E, H, g);
                     const double chi2 = ctrl->E[27];
                     if (ctrl->first) ctrl->first_sigma = ctrl->sigma;
                     const bool wasFirst = ctrl->first;
-                    record_first(H, g, chi2, 0.0, ctrl->n_eval);
-                    svo::ldlt_solve<6>(H, g, dx);
+                    record_first(ctrl->E, chi2, 0.0, ctrl->n_eval);
+                    solve6(ctrl->E, 0.0, dx);
                     if (wasFirst && a.stats)
                         for (int i = 0; i < 6; i++) a.stats[(size_t)job * nLevels + si].dx[i] = dx[i];
                     ctrl->iters_level++;
@@ -756,17 +1084,16 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
                             ctrl->preChi2  = ctrl->curE[27];
                             ctrl->status   = SVO_ST_SUCCESS;
                         }
-                        expand_H(ctrl->curE, H, g);
                         if (ctrl->it == 0) {
-                            double mx = H[0];
-                            for (int i = 1; i < 6; i++) mx = fmax(mx, H[i * 6 + i]);
+                            // diagonal entries of the packed upper triangle: 0, 6, 11, 15, 18, 20
+                            const double* Ec = ctrl->curE;
+                            const double mx  = fmax(fmax(fmax(Ec[0], Ec[6]), fmax(Ec[11], Ec[15])), fmax(Ec[18], Ec[20]));
                             ctrl->lambda *= mx;  // :296-299
                         }
                         const double lambda = ctrl->lambda;
                         const bool wasFirst = ctrl->first;
-                        record_first(H, g, ctrl->curE[27], lambda, ctrl->cur_n);
-                        for (int i = 0; i < 6; i++) H[i * 6 + i] += lambda;
-                        svo::ldlt_solve<6>(H, g, dx);
+                        record_first(ctrl->curE, ctrl->curE[27], lambda, ctrl->cur_n);
+                        solve6(ctrl->curE, lambda, dx);
                         if (wasFirst && a.stats)
                             for (int i = 0; i < 6; i++) a.stats[(size_t)job * nLevels + si].dx[i] = dx[i];
                         svo::pose_update_right_exp_neg(ctrl->pose, dx);  // :310 applied before any check
@@ -798,8 +1125,14 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
                 set_Rt(ctrl);
             }
             __syncthreads();
+            tph[5] += clock64() - cs0;  // solve + pose update (all threads wait for thread 0)
             if (ctrl->done) break;
         }
+        if (a.dbg && job == 0 && tid == 64)
+            for (int i = 0; i < 8; i++) {
+                a.dbg[si * 8 + i] = tph[i];
+                if (si < 1) a.dbg[32 + 24 + i] = sprof[i];  // coarsest level only (slots 56..63)
+            }
         if (tid == 0) {
             ctrl->evals_total += ctrl->evals_level;
             ctrl->iters_total += ctrl->iters_level;
@@ -823,7 +1156,7 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
         res.status      = ctrl->status;
         res.evaluations = ctrl->evals_total;
         res.iterations  = ctrl->iters_total;
-        res.reserved    = 0;
+        res.reserved    = (int32_t)tierCount;
         a.results[job]  = res;
     }
 }
@@ -856,6 +1189,7 @@ svo_status launch_v2(svo_ctx* ctx, int maxF)
     args.job_stride = job_stride;
     args.Fpad       = Fpad;
     args.prm        = prm;
+    args.dbg        = ctx->d_dbg;
     for (int i = 0; i < 4; i++) args.K[i] = ctx->cfg.K[i];
 
     dim3 pgrid((Fpad + 127) / 128, nLevels, nJobs);

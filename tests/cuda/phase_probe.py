@@ -1,0 +1,27 @@
+import importlib, sys, numpy as np
+sys.path.insert(0, "/root/repo")
+pkg = importlib.import_module("semi-direct-visual-odometry_b200")
+pair = pkg.synth.make_pair(0, 500)
+for mode in (2, 1, 0):
+    with pkg.Context(pair["w"], pair["h"], pair["K"], levels=4, max_frames=2, max_jobs=1, max_features=512) as ctx:
+        ctx.upload(0, np.stack([pair["ref"], pair["cur"]]))
+        j = pkg.capi.make_jobs(1)
+        j[0]["ref_slot"], j[0]["kf_slot"], j[0]["cur_slot"] = 0, 0, 1
+        j[0]["n_ref"], j[0]["n_kf"] = pair["n_ref"], 0
+        j[0]["T_ref"], j[0]["T_kf"], j[0]["T_cur"] = pair["T_ref"], pair["T_kf"], pair["T_cur_init"]
+        for _ in range(3):
+            res, st = ctx.sparse_align(j, pair["feats"], mode=mode, max_iter=30)
+        dd = ctx.debug_cycles()
+        d = dd[:4]
+        ev = dd.reshape(-1)[32:32 + min(24, res[0]['evaluations'])]
+        med = (ev & 0xffffffff).astype(np.uint32).view(np.int32) / 65536.0
+        mad = (ev >> 32) / 131072.0
+        sp = dd.reshape(-1)[56:64]
+        print('select profile (coarsest level): hot-hit cyc %d n %d | hot-miss cyc %d n %d | 2 private passes cyc %d, bracket after cyc %d, n %d' % (sp[0], sp[4], sp[1], sp[5], sp[2], sp[3], sp[6]))
+        print('median per eval:', np.round(med, 4))
+        print('MAD per eval   :', np.round(mad, 4))
+        print("mode", mode, "evals", res[0]["evaluations"], "tiers", hex(res[0]["reserved"]))
+        print("per level [warp+sample, sel med, sel mad, sums, reduce, solve, n_eval]:")
+        print(d[:, :7])
+        tot = d[:, :6].sum(0); n = d[:, 6].sum()
+        print("cycles per evaluation:", (tot / n).round(0), "total", (tot.sum() / n).round(0), "=> us/eval %.2f" % (tot.sum() / n / 1965))
