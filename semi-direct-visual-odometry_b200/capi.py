@@ -10,7 +10,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsvo_b200.so")
+LIB_PATH = os.environ.get("SVO_B200_LIB", os.path.join(_HERE, "libsvo_b200.so"))  # override: A/B builds of the same ABI
 
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NO_DEVICE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 LM_FAITHFUL, LM_ITERATED, GN = 0, 1, 2

@@ -22,6 +22,7 @@
 #include <float.h>
 
 #include "align_common.cuh"
+#include "block_select.cuh"
 
 namespace {
 
@@ -153,465 +154,6 @@ __global__ void __launch_bounds__(128) k_align_precompute(const V2Args a)
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// block-wide exact selection on 27-bit keys held in registers
-// ------------------------------------------------------------------------------------------------------------
-struct SelSmem {
-    uint32_t* priv;    // [16][NT] thread-private packed 8-bit counters (64 bins), zero between uses
-    uint32_t* bins;    // [512] shared counters for the atomic passes, zero between uses
-    uint32_t* tot;     // [64] bin totals of a private pass
-    uint32_t* wtot;    // [4][NW] per-warp partials (count inside, count below, max below, last non-empty bin)
-    uint32_t* sel;     // [4] chosen digit, remaining rank, predecessor bin
-};
-
-// one pass over 6 bits with thread-private counters.  keys: AREA values; live: participates at all
-template <int AREA, class KeyFn>
-__device__ __forceinline__ void select_pass_private(const int (&q)[AREA], bool live, KeyFn key, uint32_t& prefix, uint32_t& mask,
-                                                    int& k, int shift, const SelSmem& s)
-{
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (live) {
-#pragma unroll
-        for (int i = 0; i < AREA; i++) {
-            const uint32_t kk = key(q[i]);
-            if ((kk & mask) == prefix) {
-                const uint32_t d = (kk >> shift) & 63u;
-                s.priv[(d >> 2) * NT + tid] += 1u << ((d & 3u) * 8u);
-            }
-        }
-    }
-    __syncthreads();
-    {   // warp w reduces word row w (bins 4w .. 4w+3) over all NT columns
-        uint32_t lo = 0, hi = 0;
-#pragma unroll
-        for (int j = 0; j < NT / 32; j++) {
-            const uint32_t wv                 = s.priv[warp * NT + lane + 32 * j];
-            s.priv[warp * NT + lane + 32 * j] = 0;
-            lo += wv & 0x00ff00ffu;
-            hi += (wv >> 8) & 0x00ff00ffu;
-        }
-        lo = __reduce_add_sync(FULL, lo);
-        hi = __reduce_add_sync(FULL, hi);
-        if (lane == 0) {
-            s.tot[warp * 4 + 0] = lo & 0xffffu;
-            s.tot[warp * 4 + 1] = hi & 0xffffu;
-            s.tot[warp * 4 + 2] = lo >> 16;
-            s.tot[warp * 4 + 3] = hi >> 16;
-        }
-    }
-    __syncthreads();
-    if (warp == 0) {
-        const uint32_t c0 = s.tot[2 * lane], c1 = s.tot[2 * lane + 1];
-        const uint32_t sum = c0 + c1;
-        uint32_t incl      = sum;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t v = __shfl_up_sync(FULL, incl, o);
-            if (lane >= o) incl += v;
-        }
-        const uint32_t excl = incl - sum;
-        const uint32_t kk   = (uint32_t)k;
-        if (kk >= excl && kk < excl + c0) {
-            s.sel[0] = 2 * lane;
-            s.sel[1] = kk - excl;
-        } else if (kk >= excl + c0 && kk < incl) {
-            s.sel[0] = 2 * lane + 1;
-            s.sel[1] = kk - excl - c0;
-        }
-    }
-    __syncthreads();
-    prefix |= s.sel[0] << shift;
-    mask |= 63u << shift;
-    k = (int)s.sel[1];
-}
-
-// one pass over `bits` (<= 9) bits with shared atomic counters (few keys match the prefix by now)
-template <int AREA, class KeyFn>
-__device__ __forceinline__ void select_pass_atomic(const int (&q)[AREA], bool live, KeyFn key, uint32_t& prefix, uint32_t& mask,
-                                                   int& k, int shift, int bits, const SelSmem& s)
-{
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t dm = (1u << bits) - 1u;
-    if (live) {
-#pragma unroll
-        for (int i = 0; i < AREA; i++) {
-            const uint32_t kk = key(q[i]);
-            if ((kk & mask) == prefix) atomicAdd(&s.bins[(kk >> shift) & dm], 1u);
-        }
-    }
-    __syncthreads();
-    const uint32_t c = s.bins[tid];  // NT == 512 bins
-    s.bins[tid]      = 0;
-    uint32_t incl    = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += v;
-    }
-    if (lane == 31) s.wtot[warp] = incl;
-    __syncthreads();
-    uint32_t base = 0;
-#pragma unroll
-    for (int w = 0; w < NW; w++) base += (w < warp) ? s.wtot[w] : 0u;
-    const uint32_t excl = base + incl - c;
-    const uint32_t kk   = (uint32_t)k;
-    if (kk >= excl && kk < excl + c) {
-        s.sel[0] = tid;
-        s.sel[1] = kk - excl;
-    }
-    __syncthreads();
-    prefix |= s.sel[0] << shift;
-    mask |= dm << shift;
-    k = (int)s.sel[1];
-}
-
-// k-th smallest key (0-based) over all live threads' keys; *rank_in_key = k minus the number of strictly smaller keys
-template <int AREA, class KeyFn>
-__device__ __forceinline__ uint32_t block_select27(const int (&q)[AREA], bool live, KeyFn key, int k, const SelSmem& s,
-                                                   int* rank_in_key)
-{
-    uint32_t prefix = 0, mask = 0;
-    select_pass_private<AREA>(q, live, key, prefix, mask, k, 21, s);
-    select_pass_private<AREA>(q, live, key, prefix, mask, k, 15, s);
-    select_pass_atomic<AREA>(q, live, key, prefix, mask, k, 6, 9, s);
-    select_pass_atomic<AREA>(q, live, key, prefix, mask, k, 0, 6, s);
-    *rank_in_key = k;
-    return prefix;
-}
-
-// largest key strictly below bound (0 if none)
-template <int AREA, class KeyFn>
-__device__ __forceinline__ uint32_t block_max_below27(const int (&q)[AREA], bool live, KeyFn key, uint32_t bound, const SelSmem& s)
-{
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t m = 0;
-    if (live) {
-#pragma unroll
-        for (int i = 0; i < AREA; i++) {
-            const uint32_t kk = key(q[i]);
-            if (kk < bound) m = max(m, kk);
-        }
-    }
-    m = __reduce_max_sync(FULL, m);
-    if (lane == 0) s.wtot[warp] = m;
-    __syncthreads();
-    uint32_t out = 0;
-#pragma unroll
-    for (int w = 0; w < NW; w++) out = max(out, s.wtot[w]);
-    __syncthreads();  // wtot is reused by the next pass
-    return out;
-}
-
-// ------------------------------------------------------------------------------------------------------------
-// tiered selection.  The generic 4-pass select above sweeps all 25 keys of every thread 4-5 times with ~10 integer
-// instructions per key and pass; the integer pipes issue at half rate, which made sigma half of the kernel.  Two
-// cheaper tiers come first:
-//   hot   the target of the previous evaluation (median or MAD key) brackets this one: ONE sweep counts the keys
-//         below the bracket and histograms (512 shared atomic counters) the few that fall inside; a second sweep
-//         resolves the chosen bin to a single key.  Keys outside the bracket cost 4-5 instructions and no memory.
-//   cold  one sweep with thread-private counters over 64 coarse bins (1 intensity unit for the median, 1/2 for the
-//         MAD) finds the coarse bin, then the hot machinery runs on exactly that bin.
-//   generic  targets outside the coarse range fall back to block_select27.
-// All tiers are exact on the fixed-point keys; only the work differs.
-// ------------------------------------------------------------------------------------------------------------
-struct Bracket {   // uniform per CTA (every thread holds the same values)
-    uint32_t center;
-    int shift;     // log2 of the bin width of the first sweep; bracket = center -/+ (256 << shift)
-    bool valid;
-};
-
-// Sweep A of a bracketed select: 512 bins of width 2^shift starting at lo; counts the keys below lo.  Straight-line
-// per key except for the (rare) shared atomic.  Returns 0 and (bin, rank inside the bin, last non-empty bin before
-// it or 0xffffffff) on a hit, -1 / +1 when the k-th key lies below / above the bracket.
-template <int AREA, class KeyFn>
-__device__ __forceinline__ int bracket_sweep_a(const int (&q)[AREA], bool live, KeyFn key, uint32_t lo, int shift, int k,
-                                               const SelSmem& s, uint32_t* binOut, int* rankOut, uint32_t* predBin)
-{
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    uint32_t below = 0;
-    if (live) {
-#pragma unroll
-        for (int i = 0; i < AREA; i++) {
-            const uint32_t t = key(q[i]) - lo;  // keys below lo wrap to >= 2^31 (keys are < 2^27)
-            below += t >> 31;
-            if ((t >> shift) < 512u) atomicAdd(&s.bins[t >> shift], 1u);
-        }
-    }
-    below = __reduce_add_sync(FULL, below);
-    if (lane == 0) s.wtot[NW + warp] = below;
-    __syncthreads();
-    const uint32_t c = s.bins[tid];
-    s.bins[tid]      = 0;
-    uint32_t incl    = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += v;
-    }
-    const uint32_t nz = __ballot_sync(FULL, c != 0);
-    if (lane == 31) {
-        s.wtot[warp]          = incl;
-        s.wtot[3 * NW + warp] = nz ? (uint32_t)(warp * 32 + 31 - __clz(nz)) : 0xffffffffu;  // last non-empty bin of the warp
-    }
-    __syncthreads();
-    const uint32_t wi = lane < NW ? s.wtot[lane] : 0u;
-    const uint32_t wb = lane < NW ? s.wtot[NW + lane] : 0u;
-    const uint32_t inside   = __reduce_add_sync(FULL, wi);
-    const uint32_t base     = __reduce_add_sync(FULL, lane < warp ? wi : 0u);
-    const uint32_t totBelow = __reduce_add_sync(FULL, wb);
-    const int kin = k - (int)totBelow;
-    if (kin < 0) return -1;
-    if (kin >= (int)inside) return 1;
-    const uint32_t excl = base + incl - c;
-    if ((uint32_t)kin >= excl && (uint32_t)kin < excl + c) {
-        s.sel[0] = tid;
-        s.sel[1] = (uint32_t)kin - excl;
-        const uint32_t lower = nz & ((1u << lane) - 1u);
-        uint32_t pb          = 0xffffffffu;
-        if (lower) {
-            pb = (uint32_t)(warp * 32 + 31 - __clz(lower));
-        } else {
-            for (int w = warp - 1; w >= 0; w--) {
-                const uint32_t lb = s.wtot[3 * NW + w];
-                if (lb != 0xffffffffu) {
-                    pb = lb;
-                    break;
-                }
-            }
-        }
-        s.sel[2] = pb;
-    }
-    __syncthreads();
-    *binOut  = s.sel[0];
-    *rankOut = (int)s.sel[1];
-    *predBin = s.sel[2];
-    return 0;
-}
-
-// Sweep B: the chosen bin [lo2, lo2 + W), W <= 128, resolved to single keys.  The 512 unit bins start up to 287 keys
-// BELOW lo2, so that the predecessor of the target (needed for the even-count median rule) is normally inside the
-// window too.  rankA = rank of the target among the keys >= lo2.  Returns the key, its rank among equal keys and the
-// predecessor key (hasPred false: the predecessor lies below the window).
-template <int AREA, class KeyFn>
-__device__ __forceinline__ void bracket_sweep_b(const int (&q)[AREA], bool live, KeyFn key, uint32_t lo2, int rankA, const SelSmem& s,
-                                                uint32_t* keyOut, int* rankOut, uint32_t* predOut, bool* hasPred)
-{
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t ws  = lo2 >= 256u ? ((lo2 - 256u) & ~31u) : 0u;  // window start
-    const uint32_t off = lo2 - ws;                                   // 0 .. 287
-    if (live) {
-#pragma unroll
-        for (int i = 0; i < AREA; i++) {
-            const uint32_t t = key(q[i]) - ws;
-            if (t < 512u) atomicAdd(&s.bins[t], 1u);
-        }
-    }
-    __syncthreads();
-    const uint32_t c = s.bins[tid];
-    s.bins[tid]      = 0;
-    uint32_t incl    = c;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += v;
-    }
-    const uint32_t nz = __ballot_sync(FULL, c != 0);
-    if (lane == 31) {
-        s.wtot[warp]          = incl;
-        s.wtot[3 * NW + warp] = nz ? (uint32_t)(warp * 32 + 31 - __clz(nz)) : 0xffffffffu;
-    }
-    if ((uint32_t)tid == off) s.sel[3] = incl - c;  // keys of this warp's bins before lo2
-    __syncthreads();
-    const uint32_t wi   = lane < NW ? s.wtot[lane] : 0u;
-    const uint32_t base = __reduce_add_sync(FULL, lane < warp ? wi : 0u);
-    const uint32_t P    = __reduce_add_sync(FULL, (uint32_t)lane < (off >> 5) ? wi : 0u) + s.sel[3];  // keys in [ws, lo2)
-    const uint32_t kin  = P + (uint32_t)rankA;
-    const uint32_t excl = base + incl - c;
-    if (kin >= excl && kin < excl + c) {
-        s.sel[0] = tid;
-        s.sel[1] = kin - excl;
-        const uint32_t lower = nz & ((1u << lane) - 1u);
-        uint32_t pb          = 0xffffffffu;
-        if (lower) {
-            pb = (uint32_t)(warp * 32 + 31 - __clz(lower));
-        } else {
-            for (int w = warp - 1; w >= 0; w--) {
-                const uint32_t lb = s.wtot[3 * NW + w];
-                if (lb != 0xffffffffu) {
-                    pb = lb;
-                    break;
-                }
-            }
-        }
-        s.sel[2] = pb;
-    }
-    __syncthreads();
-    *keyOut  = ws + s.sel[0];
-    *rankOut = (int)s.sel[1];
-    *hasPred = s.sel[1] > 0 || s.sel[2] != 0xffffffffu;
-    *predOut = s.sel[1] > 0 ? ws + s.sel[0] : ws + s.sel[2];
-}
-
-// Bracketed exact select: sweep A with bins of 2^shift from lo, then (shift > 0) sweep B over the chosen bin.  On a
-// hit: *keyOut = the k-th smallest key, *predOut = the (k-1)-th smallest (valid when needPred and k > 0).
-template <int AREA, class KeyFn>
-__device__ __forceinline__ int bracket_select(const int (&q)[AREA], bool live, KeyFn key, uint32_t lo, int shift, int k, bool needPred,
-                                              const SelSmem& s, uint32_t* keyOut, uint32_t* predOut)
-{
-    uint32_t bin, pbin;
-    int rank;
-    const int rc = bracket_sweep_a<AREA>(q, live, key, lo, shift, k, s, &bin, &rank, &pbin);
-    if (rc != 0) return rc;
-    bool hasPred;
-    if (shift == 0) {
-        *keyOut  = lo + bin;
-        hasPred  = rank > 0 || pbin != 0xffffffffu;
-        *predOut = rank > 0 ? lo + bin : lo + pbin;
-    } else {
-        int rank2;
-        bracket_sweep_b<AREA>(q, live, key, lo + (bin << shift), rank, s, keyOut, &rank2, predOut, &hasPred);
-    }
-    if (needPred && !hasPred) *predOut = block_max_below27<AREA>(q, live, key, *keyOut, s);  // rare: predecessor far below
-    return 0;
-}
-
-// cold tier, first pass: every key goes into one of 64 coarse bins (thread-private counters, no prefix test, so the
-// per-key code is straight-line).  Returns the bin of the k-th key.
-template <int AREA, class CoarseFn>
-__device__ __forceinline__ uint32_t coarse_pass_private(const int (&q)[AREA], bool live, CoarseFn coarse, int k, const SelSmem& s,
-                                                        uint32_t* belowBin)
-{
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (live) {
-#pragma unroll
-        for (int i = 0; i < AREA; i++) {
-            const uint32_t d = coarse(q[i]);
-            s.priv[(d >> 2) * NT + tid] += 1u << ((d & 3u) * 8u);
-        }
-    }
-    __syncthreads();
-    {
-        uint32_t lo = 0, hi = 0;
-#pragma unroll
-        for (int j = 0; j < NT / 32; j++) {
-            const uint32_t wv                 = s.priv[warp * NT + lane + 32 * j];
-            s.priv[warp * NT + lane + 32 * j] = 0;
-            lo += wv & 0x00ff00ffu;
-            hi += (wv >> 8) & 0x00ff00ffu;
-        }
-        lo = __reduce_add_sync(FULL, lo);
-        hi = __reduce_add_sync(FULL, hi);
-        if (lane == 0) {
-            s.tot[warp * 4 + 0] = lo & 0xffffu;
-            s.tot[warp * 4 + 1] = hi & 0xffffu;
-            s.tot[warp * 4 + 2] = lo >> 16;
-            s.tot[warp * 4 + 3] = hi >> 16;
-        }
-    }
-    __syncthreads();
-    // every warp scans the 64 totals redundantly: no third barrier
-    const uint32_t c0 = s.tot[2 * lane], c1 = s.tot[2 * lane + 1];
-    const uint32_t sum = c0 + c1;
-    uint32_t incl      = sum;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t v = __shfl_up_sync(FULL, incl, o);
-        if (lane >= o) incl += v;
-    }
-    const uint32_t excl = incl - sum;
-    const uint32_t kk   = (uint32_t)k;
-    uint32_t mine       = 0xffffffffu;
-    if (kk >= excl && kk < excl + c0)
-        mine = 2 * lane;
-    else if (kk >= excl + c0 && kk < incl)
-        mine = 2 * lane + 1;
-    const uint32_t bin = __reduce_min_sync(FULL, mine);
-    *belowBin          = __shfl_sync(FULL, (bin & 1u) ? excl + c0 : excl, (int)((bin >> 1) & 31u));  // keys in lower bins
-    return bin;
-}
-
-// coarse digit for the cold tier: 64 bins of 2^16 key units starting at (base << 16), clamped
-struct CoarseKey {
-    int base;
-    __device__ __forceinline__ uint32_t operator()(uint32_t kk) const { return (uint32_t)min(max((int)(kk >> 16) - base, 0), 63); }
-};
-template <class KeyFn>
-struct CoarseOf {
-    KeyFn key;
-    CoarseKey ck;
-    __device__ __forceinline__ uint32_t operator()(int q) const { return ck(key(q)); }
-};
-
-// k-th smallest key with its predecessor, through the tiers.  tierStat: bit 0 hot hit, bit 1 cold, bit 2 generic.
-template <int AREA, class KeyFn>
-__device__ __forceinline__ uint32_t tiered_select(const int (&q)[AREA], bool live, KeyFn key, int coarseBase, int k, bool needPred,
-                                                  Bracket& br, const SelSmem& s, uint32_t* predOut, int* tierStat, long long* prof)
-{
-    long long t0 = clock64();
-    uint32_t kOut = 0, pred = 0;
-    bool done = false;
-    if (br.valid) {
-        const uint32_t half = 256u << br.shift;
-        const uint32_t lo   = br.center > half ? br.center - half : 0u;
-        if (bracket_select<AREA>(q, live, key, lo, br.shift, k, needPred, s, &kOut, &pred) == 0) {
-            done      = true;
-            *tierStat = 1;
-        }
-        const long long t1 = clock64();
-        prof[done ? 0 : 1] += t1 - t0;  // hot hit / hot miss
-        prof[done ? 4 : 5] += 1;
-        t0 = t1;
-    }
-    if (!done) {
-        CoarseOf<KeyFn> ck{key, CoarseKey{coarseBase}};
-        uint32_t belowBins;
-        const uint32_t b = coarse_pass_private<AREA>(q, live, ck, k, s, &belowBins);
-        if (b != 0 && b != 63) {
-            // second private pass: 64 sub-bins of 2^10 key units inside the coarse bin (keys of other coarse bins do
-            // not match the prefix test), leaving a few dozen keys for the atomic sweeps
-            uint32_t prefix2 = ((uint32_t)((int)b + coarseBase)) << 16, mask2 = 0xffff0000u;
-            int kk = k - (int)belowBins;  // select_pass_private works on the rank among the keys matching the prefix
-            select_pass_private<AREA>(q, live, key, prefix2, mask2, kk, 10, s);
-            const uint32_t lo = prefix2;  // now includes the 6 sub-bin bits
-            const long long t1 = clock64();
-            prof[2] += t1 - t0;  // two private passes
-            bracket_select<AREA>(q, live, key, lo, 1, k, needPred, s, &kOut, &pred);
-            prof[3] += clock64() - t1;  // bracket select after the private passes
-            prof[6] += 1;
-            *tierStat = 2;
-        } else {
-            int rank;
-            kOut = block_select27<AREA>(q, live, key, k, s, &rank);
-            pred = kOut;
-            if (needPred && rank == 0) pred = block_max_below27<AREA>(q, live, key, kOut, s);
-            *tierStat = 4;
-        }
-    }
-    // next bracket: centred on this result, wide enough for 4x the last movement
-    const uint32_t moved = br.valid ? (kOut > br.center ? kOut - br.center : br.center - kOut) : 0xffffffffu;
-    // (shared atomics cost ~2 cycles per key inside the bracket, so brackets wider than +/- 2^13 key units = 1/8
-    // intensity unit are not worth it: those evaluations go through the cold tier)
-    int sh = 4;
-    if (br.valid) {
-        const uint32_t want = 4u * min(moved, 1u << 20) + 64u;  // half-width
-        sh = 0;
-        while ((256u << sh) < want && sh < 6) sh++;
-    }
-    br.valid  = sh <= 5;
-    br.shift  = min(sh, 5);
-    br.center = kOut;
-    *predOut  = pred;
-    return kOut;
-}
-
-struct KeySignedQ {  // order-preserving map of q in [-2^25, 2^25) to 27 bits
-    __device__ __forceinline__ uint32_t operator()(int q) const { return (uint32_t)(q + (1 << 25)); }
-};
-struct KeyAbsDev2 {  // |2 q - med2|, deviations in half fixed-point units
-    int med2;
-    __device__ __forceinline__ uint32_t operator()(int q) const { return (uint32_t)min(abs(2 * q - med2), (1 << 27) - 1); }
-};
-
-// ------------------------------------------------------------------------------------------------------------
 // iterate
 // ------------------------------------------------------------------------------------------------------------
 template <int P>
@@ -621,8 +163,7 @@ __host__ __device__ constexpr size_t v2_smem_bytes(int Fpad)
     size_t b = 0;
     b += (size_t)G::ROWW * Fpad * 4;  // level block (grid, jac, flags): one bulk copy
     b += (size_t)3 * Fpad * 8;        // pW
-    b += (size_t)16 * NT * 4;         // private counters
-    b += 512 * 4 + 64 * 4 + 4 * NW * 4 + 16;  // bins, tot, wtot, sel
+    b += SEL_SMEM_BYTES;              // selection scratch (block_select.cuh)
     b += (size_t)NW * 32 * 8;         // red
     b += sizeof(Ctrl) + 64;
     return b + 1024;                  // alignment slack
@@ -646,17 +187,16 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
     sp += (size_t)G::ROWW * Fpad * 4;
     double* pWs = reinterpret_cast<double*>(sp);  // [3][Fpad]
     sp += (size_t)3 * Fpad * 8;
-    SelSmem sel;
-    sel.priv = reinterpret_cast<uint32_t*>(sp);
+    SelCtx sc;
+    sc.pp     = 0;
+    sc.s.priv = reinterpret_cast<uint32_t*>(sp);
     sp += (size_t)16 * NT * 4;
-    sel.bins = reinterpret_cast<uint32_t*>(sp);
-    sp += 512 * 4;
-    sel.tot = reinterpret_cast<uint32_t*>(sp);
+    sc.s.bins = reinterpret_cast<uint32_t*>(sp);
+    sp += 2 * 512 * 4;
+    sc.s.tot = reinterpret_cast<uint32_t*>(sp);
     sp += 64 * 4;
-    sel.wtot = reinterpret_cast<uint32_t*>(sp);
+    sc.s.wtot = reinterpret_cast<uint32_t*>(sp);
     sp += 4 * NW * 4;
-    sel.sel = reinterpret_cast<uint32_t*>(sp);
-    sp += 16;
     sp          = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sp) + 15) & ~uintptr_t(15));
     double* red = reinterpret_cast<double*>(sp);  // [NW][32]
     sp += (size_t)NW * 32 * 8;
@@ -683,8 +223,9 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
     }
 
     const float* scr = a.scratch + (long long)job * a.job_stride;
-    for (int i = tid; i < 16 * NT; i += NT) sel.priv[i] = 0;
-    sel.bins[tid] = 0;
+    for (int i = tid; i < 16 * NT; i += NT) sc.s.priv[i] = 0;
+    sc.s.bins[tid]       = 0;
+    sc.s.bins[512 + tid] = 0;
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -727,7 +268,6 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
     }
     const double fx0 = a.K[0], fy0 = a.K[1], cx0 = a.K[2], cy0 = a.K[3];
     const int border = P / 2 + 2;
-    int dbgEval = 0;
     uint32_t tierCount = 0;  // diagnostics: hot | cold << 8 | generic << 16 selections
 
 #pragma unroll 1
@@ -779,10 +319,14 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
         Bracket brMed{0u, 4, false}, brMad{0u, 4, false};  // selection brackets carried between evaluations
 
         // ================= evaluate (computeResiduals + tukeyWeighting + normal equations) =================
+#ifdef SVO_PROFILE
         long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-        long long sprof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#define SVO_TICK(var) const long long var = clock64()
+#else
+#define SVO_TICK(var)
+#endif
         auto evaluate = [&]() {
-            const long long c0 = clock64();
+            SVO_TICK(c0);
             // --- warp the feature (FP64) ---
             bool vis = false;
             int uI = 0, vI = 0;
@@ -807,7 +351,7 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
                 }
             }
             // --- refresh the register window if the footprint left it ---
-            int q[G::AREA];
+            uint32_t key[G::AREA];  // residuals as order-preserving fixed-point keys: rint(r 2^16) + 2^25
             if (vis) {
                 const int x0 = uI + G::PB, y0 = vI + G::PB;  // footprint origin
                 if (!winValid || y0 != wy || x0 < wx || x0 + G::FW > wx + 8) {
@@ -858,7 +402,7 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
                         for (int c = 0; c < P; c++) {
                             const float val = wv0 * prevRow[c] + fv * curRow[c];
                             const float T   = gridS[(size_t)((r - 1 + 1) * G::GW + (c + 1)) * Fpad + f];
-                            q[(r - 1) * P + c] = __float2int_rn((val - T) * 65536.f);
+                            key[(r - 1) * P + c] = (uint32_t)(__float2int_rn((val - T) * 65536.f) + (1 << 25));
                         }
                     }
 #pragma unroll
@@ -866,16 +410,17 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < G::AREA; i++) q[i] = 0;
+                for (int i = 0; i < G::AREA; i++) key[i] = 0;
             }
             const int nvis     = __syncthreads_count(vis);
-            const long long c1 = clock64();
+            SVO_TICK(c1);
             const int numValid = nvis * G::AREA;
             const int N        = F * G::AREA;
 
             // --- sigma = 1.4826 MAD, src/optimizer.cpp:485-507, src/algorithm.cpp:834-872 (MEDIAN_EXACT) ---
             double sigma;
-            long long cMid = c1;
+            int med2         = 0;  // twice the median, fixed point
+            uint32_t negMask = 0;  // sign of (2 q - med2) per patch pixel, to undo the MAD key transform below
             if (nvis == 0) {
                 sigma = DBL_EPSILON;  // the reference gets MAD = 0 from all-sentinel input
             } else {
@@ -884,24 +429,25 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
                 // element `mid` of the sorted N-vector (invalid rows sort last, so it is a valid one)
                 uint32_t kLo, dLo;
                 int tier;
-                const uint32_t kHi = tiered_select<G::AREA>(q, vis, KeySignedQ{}, 512 - 32, mid, evenAvg, brMed, sel, &kLo, &tier, sprof);
+                const uint32_t kHi = tiered_select<G::AREA>(key, vis, 512 - 32, mid, evenAvg, brMed, sc, &kLo, &tier);
                 tierCount += tier == 1 ? 1 : (tier == 2 ? 0x100 : 0x10000);
                 if (!evenAvg) kLo = kHi;
-                const int med2 = ((int)kHi - (1 << 25)) + ((int)kLo - (1 << 25));
-                KeyAbsDev2 kd{med2};
-                cMid = clock64();
-                const uint32_t dHi = tiered_select<G::AREA>(q, vis, kd, 0, mid, evenAvg, brMad, sel, &dLo, &tier, sprof);
+                med2 = ((int)kHi - (1 << 25)) + ((int)kLo - (1 << 25));
+                // keys in place: |2 q - med2|, deviations in half fixed-point units (2^-17)
+#pragma unroll
+                for (int i = 0; i < G::AREA; i++) {
+                    const int d = 2 * ((int)key[i] - (1 << 25)) - med2;
+                    negMask |= (d < 0 ? 1u : 0u) << i;
+                    key[i] = (uint32_t)abs(d);
+                }
+                const uint32_t dHi = tiered_select<G::AREA>(key, vis, 0, mid, evenAvg, brMad, sc, &dLo, &tier);
                 tierCount += tier == 1 ? 1 : (tier == 2 ? 0x100 : 0x10000);
                 if (!evenAvg) dLo = dHi;
-                if (a.dbg && job == 0 && tid == 64 && dbgEval < 24)
-                    a.dbg[32 + dbgEval] = ((long long)dHi << 32) | (uint32_t)((int)kHi - (1 << 25));
-                dbgEval++;
-                // deviations are in units of 2^-17
                 const double mad = 0.5 * ((double)dHi + (double)dLo);
                 sigma            = 1.482602218505602 * mad * (1.0 / 131072.0);
                 if (sigma <= DBL_EPSILON) sigma = DBL_EPSILON;
             }
-            const long long c2 = clock64();
+            SVO_TICK(c2);
             const double cD = 4.6851 * sigma;
             const float cF  = (float)cD;
             const float ic2 = (float)(1.0 / (cD * cD));
@@ -916,7 +462,10 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
                 for (int y = 0; y < P; y++) {
 #pragma unroll
                     for (int x = 0; x < P; x++) {
-                        const float rr = (float)q[y * P + x] * (1.f / 65536.f);
+                        // 2 q = med2 +/- |2 q - med2| (exact), r = q 2^-16
+                        const int i2   = y * P + x;
+                        const int q2   = med2 + (((negMask >> i2) & 1u) ? -(int)key[i2] : (int)key[i2]);
+                        const float rr = (float)q2 * (1.f / 131072.f);
                         const float gl = gridS[(size_t)((y + 1) * G::GW + x) * Fpad + f];
                         const float gr = gridS[(size_t)((y + 1) * G::GW + x + 2) * Fpad + f];
                         const float gu = gridS[(size_t)(y * G::GW + x + 1) * Fpad + f];
@@ -951,7 +500,7 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
                 for (int i = 0; i < 6; i++) val[21 + i] = bx * A[i] + by * B[i];
                 val[27] = ch;
             }
-            const long long c3 = clock64();
+            SVO_TICK(c3);
             // --- transposed warp reduction: afterwards lane i holds the warp total of val[i] ---
 #pragma unroll
             for (int s = 16; s >= 1; s >>= 1) {
@@ -977,13 +526,14 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
                 ctrl->evals_level++;
             }
             __syncthreads();
+#ifdef SVO_PROFILE
             const long long c4 = clock64();
-            tph[0] += c1 - c0;    // warp + window + bilinear + residual
-            tph[1] += cMid - c1;  // median select
-            tph[2] += c2 - cMid;  // MAD select
-            tph[3] += c3 - c2;    // weights + patch sums + expansion
-            tph[4] += c4 - c3;    // reductions
+            tph[0] += c1 - c0;  // warp + window + bilinear + residual (+ the wait for the previous solve)
+            tph[1] += c2 - c1;  // sigma: median + MAD selections
+            tph[3] += c3 - c2;  // weights + patch sums + expansion
+            tph[4] += c4 - c3;  // reductions
             tph[6] += 1;
+#endif
         };
 
         // record the first iteration of the level for the stats record
@@ -1013,7 +563,6 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
 #pragma unroll 1
         while (true) {
             evaluate();
-            const long long cs0 = clock64();
             if (tid == 0) {
                 double dx[6];
                 if (gn) {
@@ -1125,14 +674,12 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
                 set_Rt(ctrl);
             }
             __syncthreads();
-            tph[5] += clock64() - cs0;  // solve + pose update (all threads wait for thread 0)
             if (ctrl->done) break;
         }
+#ifdef SVO_PROFILE
         if (a.dbg && job == 0 && tid == 64)
-            for (int i = 0; i < 8; i++) {
-                a.dbg[si * 8 + i] = tph[i];
-                if (si < 1) a.dbg[32 + 24 + i] = sprof[i];  // coarsest level only (slots 56..63)
-            }
+            for (int i = 0; i < 8; i++) a.dbg[si * 8 + i] = tph[i];
+#endif
         if (tid == 0) {
             ctrl->evals_total += ctrl->evals_level;
             ctrl->iters_total += ctrl->iters_level;

@@ -16,12 +16,8 @@ for mode in (2, 1, 0):
         ev = dd.reshape(-1)[32:32 + min(24, res[0]['evaluations'])]
         med = (ev & 0xffffffff).astype(np.uint32).view(np.int32) / 65536.0
         mad = (ev >> 32) / 131072.0
-        sp = dd.reshape(-1)[56:64]
-        print('select profile (coarsest level): hot-hit cyc %d n %d | hot-miss cyc %d n %d | 2 private passes cyc %d, bracket after cyc %d, n %d' % (sp[0], sp[4], sp[1], sp[5], sp[2], sp[3], sp[6]))
-        print('median per eval:', np.round(med, 4))
-        print('MAD per eval   :', np.round(mad, 4))
         print("mode", mode, "evals", res[0]["evaluations"], "tiers", hex(res[0]["reserved"]))
-        print("per level [warp+sample, sel med, sel mad, sums, reduce, solve, n_eval]:")
+        print("per level [wait-solve+warp+sample, sigma, -, sums, reduce, -, n_eval]:")
         print(d[:, :7])
         tot = d[:, :6].sum(0); n = d[:, 6].sum()
         print("cycles per evaluation:", (tot / n).round(0), "total", (tot.sum() / n).round(0), "=> us/eval %.2f" % (tot.sum() / n / 1965))
