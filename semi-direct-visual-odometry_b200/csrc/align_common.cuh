@@ -1,4 +1,4 @@
-// align_common.cuh -- optimiser state and small helpers shared by the alignment kernels (v1 generic, v2 fast path)
+// align_common.cuh -- optimiser state and small helpers shared by the alignment kernels (generic kernel sparse_align.cu, cluster fast path sparse_align_v3.cu)
 #pragma once
 #include "ctx.h"
 #include "math.cuh"

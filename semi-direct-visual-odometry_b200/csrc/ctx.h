@@ -81,6 +81,7 @@ struct svo_ctx {
     const svo_align_job* src_jobs;      // where the H2D of the staged batch reads from (pinned user memory or h_jobs)
     const svo_align_feature* src_feats;
     svo_align_params staged_params;
+    int last_align_nt, last_align_c;    // shape of the last cluster launch (threads per CTA, CTAs per pair)
 
     // feature alignment batch
     svo_fa_item* h_fa_items;     // pinned
@@ -128,5 +129,5 @@ svo_status launch_grid_select(svo_ctx* ctx, int slot, int cell, uint32_t thr, in
 svo_status launch_sparse_align(svo_ctx* ctx);
 svo_status launch_feature_align(svo_ctx* ctx);
 size_t sparse_align_smem_bytes(int nthreads, int max_features, int patch_area);
-bool sparse_align_v2_supported(const svo_ctx* ctx, int maxF);
-svo_status launch_sparse_align_v2(svo_ctx* ctx, int maxF);
+bool sparse_align_v3_supported(const svo_ctx* ctx, int maxF);
+svo_status launch_sparse_align_v3(svo_ctx* ctx, int maxF);

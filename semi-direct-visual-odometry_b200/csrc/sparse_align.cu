@@ -722,11 +722,12 @@ svo_status launch_sparse_align(svo_ctx* ctx)
     // feature capacity of this launch: the largest job, rounded up (keeps shared memory small for small jobs)
     int maxF = 1;
     for (int j = 0; j < nJobs; j++) maxF = std::max(maxF, ctx->src_jobs[j].n_ref + ctx->src_jobs[j].n_kf);
-    // fast path (sparse_align_v2.cu): patch 4 / 5, <= 512 features per pair.  SVO_ALIGN_GENERIC=1 forces the generic
-    // kernel below (A/B measurements); both are CUDA paths -- there is no CPU fallback anywhere.
+    // fast path (sparse_align_v3.cu): patch 4 / 5, a thread-block cluster per pair, <= 2,048 features per pair.
+    // SVO_ALIGN_GENERIC=1 forces the generic kernel below (A/B measurements); both are CUDA paths, there is no CPU
+    // fallback anywhere.
     {
         const char* e = getenv("SVO_ALIGN_GENERIC");
-        if (!(e && e[0] == '1') && sparse_align_v2_supported(ctx, maxF)) return launch_sparse_align_v2(ctx, maxF);
+        if (!(e && e[0] == '1') && sparse_align_v3_supported(ctx, maxF)) return launch_sparse_align_v3(ctx, maxF);
     }
     maxF = (maxF + 15) & ~15;
     if ((int64_t)maxF * area >= 65536) SVO_FAIL(SVO_ERR_CAPACITY, "features * patch area must stay below 65536");

@@ -1,33 +1,38 @@
-// sparse_align_v2.cu -- fast path of ImageAlignment::align (src/image_alignment.cpp:25-67) for patch sizes 4 / 5 and
-// at most 512 features per frame pair.  Two kernels:
+// sparse_align_v3.cu -- fast path of ImageAlignment::align (src/image_alignment.cpp:25-67) for patch sizes 4 / 5: one
+// THREAD-BLOCK CLUSTER per frame pair.  Two kernels:
 //
 // k_align_precompute<P>  (computeJacobian, :69-192, for ALL levels at once; one thread per job x level x feature)
 //     FP64: world point p_W = T_frame^-1 (bearing |P - C|), visibility at the level, the 2x6 image Jacobian rows A, B
 //     (computeImageJac, :194-248) and the (P+2)^2 grid of bilinear template samples around the feature, from which
-//     T (centre P x P), gx and gy (central differences) follow.  Written feature-minor to an HBM scratch so that the
-//     iterate kernel reads a level with ONE bulk async copy.
+//     T (centre P x P), gx and gy (central differences) follow.  Written feature-minor, one contiguous block per
+//     (CTA of the cluster, level), so that the iterate kernel stages a level with ONE bulk async copy.
 //
-// k_align_iterate<P>     (optimizeLM / optimizeGN, src/optimizer.cpp:41-370, over all levels; one CTA per pair,
-//                         persistent: never returns to the host between iterations)
-//     thread f owns feature f.  Per evaluation (computeResiduals, :251-370 + tukeyWeighting + normal equations):
+// k_align_cluster<P, NT> (optimizeLM / optimizeGN, src/optimizer.cpp:41-370, over all levels; a cluster of C CTAs of
+//                         NT threads per pair, persistent: never returns to the host between iterations)
+//     CTA r of the cluster owns features [r NT, (r+1) NT), thread f owns one feature.  C x NT >= features: 500
+//     features run as 2 x 256 (two CTAs of DIFFERENT pairs share an SM, so the serial phases of one pair overlap the
+//     parallel phases of another), 1,000 features as 4 x 256, a single latency-critical pair as 8 x 64 on 8 SMs.
+//     Per evaluation (computeResiduals, :251-370 + tukeyWeighting + normal equations):
 //       warp      p_cur = R p_W + t, project, scale (FP64)
 //       sample    the (P+1)^2 footprint of the current image lives in REGISTERS (8-byte row windows) and is re-fetched
 //                 from L2 only when the feature's integer position leaves the window; bilinear in FP32
 //       residual  r = I - T, kept in registers as fixed point q = rint(r 2^16) (|r| <= 255 is exact in 25 bits)
-//       sigma     1.4826 MAD by two exact order statistics: block-wide MSD radix select on the fixed-point keys
-//                 (6+6 bit passes on thread-private shared-memory counters, 9+6 bit passes on shared atomics)
+//       sigma     1.4826 MAD by two exact order statistics over the keys of the whole cluster (cluster_select.cuh:
+//                 per-CTA shared-memory histograms combined through distributed shared memory, one cluster barrier
+//                 per sweep)
 //       reduce    per-feature patch sums sxx sxy syy bx by chi2 -> 28 entries of J^T W J, J^T W r, chi2 through the
-//                 factorisation J_row = gx A + gy B; transposed warp-shuffle reduction, FP64 across warps
-//       solve     damping, pivoted LDLT 6x6, pose <- pose exp(-dx) in FP64 on one thread; accept / reject on device
+//                 factorisation J_row = gx A + gy B; transposed warp-shuffle reduction, FP64 across warps, then across
+//                 the CTAs of the cluster in a fixed order (every CTA gets bit-identical sums)
+//       solve     damping, LDLT 6x6, pose <- pose exp(-dx) in FP64, redundantly in every CTA (no broadcast); accept /
+//                 reject on device
 #include <float.h>
+#include <stdlib.h>
 
 #include "align_common.cuh"
-#include "block_select.cuh"
+#include "cluster_select.cuh"
 
 namespace {
 
-constexpr int NT       = 512;
-constexpr int NW       = NT / 32;
 constexpr unsigned FULL = 0xffffffffu;
 
 template <int P>
@@ -40,15 +45,17 @@ struct PatchGeo {
     static constexpr int ROWW = GA + 12 + 1;  // scratch words per feature and level: grid, A, B, flag
 };
 
-struct V2Args {
+struct V3Args {
     ArenaView view;
     const svo_align_job* jobs;
     const svo_align_feature* feats;
     svo_align_result* results;
     svo_align_level_stats* stats;  // nullable
-    float* scratch;                // [job][ pW: 3*Fpad doubles | level blocks: ROWW*Fpad floats each ]
+    float* scratch;                // [job][chunk = CTA of the cluster][ pW: 3*NT doubles | level blocks: ROWW*NT floats each ]
     long long job_stride;          // floats per job in scratch
-    int Fpad;                      // features per job rounded up (multiple of 32, <= NT)
+    long long chunk_stride;        // floats per chunk
+    int NT;                        // threads (= features) per CTA
+    int C;                         // CTAs per cluster (= chunks per job)
     svo_align_params prm;
     double K[4];
     long long* dbg;                // nullable: per-phase cycle counters of job 0 (svo_debug_cycles)
@@ -60,20 +67,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // precompute
 // ------------------------------------------------------------------------------------------------------------
 template <int P>
-__global__ void __launch_bounds__(128) k_align_precompute(const V2Args a)
+__global__ void __launch_bounds__(128) k_align_precompute(const V3Args a)
 {
     using G = PatchGeo<P>;
-    const int nLevels = a.prm.max_level - a.prm.min_level + 1;
-    const int f       = blockIdx.x * blockDim.x + threadIdx.x;
-    const int si      = blockIdx.y;  // 0 = coarsest
-    const int job     = blockIdx.z;
-    if (f >= a.Fpad) return;
+    const int f   = blockIdx.x * blockDim.x + threadIdx.x;  // feature slot of the job
+    const int si  = blockIdx.y;                             // 0 = coarsest
+    const int job = blockIdx.z;
+    const int NT  = a.NT;
+    if (f >= a.C * NT) return;
     const int level        = a.prm.max_level - si;
     const svo_align_job* J = a.jobs + job;
     const int nRef = J->n_ref, F = J->n_ref + J->n_kf;
-    float* base    = a.scratch + (long long)job * a.job_stride;
+    const int fl   = f % NT;  // column inside the chunk
+    float* base    = a.scratch + (long long)job * a.job_stride + (long long)(f / NT) * a.chunk_stride;
     double* pWout  = reinterpret_cast<double*>(base);
-    float* blk     = base + 6 * a.Fpad + (long long)si * G::ROWW * a.Fpad;
+    float* blk     = base + 6 * NT + (long long)si * G::ROWW * NT;
     uint32_t flag  = 0;
     if (f < F) {
         const svo_align_feature* ft = a.feats + J->feat_offset + f;
@@ -93,9 +101,9 @@ __global__ void __launch_bounds__(128) k_align_precompute(const V2Args a)
             double pW[3];
             svo::pose_inv_act(Tf, pC, pW);
             if (si == 0) {
-                pWout[0 * a.Fpad + f] = pW[0];
-                pWout[1 * a.Fpad + f] = pW[1];
-                pWout[2 * a.Fpad + f] = pW[2];
+                pWout[0 * NT + fl] = pW[0];
+                pWout[1 * NT + fl] = pW[1];
+                pWout[2 * NT + fl] = pW[2];
             }
             const int lw = a.view.w[level], lh = a.view.h[level], lpitch = a.view.pitch[level];
             const double denom = (double)(1 << level);
@@ -110,19 +118,19 @@ __global__ void __launch_bounds__(128) k_align_precompute(const V2Args a)
                 const double fx = a.K[0] / denom, fy = a.K[1] / denom;
                 const double x = pW[0], y = pW[1], z = pW[2];
                 const double x2 = x * x, y2 = y * y, z2 = z * z;
-                float* jf = blk + (long long)G::GA * a.Fpad + f;
-                jf[0 * a.Fpad]  = (float)(fx / z);
-                jf[1 * a.Fpad]  = 0.f;
-                jf[2 * a.Fpad]  = (float)(-(fx * x) / z2);
-                jf[3 * a.Fpad]  = (float)(-(fx * x * y) / z2);
-                jf[4 * a.Fpad]  = (float)((fx * x2) / z2 + fx);
-                jf[5 * a.Fpad]  = (float)(-(fx * y) / z);
-                jf[6 * a.Fpad]  = 0.f;
-                jf[7 * a.Fpad]  = (float)(fy / z);
-                jf[8 * a.Fpad]  = (float)(-(fy * y) / z2);
-                jf[9 * a.Fpad]  = (float)(-(fy * y2) / z2 - fy);
-                jf[10 * a.Fpad] = (float)((fy * x * y) / z2);
-                jf[11 * a.Fpad] = (float)((fy * x) / z);
+                float* jf = blk + G::GA * NT + fl;
+                jf[0 * NT]  = (float)(fx / z);
+                jf[1 * NT]  = 0.f;
+                jf[2 * NT]  = (float)(-(fx * x) / z2);
+                jf[3 * NT]  = (float)(-(fx * x * y) / z2);
+                jf[4 * NT]  = (float)((fx * x2) / z2 + fx);
+                jf[5 * NT]  = (float)(-(fx * y) / z);
+                jf[6 * NT]  = 0.f;
+                jf[7 * NT]  = (float)(fy / z);
+                jf[8 * NT]  = (float)(-(fy * y) / z2);
+                jf[9 * NT]  = (float)(-(fy * y2) / z2 - fy);
+                jf[10 * NT] = (float)((fy * x * y) / z2);
+                jf[11 * NT] = (float)((fy * x) / z);
                 // template grid: bilinear samples at (u + gx - 1 + PB, v + gy - 1 + PB), gx, gy in [0, GW)
                 const uint8_t* img = a.view.img[level] +
                                      (long long)(f < nRef ? J->ref_slot : J->kf_slot) * a.view.plane_stride[level] +
@@ -142,7 +150,7 @@ __global__ void __launch_bounds__(128) k_align_precompute(const V2Args a)
                     if (ry > 0) {
 #pragma unroll
                         for (int cx = 0; cx < G::GW; cx++)
-                            blk[(long long)((ry - 1) * G::GW + cx) * a.Fpad + f] = (float)(wv0 * prev[cx] + fv * cur[cx]);  // :903
+                            blk[((ry - 1) * G::GW + cx) * NT + fl] = (float)(wv0 * prev[cx] + fv * cur[cx]);  // :903
                     }
 #pragma unroll
                     for (int cx = 0; cx < G::GW; cx++) prev[cx] = cur[cx];
@@ -150,66 +158,71 @@ __global__ void __launch_bounds__(128) k_align_precompute(const V2Args a)
             }
         }
     }
-    reinterpret_cast<uint32_t*>(blk)[(long long)(G::GA + 12) * a.Fpad + f] = flag;
+    reinterpret_cast<uint32_t*>(blk)[(G::GA + 12) * NT + fl] = flag;
 }
 
 // ------------------------------------------------------------------------------------------------------------
 // iterate
 // ------------------------------------------------------------------------------------------------------------
-template <int P>
-__host__ __device__ constexpr size_t v2_smem_bytes(int Fpad)
+template <int P, int NT>
+__host__ __device__ constexpr size_t v3_smem_bytes()
 {
     using G = PatchGeo<P>;
     size_t b = 0;
-    b += (size_t)G::ROWW * Fpad * 4;  // level block (grid, jac, flags): one bulk copy
-    b += (size_t)3 * Fpad * 8;        // pW
-    b += SEL_SMEM_BYTES;              // selection scratch (block_select.cuh)
-    b += (size_t)NW * 32 * 8;         // red
+    b += (size_t)G::ROWW * NT * 4;    // level block (grid, jac, flags): one bulk copy
+    b += (size_t)3 * NT * 8;          // pW
+    b += cs_smem_bytes<NT>();         // selection rounds (cluster_select.cuh)
+    b += (size_t)(NT / 32) * 32 * 8;  // red
+    b += 2 * 32 * 8;                  // xE: this CTA's 28 sums, ping-pong, read by the whole cluster
     b += sizeof(Ctrl) + 64;
     return b + 1024;                  // alignment slack
 }
 
-template <int P>
-__global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
+template <int NT>
+struct V3Occ {  // CTAs per SM the register file allows at 128 registers per thread
+    static constexpr int MINB = NT >= 512 ? 1 : (NT == 256 ? 2 : 4);
+};
+
+template <int P, int NT>
+__global__ void __launch_bounds__(NT, V3Occ<NT>::MINB) k_align_cluster(const V3Args a)
 {
-    using G = PatchGeo<P>;
+    using G          = PatchGeo<P>;
+    constexpr int NW = NT / 32;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int job = blockIdx.x;
+    const int C        = a.C;
+    const int job      = blockIdx.x / C;
+    const int crank    = blockIdx.x % C;  // == %cluster_ctarank: clusters are C consecutive CTAs along x
     const svo_align_job* J = a.jobs + job;
     const int F       = J->n_ref + J->n_kf;
-    const int Fpad    = a.Fpad;
     const int nLevels = a.prm.max_level - a.prm.min_level + 1;
+    svo_align_level_stats* statsOut = crank == 0 ? a.stats : nullptr;  // CTA 0 of the cluster reports
 
     // ---- shared memory carve-up ----
     unsigned char* sp = smem_raw;
-    float* blk        = reinterpret_cast<float*>(sp);  // [ROWW][Fpad]
-    sp += (size_t)G::ROWW * Fpad * 4;
-    double* pWs = reinterpret_cast<double*>(sp);  // [3][Fpad]
-    sp += (size_t)3 * Fpad * 8;
-    SelCtx sc;
-    sc.pp     = 0;
-    sc.s.priv = reinterpret_cast<uint32_t*>(sp);
-    sp += (size_t)16 * NT * 4;
-    sc.s.bins = reinterpret_cast<uint32_t*>(sp);
-    sp += 2 * 512 * 4;
-    sc.s.tot = reinterpret_cast<uint32_t*>(sp);
-    sp += 64 * 4;
-    sc.s.wtot = reinterpret_cast<uint32_t*>(sp);
-    sp += 4 * NW * 4;
+    float* blk        = reinterpret_cast<float*>(sp);  // [ROWW][NT]
+    sp += (size_t)G::ROWW * NT * 4;
+    double* pWs = reinterpret_cast<double*>(sp);  // [3][NT]
+    sp += (size_t)3 * NT * 8;
+    SelCtx<NT> sc;
+    sc.init(sp, C);
+    sp += cs_smem_bytes<NT>();
     sp          = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sp) + 15) & ~uintptr_t(15));
     double* red = reinterpret_cast<double*>(sp);  // [NW][32]
     sp += (size_t)NW * 32 * 8;
+    double* xE = reinterpret_cast<double*>(sp);   // [2][32]
+    sp += 2 * 32 * 8;
     unsigned long long* mbar = reinterpret_cast<unsigned long long*>(sp);
     sp += 16;
     Ctrl* ctrl = reinterpret_cast<Ctrl*>(sp);
+    int pe     = 0;  // which half of xE the next reduction uses
 
     const float* gridS    = blk;
-    const float* jacS     = blk + (size_t)G::GA * Fpad;
-    const uint32_t* flagS = reinterpret_cast<const uint32_t*>(blk + (size_t)(G::GA + 12) * Fpad);
+    const float* jacS     = blk + (size_t)G::GA * NT;
+    const uint32_t* flagS = reinterpret_cast<const uint32_t*>(blk + (size_t)(G::GA + 12) * NT);
 
-    if (J->n_ref == 0) {  // src/image_alignment.cpp:27-28
-        if (tid == 0) {
+    if (J->n_ref == 0) {  // src/image_alignment.cpp:27-28 (uniform over the cluster)
+        if (tid == 0 && crank == 0) {
             svo_align_result res;
             for (int i = 0; i < 7; i++) res.T_cur[i] = J->T_cur[i];
             res.rmse        = 0.0;
@@ -222,10 +235,7 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
         return;
     }
 
-    const float* scr = a.scratch + (long long)job * a.job_stride;
-    for (int i = tid; i < 16 * NT; i += NT) sc.s.priv[i] = 0;
-    sc.s.bins[tid]       = 0;
-    sc.s.bins[512 + tid] = 0;
+    const float* scr = a.scratch + (long long)job * a.job_stride + (long long)crank * a.chunk_stride;
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(mbar)), "r"(1));
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -239,11 +249,15 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
         ctrl->status      = SVO_ST_FAILED;
         ctrl->rmse        = 0.0;
     }
-    __syncthreads();
+    // the selection buffers of every CTA are zero before any CTA of the cluster reads them
+    if (C > 1)
+        cs_cluster_sync();
+    else
+        __syncthreads();
     uint32_t mphase = 0;
     // world points (level independent): bulk copy HBM -> shared
     if (tid == 0) {
-        const uint32_t bytes = (uint32_t)(3 * Fpad * 8);
+        const uint32_t bytes = (uint32_t)(3 * NT * 8);
         asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
         asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
                          smem_u32(pWs)),
@@ -259,12 +273,13 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
                          : "memory");
         mphase ^= 1;
     }
-    const int f = tid;
+    const int f  = tid;               // column of this thread's feature inside the CTA's chunk
+    const int fg = crank * NT + tid;  // feature slot of the job
     double pwx = 0, pwy = 0, pwz = 1;
-    if (f < F) {
+    if (fg < F) {
         pwx = pWs[f];
-        pwy = pWs[Fpad + f];
-        pwz = pWs[2 * Fpad + f];
+        pwy = pWs[NT + f];
+        pwz = pWs[2 * NT + f];
     }
     const double fx0 = a.K[0], fy0 = a.K[1], cx0 = a.K[2], cy0 = a.K[3];
     const int border = P / 2 + 2;
@@ -279,8 +294,8 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
         // ---- the level's template block: one bulk async copy HBM -> shared ----
         __syncthreads();  // everyone is done with the previous level's block
         if (tid == 0) {
-            const uint32_t bytes = (uint32_t)(G::ROWW * Fpad * 4);
-            const float* src     = scr + 6 * Fpad + (long long)si * G::ROWW * Fpad;
+            const uint32_t bytes = (uint32_t)(G::ROWW * NT * 4);
+            const float* src     = scr + 6 * NT + (long long)si * G::ROWW * NT;
             asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
             asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(mbar)), "r"(bytes) : "memory");
             asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
@@ -310,7 +325,7 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
             mphase ^= 1;
         }
         __syncthreads();  // ctrl init visible
-        const bool refvis = f < F && flagS[f] != 0;
+        const bool refvis = fg < F && flagS[f] != 0;
 
         // current-image window of this feature: FW rows x 8 bytes starting at column wx, row wy
         uint32_t winLo[G::FW], winHi[G::FW];
@@ -401,7 +416,7 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
 #pragma unroll
                         for (int c = 0; c < P; c++) {
                             const float val = wv0 * prevRow[c] + fv * curRow[c];
-                            const float T   = gridS[(size_t)((r - 1 + 1) * G::GW + (c + 1)) * Fpad + f];
+                            const float T   = gridS[(size_t)((r - 1 + 1) * G::GW + (c + 1)) * NT + f];
                             key[(r - 1) * P + c] = (uint32_t)(__float2int_rn((val - T) * 65536.f) + (1 << 25));
                         }
                     }
@@ -412,40 +427,38 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
 #pragma unroll
                 for (int i = 0; i < G::AREA; i++) key[i] = 0;
             }
-            const int nvis     = __syncthreads_count(vis);
+            // visible features of the cluster: summed at the first barrier of the median selection
+            sc.add_aux((uint32_t)__popc(__ballot_sync(FULL, vis)));
             SVO_TICK(c1);
-            const int numValid = nvis * G::AREA;
-            const int N        = F * G::AREA;
+            const int N = F * G::AREA;
 
             // --- sigma = 1.4826 MAD, src/optimizer.cpp:485-507, src/algorithm.cpp:834-872 (MEDIAN_EXACT) ---
-            double sigma;
-            int med2         = 0;  // twice the median, fixed point
-            uint32_t negMask = 0;  // sign of (2 q - med2) per patch pixel, to undo the MAD key transform below
-            if (nvis == 0) {
-                sigma = DBL_EPSILON;  // the reference gets MAD = 0 from all-sentinel input
-            } else {
-                const int mid      = numValid / 2;
-                const bool evenAvg = !(N & 1) && mid > 0;  // mean of elements mid-1 and mid
-                // element `mid` of the sorted N-vector (invalid rows sort last, so it is a valid one)
-                uint32_t kLo, dLo;
+            double sigma     = DBL_EPSILON;  // no visible pixel: the reference gets MAD = 0 from all-sentinel input
+            int med2         = 0;            // twice the median, fixed point
+            uint32_t negMask = 0;            // sign of (2 q - med2) per patch pixel, to undo the MAD key transform below
+            int mid          = 0;            // numValid / 2: element `mid` of the sorted N-vector (invalid rows sort last)
+            int numValid     = 0;
+            {
+                uint32_t kHi, kLo, dHi, dLo;
                 int tier;
-                const uint32_t kHi = tiered_select<G::AREA>(key, vis, 512 - 32, mid, evenAvg, brMed, sc, &kLo, &tier);
-                tierCount += tier == 1 ? 1 : (tier == 2 ? 0x100 : 0x10000);
-                if (!evenAvg) kLo = kHi;
-                med2 = ((int)kHi - (1 << 25)) + ((int)kLo - (1 << 25));
-                // keys in place: |2 q - med2|, deviations in half fixed-point units (2^-17)
+                // mean of elements mid-1 and mid when N is even: the selection returns both
+                if (cs_tiered_select<G::AREA, NT>(key, vis, 512 - 32, mid, true, N, brMed, sc, &kHi, &kLo, &tier)) {
+                    numValid = (int)sc.auxTotal * G::AREA;
+                    tierCount += tier == 1 ? 1 : (tier == 2 ? 0x100 : 0x10000);
+                    med2 = ((int)kHi - (1 << 25)) + ((int)kLo - (1 << 25));
+                    // keys in place: |2 q - med2|, deviations in half fixed-point units (2^-17)
 #pragma unroll
-                for (int i = 0; i < G::AREA; i++) {
-                    const int d = 2 * ((int)key[i] - (1 << 25)) - med2;
-                    negMask |= (d < 0 ? 1u : 0u) << i;
-                    key[i] = (uint32_t)abs(d);
+                    for (int i = 0; i < G::AREA; i++) {
+                        const int d = 2 * ((int)key[i] - (1 << 25)) - med2;
+                        negMask |= (d < 0 ? 1u : 0u) << i;
+                        key[i] = (uint32_t)abs(d);
+                    }
+                    cs_tiered_select<G::AREA, NT>(key, vis, 0, mid, false, N, brMad, sc, &dHi, &dLo, &tier);
+                    tierCount += tier == 1 ? 1 : (tier == 2 ? 0x100 : 0x10000);
+                    const double mad = 0.5 * ((double)dHi + (double)dLo);
+                    sigma            = 1.482602218505602 * mad * (1.0 / 131072.0);
+                    if (sigma <= DBL_EPSILON) sigma = DBL_EPSILON;
                 }
-                const uint32_t dHi = tiered_select<G::AREA>(key, vis, 0, mid, evenAvg, brMad, sc, &dLo, &tier);
-                tierCount += tier == 1 ? 1 : (tier == 2 ? 0x100 : 0x10000);
-                if (!evenAvg) dLo = dHi;
-                const double mad = 0.5 * ((double)dHi + (double)dLo);
-                sigma            = 1.482602218505602 * mad * (1.0 / 131072.0);
-                if (sigma <= DBL_EPSILON) sigma = DBL_EPSILON;
             }
             SVO_TICK(c2);
             const double cD = 4.6851 * sigma;
@@ -466,10 +479,10 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
                         const int i2   = y * P + x;
                         const int q2   = med2 + (((negMask >> i2) & 1u) ? -(int)key[i2] : (int)key[i2]);
                         const float rr = (float)q2 * (1.f / 131072.f);
-                        const float gl = gridS[(size_t)((y + 1) * G::GW + x) * Fpad + f];
-                        const float gr = gridS[(size_t)((y + 1) * G::GW + x + 2) * Fpad + f];
-                        const float gu = gridS[(size_t)(y * G::GW + x + 1) * Fpad + f];
-                        const float gd = gridS[(size_t)((y + 2) * G::GW + x + 1) * Fpad + f];
+                        const float gl = gridS[(size_t)((y + 1) * G::GW + x) * NT + f];
+                        const float gr = gridS[(size_t)((y + 1) * G::GW + x + 2) * NT + f];
+                        const float gu = gridS[(size_t)(y * G::GW + x + 1) * NT + f];
+                        const float gd = gridS[(size_t)((y + 2) * G::GW + x + 1) * NT + f];
                         const float gx = 0.5f * (gr - gl), gy = 0.5f * (gd - gu);
                         float w        = 0.f;
                         if (fabsf(rr) <= cF) {
@@ -488,8 +501,8 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
                 float A[6], B[6];
 #pragma unroll
                 for (int i = 0; i < 6; i++) {
-                    A[i] = jacS[(size_t)i * Fpad + f];
-                    B[i] = jacS[(size_t)(6 + i) * Fpad + f];
+                    A[i] = jacS[(size_t)i * NT + f];
+                    B[i] = jacS[(size_t)(6 + i) * NT + f];
                 }
                 int k = 0;
 #pragma unroll
@@ -514,11 +527,26 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
             }
             red[warp * 32 + lane] = (double)val[0];
             __syncthreads();
-            if (tid < 28) {
-                double s = 0.0;
+            if (C == 1) {
+                if (tid < 28) {
+                    double s = 0.0;
 #pragma unroll
-                for (int w = 0; w < NW; w++) s += red[w * 32 + tid];
-                ctrl->E[tid] = s;
+                    for (int w = 0; w < NW; w++) s += red[w * 32 + tid];
+                    ctrl->E[tid] = s;
+                }
+            } else {
+                // this CTA's sums -> xE, then every CTA adds the C copies in the same order: bit-identical E everywhere
+                if (tid < 28) {
+                    double s = 0.0;
+#pragma unroll
+                    for (int w = 0; w < NW; w++) s += red[w * 32 + tid];
+                    xE[pe * 32 + tid] = s;
+                }
+                cs_cluster_sync();
+                if (tid < 28) {
+                    ctrl->E[tid] = cs_gather_sum_f64(smem_u32(xE + pe * 32 + tid), C);
+                }
+                pe ^= 1;
             }
             if (tid == 32) {
                 ctrl->sigma  = sigma;
@@ -540,8 +568,8 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
         auto record_first = [&](const double* E, double chi2, double lambda, int n) {
             if (!ctrl->first) return;
             ctrl->first = 0;
-            if (a.stats) {
-                svo_align_level_stats* s = a.stats + (size_t)job * nLevels + si;
+            if (statsOut) {
+                svo_align_level_stats* s = statsOut + (size_t)job * nLevels + si;
                 double H[36], g[6];
                 expand_H(E, H, g);
                 for (int i = 0; i < 36; i++) s->H[i] = H[i];
@@ -571,8 +599,8 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
                     const bool wasFirst = ctrl->first;
                     record_first(ctrl->E, chi2, 0.0, ctrl->n_eval);
                     solve6(ctrl->E, 0.0, dx);
-                    if (wasFirst && a.stats)
-                        for (int i = 0; i < 6; i++) a.stats[(size_t)job * nLevels + si].dx[i] = dx[i];
+                    if (wasFirst && statsOut)
+                        for (int i = 0; i < 6; i++) statsOut[(size_t)job * nLevels + si].dx[i] = dx[i];
                     ctrl->iters_level++;
                     double mx = dx[0];
                     bool nan  = false;
@@ -643,8 +671,8 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
                         const bool wasFirst = ctrl->first;
                         record_first(ctrl->curE, ctrl->curE[27], lambda, ctrl->cur_n);
                         solve6(ctrl->curE, lambda, dx);
-                        if (wasFirst && a.stats)
-                            for (int i = 0; i < 6; i++) a.stats[(size_t)job * nLevels + si].dx[i] = dx[i];
+                        if (wasFirst && statsOut)
+                            for (int i = 0; i < 6; i++) statsOut[(size_t)job * nLevels + si].dx[i] = dx[i];
                         svo::pose_update_right_exp_neg(ctrl->pose, dx);  // :310 applied before any check
                         ctrl->iters_level++;
                         double mx = dx[0], step = 0;
@@ -677,14 +705,14 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
             if (ctrl->done) break;
         }
 #ifdef SVO_PROFILE
-        if (a.dbg && job == 0 && tid == 64)
+        if (a.dbg && job == 0 && crank == 0 && tid == 33)
             for (int i = 0; i < 8; i++) a.dbg[si * 8 + i] = tph[i];
 #endif
         if (tid == 0) {
             ctrl->evals_total += ctrl->evals_level;
             ctrl->iters_total += ctrl->iters_level;
-            if (a.stats) {
-                svo_align_level_stats* s = a.stats + (size_t)job * nLevels + si;
+            if (statsOut) {
+                svo_align_level_stats* s = statsOut + (size_t)job * nLevels + si;
                 for (int i = 0; i < 4; i++) s->pose_after[i] = ctrl->pose.q[i];
                 for (int i = 0; i < 3; i++) s->pose_after[4 + i] = ctrl->pose.t[i];
                 s->rmse        = ctrl->rmse;
@@ -695,7 +723,7 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
         }
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && crank == 0) {
         svo_align_result res;
         for (int i = 0; i < 4; i++) res.T_cur[i] = ctrl->pose.q[i];
         for (int i = 0; i < 3; i++) res.T_cur[4 + i] = ctrl->pose.t[i];
@@ -706,18 +734,74 @@ __global__ void __launch_bounds__(NT, 1) k_align_iterate(const V2Args a)
         res.reserved    = (int32_t)tierCount;
         a.results[job]  = res;
     }
+    if (C > 1) cs_cluster_sync();  // no CTA leaves while a peer may still read its shared memory
+}
+
+template <int P, int NT>
+svo_status launch_v3_nt(svo_ctx* ctx, const V3Args& args, int nJobs)
+{
+    const size_t smem = v3_smem_bytes<P, NT>();
+    SVO_CUDA(cudaFuncSetAttribute(k_align_cluster<P, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim          = dim3((unsigned)(nJobs * args.C), 1, 1);
+    cfg.blockDim         = dim3(NT, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream           = ctx->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id               = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = (unsigned)args.C;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs              = at;
+    cfg.numAttrs           = 1;
+    SVO_CUDA(cudaLaunchKernelEx(&cfg, k_align_cluster<P, NT>, args));
+    return SVO_OK;
+}
+
+// Shape of the launch: NT threads (= features) per CTA, C CTAs per pair.  Measured on B200 (profiles/): a cluster
+// barrier with release / acquire semantics costs more than the work it spreads as long as one CTA can hold the pair,
+// so C = 1 up to 512 features (the smallest CTA that covers them: more co-resident CTAs per SM), and clusters of 2 / 4
+// CTAs of 512 threads beyond (1,000 features = 2 x 512).  SVO_ALIGN_NT / SVO_ALIGN_C override (experiments).
+void v3_shape(const svo_ctx* ctx, int maxF, int nJobs, int* NT, int* C)
+{
+    (void)ctx;
+    (void)nJobs;
+    int c = (maxF + 511) / 512;
+    if (c < 1) c = 1;
+    if (c == 3) c = 4;
+    if (c > 4) c = 8;
+    int nt = 64;
+    while (nt < 512 && nt * c < maxF) nt *= 2;
+    if (const char* e = getenv("SVO_ALIGN_NT")) {
+        const int v = atoi(e);
+        if (v == 64 || v == 128 || v == 256 || v == 512) {
+            nt = v;
+            c  = (maxF + nt - 1) / nt;
+            if (c < 1) c = 1;
+            if (c == 3) c = 4;
+            if (c > 4 && c < 8) c = 8;
+        }
+    }
+    if (const char* e = getenv("SVO_ALIGN_C")) {
+        const int v = atoi(e);
+        if ((v == 1 || v == 2 || v == 4 || v == 8) && v * nt >= maxF) c = v;
+    }
+    *NT = nt;
+    *C  = c;
 }
 
 template <int P>
-svo_status launch_v2(svo_ctx* ctx, int maxF)
+svo_status launch_v3(svo_ctx* ctx, int maxF)
 {
     using G                     = PatchGeo<P>;
     const svo_align_params& prm = ctx->staged_params;
     const int nJobs             = ctx->staged_jobs;
     const int nLevels           = prm.max_level - prm.min_level + 1;
-    const int Fpad              = (maxF + 31) & ~31;
-    const long long job_stride  = 6LL * Fpad + (long long)nLevels * G::ROWW * Fpad;  // floats
-    const size_t need           = (size_t)job_stride * 4 * nJobs;
+    int NT, C;
+    v3_shape(ctx, maxF, nJobs, &NT, &C);
+    const long long chunk_stride = 6LL * NT + (long long)nLevels * G::ROWW * NT;  // floats
+    const long long job_stride   = chunk_stride * C;
+    const size_t need            = (size_t)job_stride * 4 * nJobs;
     if (need > ctx->scratch2_bytes) {
         SVO_CUDA(cudaStreamSynchronize(ctx->stream));
         if (ctx->d_scratch2) SVO_CUDA(cudaFree(ctx->d_scratch2));
@@ -726,43 +810,51 @@ svo_status launch_v2(svo_ctx* ctx, int maxF)
         SVO_CUDA(cudaMalloc(&ctx->d_scratch2, need));
         ctx->scratch2_bytes = need;
     }
-    V2Args args;
-    args.view       = make_view(ctx->arena);
-    args.jobs       = ctx->d_jobs;
-    args.feats      = ctx->d_feats;
-    args.results    = ctx->d_results;
-    args.stats      = ctx->staged_want_stats ? ctx->d_stats : nullptr;
-    args.scratch    = ctx->d_scratch2;
-    args.job_stride = job_stride;
-    args.Fpad       = Fpad;
-    args.prm        = prm;
-    args.dbg        = ctx->d_dbg;
+    V3Args args;
+    args.view         = make_view(ctx->arena);
+    args.jobs         = ctx->d_jobs;
+    args.feats        = ctx->d_feats;
+    args.results      = ctx->d_results;
+    args.stats        = ctx->staged_want_stats ? ctx->d_stats : nullptr;
+    args.scratch      = ctx->d_scratch2;
+    args.job_stride   = job_stride;
+    args.chunk_stride = chunk_stride;
+    args.NT           = NT;
+    args.C            = C;
+    args.prm          = prm;
+    args.dbg          = ctx->d_dbg;
     for (int i = 0; i < 4; i++) args.K[i] = ctx->cfg.K[i];
 
-    dim3 pgrid((Fpad + 127) / 128, nLevels, nJobs);
+    dim3 pgrid((C * NT + 127) / 128, nLevels, nJobs);
     k_align_precompute<P><<<pgrid, 128, 0, ctx->stream>>>(args);
-    const size_t smem = v2_smem_bytes<P>(Fpad);
-    SVO_CUDA(cudaFuncSetAttribute(k_align_iterate<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    k_align_iterate<P><<<nJobs, NT, smem, ctx->stream>>>(args);
+    svo_status st;
+    switch (NT) {
+        case 64: st = launch_v3_nt<P, 64>(ctx, args, nJobs); break;
+        case 128: st = launch_v3_nt<P, 128>(ctx, args, nJobs); break;
+        case 256: st = launch_v3_nt<P, 256>(ctx, args, nJobs); break;
+        default: st = launch_v3_nt<P, 512>(ctx, args, nJobs); break;
+    }
+    if (st != SVO_OK) return st;
     ctx->launches += 2;
+    ctx->last_align_nt = NT;
+    ctx->last_align_c  = C;
     SVO_CUDA(cudaGetLastError());
     return SVO_OK;
 }
 
 }  // namespace
 
-// returns true when the fast path handles this batch
-bool sparse_align_v2_supported(const svo_ctx* ctx, int maxF)
+// returns true when the cluster fast path handles this batch: patch 4 / 5, at most 8 CTAs per pair
+bool sparse_align_v3_supported(const svo_ctx* ctx, int maxF)
 {
     const svo_align_params& prm = ctx->staged_params;
     if (prm.patch_size != 4 && prm.patch_size != 5) return false;
-    if (maxF > NT) return false;
-    const int Fpad    = (maxF + 31) & ~31;
-    const size_t smem = prm.patch_size == 5 ? v2_smem_bytes<5>(Fpad) : v2_smem_bytes<4>(Fpad);
-    return smem <= (size_t)ctx->max_smem_optin;
+    int NT, C;
+    v3_shape(ctx, maxF, ctx->staged_jobs, &NT, &C);
+    return C <= 8;
 }
 
-svo_status launch_sparse_align_v2(svo_ctx* ctx, int maxF)
+svo_status launch_sparse_align_v3(svo_ctx* ctx, int maxF)
 {
-    return ctx->staged_params.patch_size == 5 ? launch_v2<5>(ctx, maxF) : launch_v2<4>(ctx, maxF);
+    return ctx->staged_params.patch_size == 5 ? launch_v3<5>(ctx, maxF) : launch_v3<4>(ctx, maxF);
 }

@@ -133,13 +133,19 @@ def _check_levels(stats, lv, synth, faithful):
             assert g["status"] == o["status"] and g["iterations"] == o["iterations"]
 
 
-@pytest.fixture(params=["fast", "generic"])
+@pytest.fixture(params=["fast", "cluster4", "cluster8", "generic"])
 def align_path(request, monkeypatch):
-    """Both CUDA implementations of the alignment: the fast path (patch 4/5, <= 512 features) and the generic kernel."""
+    """The CUDA implementations of the alignment: the fast path in its default shape (one CTA per pair up to 512
+    features), the same kernel forced into thread-block clusters of 4 x 128 / 8 x 64 threads per pair (distributed
+    shared memory exchange), and the generic kernel."""
+    for k in ("SVO_ALIGN_GENERIC", "SVO_ALIGN_NT", "SVO_ALIGN_C"):
+        monkeypatch.delenv(k, raising=False)
     if request.param == "generic":
         monkeypatch.setenv("SVO_ALIGN_GENERIC", "1")
-    else:
-        monkeypatch.delenv("SVO_ALIGN_GENERIC", raising=False)
+    elif request.param == "cluster4":
+        monkeypatch.setenv("SVO_ALIGN_NT", "128")
+    elif request.param == "cluster8":
+        monkeypatch.setenv("SVO_ALIGN_NT", "64")
     return request.param
 
 
@@ -186,6 +192,24 @@ def test_sparse_align_iterated_parity(pkg, orc, synth, pair_cache, align_path, m
     assert np.abs(res[0]["T_cur"][4:] - T[4:]).max() < TRANS_TOL
     assert synth.rotation_angle(res[0]["T_cur"], pair["T_cur_true"]) < 2e-4
     assert np.abs(res[0]["T_cur"][4:] - pair["T_cur_true"][4:]).max() < 5e-3
+
+
+@pytest.mark.parametrize("n_features,mode", [(1000, "LM_FAITHFUL"), (1197, "LM_FAITHFUL"), (1001, "GN")])
+def test_sparse_align_many_features_cluster(pkg, orc, synth, pair_cache, n_features, mode):
+    """BASELINE config 4 shape: ~1,000 features per pair (cell 20) run as a cluster of 512-thread CTAs."""
+    pair = pair_cache(5, n_features, cell=20)
+    assert pair["n_ref"] > 512
+    pyr = _pyrs(orc, pair)
+    m = getattr(orc, mode)
+    rmse, T, status, lv = _oracle_align(orc, pair, pyr, m, max_iter=30)
+    with _ctx(pkg, pair, max_features=1280) as ctx:
+        ctx.upload(0, np.stack([pair["ref"], pair["cur"]]))
+        res, stats = ctx.sparse_align(_job(pkg, pair), pair["feats"], mode=getattr(pkg.capi, mode), max_iter=30)
+    faithful = mode == "LM_FAITHFUL"
+    _check_levels(stats[0] if faithful else stats[0][:1], lv if faithful else lv[:1], synth, faithful)
+    assert synth.rotation_angle(res[0]["T_cur"], T) < ROT_TOL
+    assert np.abs(res[0]["T_cur"][4:] - T[4:]).max() < TRANS_TOL
+    assert res[0]["status"] == status
 
 
 def test_sparse_align_identity_motion(pkg, orc, synth, pair_cache):
