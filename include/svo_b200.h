@@ -89,6 +89,13 @@ svo_status svo_level_dims(const svo_ctx* ctx, int level, int* w, int* h, int* pi
  * ------------------------------------------------------------------------------------------- */
 svo_status svo_frames_upload(svo_ctx* ctx, int first_slot, int n, const uint8_t* imgs, int pitch,
                              int64_t frame_stride);
+/* Same work, enqueued on the context's ingest streams so that it runs CONCURRENTLY with what is already enqueued on
+ * the main stream (the alignment of the previous batch of frames): what a pipelined caller of Frame::Frame
+ * (src/frame.cpp:26) does with the next camera frame while the tracker still works on the current one.  Every later
+ * call that touches frame slots is ordered after it.  The caller guarantees that no job enqueued but not yet fetched
+ * references these slots (double-buffer the slots of the incoming frames). */
+svo_status svo_frames_prefetch(svo_ctx* ctx, int first_slot, int n, const uint8_t* imgs, int pitch,
+                               int64_t frame_stride);
 /* same, level-0 images already on the device (dptr: device pointer) */
 svo_status svo_frames_upload_device(svo_ctx* ctx, int first_slot, int n, const void* dptr, int pitch,
                                     int64_t frame_stride);

@@ -19,7 +19,7 @@ MAX_LEVELS = 8
 # every symbol include/svo_b200.h declares (tests check that the library exports all of them)
 SYMBOLS = [
     "svo_create", "svo_destroy", "svo_last_error", "svo_version", "svo_sync", "svo_launch_count", "svo_stream",
-    "svo_host_alloc", "svo_host_free", "svo_level_dims", "svo_frames_upload", "svo_frames_upload_device",
+    "svo_host_alloc", "svo_host_free", "svo_level_dims", "svo_frames_upload", "svo_frames_prefetch", "svo_frames_upload_device",
     "svo_frames_rebuild", "svo_frame_download", "svo_select_grid", "svo_sparse_align", "svo_sparse_align_stage",
     "svo_sparse_align_h2d", "svo_sparse_align_launch", "svo_sparse_align_d2h", "svo_sparse_align_fetch",
     "svo_sparse_align_results_device", "svo_debug_cycles",
@@ -74,10 +74,11 @@ def load():
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
+    path = os.environ.get("SVO_B200_LIB", LIB_PATH)  # diagnostics: the instrumented twin built by `make prof`
+    if not os.path.exists(path):
         raise ImportError("libsvo_b200.so is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                           "(nvcc, sm_100a).  This package has no CPU or PyTorch fallback.")
-    L = C.CDLL(LIB_PATH)
+    L = C.CDLL(path)
     vp, i, i64 = C.c_void_p, C.c_int, C.c_int64
     L.svo_create.argtypes = [C.POINTER(Config), C.POINTER(vp)]
     L.svo_destroy.argtypes = [vp]
@@ -94,6 +95,7 @@ def load():
     L.svo_host_free.argtypes = [vp, vp]
     L.svo_level_dims.argtypes = [vp, i, C.POINTER(i), C.POINTER(i), C.POINTER(i)]
     L.svo_frames_upload.argtypes = [vp, i, i, vp, i, i64]
+    L.svo_frames_prefetch.argtypes = [vp, i, i, vp, i, i64]
     L.svo_frames_upload_device.argtypes = [vp, i, i, vp, i, i64]
     L.svo_frames_rebuild.argtypes = [vp, i, i]
     L.svo_frame_download.argtypes = [vp, i, i, i, vp, i]
@@ -208,6 +210,19 @@ class Context:
             a = np.ascontiguousarray(a)
         self._check(self.L.svo_frames_upload(self.h, first_slot, a.shape[0], a.ctypes.data, a.strides[1], a.strides[0]))
         return a  # keep alive until the stream has consumed it (pinned path is asynchronous)
+
+    def prefetch(self, first_slot, imgs):
+        """upload() on the ingest streams: overlaps work already enqueued (svo_frames_prefetch); the slots must not be
+        referenced by a batch that is still in flight."""
+        a = np.asarray(imgs)
+        assert a.dtype == np.uint8
+        if a.ndim == 2:
+            a = a[None]
+        assert a.shape[1:] == (self.height, self.width), a.shape
+        if not (a.strides[2] == 1 and a.strides[1] >= self.width):
+            a = np.ascontiguousarray(a)
+        self._check(self.L.svo_frames_prefetch(self.h, first_slot, a.shape[0], a.ctypes.data, a.strides[1], a.strides[0]))
+        return a
 
     def upload_device(self, first_slot, n, dptr, pitch, frame_stride):
         self._check(self.L.svo_frames_upload_device(self.h, first_slot, n, dptr, pitch, frame_stride))

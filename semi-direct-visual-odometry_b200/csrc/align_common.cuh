@@ -50,7 +50,7 @@ __device__ __forceinline__ void expand_H(const double* E, double* H, double* g)
 }
 
 // dx = (H + diag_add I)^-1 g with H, g packed in E (21 + 6): register-resident fast path, pivoted LDLT fallback
-__device__ __forceinline__ void solve6(const double* E, double diag_add, double* dx)
+__device__ __noinline__ void solve6(const double* E, double diag_add, double* dx)
 {
     if (svo::ldlt6_nopivot(E, diag_add, E + 21, dx)) return;
     double H[36], g[6];

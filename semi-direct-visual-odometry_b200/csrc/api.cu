@@ -34,6 +34,18 @@ void release(svo_ctx* ctx)
         if (ctx->ev_consumed[i]) cudaEventDestroy(ctx->ev_consumed[i]);
     }
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
+    if (ctx->ingest_stream) {
+        cudaStreamSynchronize(ctx->ingest_stream);
+        cudaStreamDestroy(ctx->ingest_stream);
+    }
+    if (ctx->ev_ingest_done) cudaEventDestroy(ctx->ev_ingest_done);
+    for (int i = 0; i < 2; i++) {
+        if (ctx->d_pf_stage[i]) cudaFree(ctx->d_pf_stage[i]);
+        if (ctx->ev_pf_consumed[i]) cudaEventDestroy(ctx->ev_pf_consumed[i]);
+    }
+    for (int i = 0; i < 64; i++)
+        if (ctx->ev_pf_chunk[i]) cudaEventDestroy(ctx->ev_pf_chunk[i]);
+    if (ctx->ev_jobs_h2d) cudaEventDestroy(ctx->ev_jobs_h2d);
     cudaFree(ctx->d_cell_best);
     cudaFree(ctx->d_occupancy);
     cudaFree(ctx->d_sel_out);
@@ -96,6 +108,18 @@ svo_status init(svo_ctx* ctx)
         h = (h + 1) / 2;
     }
     SVO_CUDA(cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking));
+    {   // the ingest kernels are short and feed the DMA pipeline: highest priority, so that their CTAs are scheduled as
+        // soon as an SM has room even while a long alignment launch owns the device
+        int lo = 0, hi = 0;
+        SVO_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+        SVO_CUDA(cudaStreamCreateWithPriority(&ctx->ingest_stream, cudaStreamNonBlocking, hi));
+    }
+    SVO_CUDA(cudaEventCreateWithFlags(&ctx->ev_ingest_done, cudaEventDisableTiming));
+    ctx->pyr_stream     = ctx->stream;
+    ctx->ingest_pending = false;
+    for (int i = 0; i < 2; i++) SVO_CUDA(cudaEventCreateWithFlags(&ctx->ev_pf_consumed[i], cudaEventDisableTiming));
+    for (int i = 0; i < 64; i++) SVO_CUDA(cudaEventCreateWithFlags(&ctx->ev_pf_chunk[i], cudaEventDisableTiming));
+    SVO_CUDA(cudaEventCreateWithFlags(&ctx->ev_jobs_h2d, cudaEventDisableTiming));
     ctx->stage_frames = std::min(kStageFrames, c.max_frames);
     const size_t stage_bytes = (size_t)c.width * c.height * ctx->stage_frames + 64;
     for (int i = 0; i < 2; i++) {
@@ -157,6 +181,16 @@ svo_status ensure_scratch(svo_ctx* ctx, int area)
 
 inline bool bad_slot(const svo_ctx* ctx, int s) { return s < 0 || s >= ctx->cfg.max_frames; }
 
+// work on the main stream that touches frame slots runs after the last svo_frames_prefetch
+svo_status wait_ingest(svo_ctx* ctx)
+{
+    if (ctx->ingest_pending) {
+        SVO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_ingest_done, 0));
+        ctx->ingest_pending = false;
+    }
+    return SVO_OK;
+}
+
 }  // namespace
 
 extern "C" {
@@ -198,6 +232,7 @@ const char* svo_last_error(const svo_ctx* ctx) { return ctx ? ctx->err.c_str() :
 svo_status svo_sync(svo_ctx* ctx)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_CUDA(cudaStreamSynchronize(ctx->ingest_stream));
     SVO_CUDA(cudaStreamSynchronize(ctx->stream));
     return SVO_OK;
 }
@@ -233,7 +268,8 @@ svo_status svo_host_free(svo_ctx* ctx, void* p)
 // ------------------------------------------------------------------------------------------------
 // frames
 // ------------------------------------------------------------------------------------------------
-svo_status svo_frames_upload(svo_ctx* ctx, int first_slot, int n, const uint8_t* imgs, int pitch, int64_t frame_stride)
+static svo_status frames_upload_impl(svo_ctx* ctx, int first_slot, int n, const uint8_t* imgs, int pitch, int64_t frame_stride,
+                                     bool overlap)
 {
     if (!ctx) return SVO_ERR_INVALID;
     if (n == 0) return SVO_OK;
@@ -242,11 +278,55 @@ svo_status svo_frames_upload(svo_ctx* ctx, int first_slot, int n, const uint8_t*
         (n > 1 && frame_stride < (int64_t)pitch * g.h))
         SVO_FAIL(SVO_ERR_INVALID, "svo_frames_upload: bad slot range, pitch or stride");
     SVO_CUDA(cudaSetDevice(ctx->cfg.device));
+    // the stream the repack + pyramid kernels run on: the main stream (ordered with everything else), or the ingest
+    // stream (svo_frames_prefetch: concurrent with work already enqueued on the main stream)
+    cudaStream_t ks = overlap ? ctx->ingest_stream : ctx->stream;
+    if (!overlap) {
+        const svo_status ws = wait_ingest(ctx);
+        if (ws != SVO_OK) return ws;
+    }
+    ctx->pyr_stream = ks;
     cudaPointerAttributes attr;
     const bool pinned = cudaPointerGetAttributes(&attr, imgs) == cudaSuccess && attr.type == cudaMemoryTypeHost;
     cudaGetLastError();
     const bool dense       = pitch == g.w && (n == 1 || frame_stride == (int64_t)g.w * g.h);
     const int64_t frame_sz = (int64_t)g.w * g.h;
+    if (overlap && pinned && dense) {
+        // whole-batch staging: the copy engine streams the batch without ever waiting for a kernel; repack + pyramid
+        // kernels follow chunk by chunk on the high-priority ingest stream whenever SMs are free
+        const int b = ctx->pf_next;
+        ctx->pf_next ^= 1;
+        const size_t need = (size_t)n * frame_sz + 64;
+        if (need > ctx->pf_stage_bytes[b]) {
+            SVO_CUDA(cudaEventSynchronize(ctx->ev_pf_consumed[b]));
+            if (ctx->d_pf_stage[b]) SVO_CUDA(cudaFree(ctx->d_pf_stage[b]));
+            ctx->d_pf_stage[b]     = nullptr;
+            ctx->pf_stage_bytes[b] = 0;
+            SVO_CUDA(cudaMalloc(&ctx->d_pf_stage[b], need));
+            ctx->pf_stage_bytes[b] = need;
+        }
+        SVO_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->ev_pf_consumed[b], 0));
+        const int chunk = 64;
+        for (int i0 = 0; i0 < n; i0 += chunk) {
+            const int m      = std::min(chunk, n - i0);
+            uint8_t* dstage = ctx->d_pf_stage[b] + (int64_t)i0 * frame_sz;
+            cudaEvent_t ev  = ctx->ev_pf_chunk[ctx->pf_chunk_next];
+            ctx->pf_chunk_next = (ctx->pf_chunk_next + 1) & 63;
+            SVO_CUDA(cudaMemcpyAsync(dstage, imgs + (int64_t)i0 * frame_stride, (size_t)m * frame_sz, cudaMemcpyHostToDevice,
+                                     ctx->copy_stream));
+            SVO_CUDA(cudaEventRecord(ev, ctx->copy_stream));
+            SVO_CUDA(cudaStreamWaitEvent(ks, ev, 0));
+            svo_status st = launch_repack(ctx, dstage, g.w, frame_sz, first_slot + i0, m);
+            if (st != SVO_OK) return st;
+            st = launch_pyramid_build(ctx, first_slot + i0, m);
+            if (st != SVO_OK) return st;
+        }
+        SVO_CUDA(cudaEventRecord(ctx->ev_pf_consumed[b], ks));
+        ctx->pyr_stream = ctx->stream;
+        SVO_CUDA(cudaEventRecord(ctx->ev_ingest_done, ctx->ingest_stream));
+        ctx->ingest_pending = true;
+        return SVO_OK;
+    }
     // Chunked pipeline: the DMA of chunk i+1 (copy stream) overlaps k_repack + the pyramid kernels of chunk i (main
     // stream).  PCIe moves DENSE bytes in one 1-D transfer per chunk; the pitched arena layout is made on the device.
     for (int i0 = 0; i0 < n; i0 += ctx->stage_frames) {
@@ -275,15 +355,31 @@ svo_status svo_frames_upload(svo_ctx* ctx, int first_slot, int n, const uint8_t*
             SVO_CUDA(cudaMemcpyAsync(ctx->d_img_stage[buf], st, (size_t)m * frame_sz, cudaMemcpyHostToDevice, ctx->copy_stream));
         }
         SVO_CUDA(cudaEventRecord(ctx->ev_h2d[buf], ctx->copy_stream));
-        SVO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_h2d[buf], 0));
+        SVO_CUDA(cudaStreamWaitEvent(ks, ctx->ev_h2d[buf], 0));
         svo_status st = launch_repack(ctx, ctx->d_img_stage[buf], g.w, frame_sz, first_slot + i0, m);
         if (st != SVO_OK) return st;
-        SVO_CUDA(cudaEventRecord(ctx->ev_consumed[buf], ctx->stream));
+        SVO_CUDA(cudaEventRecord(ctx->ev_consumed[buf], ks));
         st = launch_pyramid_build(ctx, first_slot + i0, m);
         if (st != SVO_OK) return st;
     }
+    ctx->pyr_stream = ctx->stream;
+    if (overlap) {
+        SVO_CUDA(cudaEventRecord(ctx->ev_ingest_done, ctx->ingest_stream));
+        ctx->ingest_pending = true;
+    }
     return SVO_OK;
 }
+
+svo_status svo_frames_upload(svo_ctx* ctx, int first_slot, int n, const uint8_t* imgs, int pitch, int64_t frame_stride)
+{
+    return frames_upload_impl(ctx, first_slot, n, imgs, pitch, frame_stride, false);
+}
+
+svo_status svo_frames_prefetch(svo_ctx* ctx, int first_slot, int n, const uint8_t* imgs, int pitch, int64_t frame_stride)
+{
+    return frames_upload_impl(ctx, first_slot, n, imgs, pitch, frame_stride, true);
+}
+
 
 svo_status svo_frames_upload_device(svo_ctx* ctx, int first_slot, int n, const void* dptr, int pitch, int64_t frame_stride)
 {
@@ -294,6 +390,8 @@ svo_status svo_frames_upload_device(svo_ctx* ctx, int first_slot, int n, const v
         SVO_FAIL(SVO_ERR_INVALID, "svo_frames_upload_device: bad slot range or pitch");
     SVO_CUDA(cudaSetDevice(ctx->cfg.device));
     {
+        const svo_status ws = wait_ingest(ctx);
+        if (ws != SVO_OK) return ws;
         const svo_status st = launch_repack(ctx, (const uint8_t*)dptr, pitch, frame_stride, first_slot, n);
         if (st != SVO_OK) return st;
     }
@@ -307,6 +405,10 @@ svo_status svo_frames_rebuild(svo_ctx* ctx, int first_slot, int n)
     if (n < 0 || bad_slot(ctx, first_slot) || bad_slot(ctx, first_slot + n - 1))
         SVO_FAIL(SVO_ERR_INVALID, "svo_frames_rebuild: bad slot range");
     SVO_CUDA(cudaSetDevice(ctx->cfg.device));
+    {
+        const svo_status ws = wait_ingest(ctx);
+        if (ws != SVO_OK) return ws;
+    }
     return launch_pyramid_build(ctx, first_slot, n);
 }
 
@@ -318,6 +420,10 @@ svo_status svo_frame_download(svo_ctx* ctx, int slot, int level, int which, uint
     const LevelGeom& g = ctx->arena.geom[level];
     if (dst_pitch < g.w) SVO_FAIL(SVO_ERR_INVALID, "svo_frame_download: dst_pitch below the level width");
     SVO_CUDA(cudaSetDevice(ctx->cfg.device));
+    {
+        const svo_status ws = wait_ingest(ctx);
+        if (ws != SVO_OK) return ws;
+    }
     const uint8_t* src = (which ? ctx->arena.grad[level] : ctx->arena.img[level]) + (int64_t)slot * g.plane_stride;
     SVO_CUDA(cudaMemcpy2DAsync(dst, dst_pitch, src, g.pitch, g.w, g.h, cudaMemcpyDeviceToHost, ctx->stream));
     SVO_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -337,6 +443,10 @@ svo_status svo_select_grid(svo_ctx* ctx, int slot, int cell, uint32_t thr, const
     const int rows = g.h / cell + 1, cols = g.w / cell + 1;  // src/feature_selection.cpp:19-25
     if (rows * cols > ctx->sel_cap_cells) SVO_FAIL(SVO_ERR_CAPACITY, "svo_select_grid: too many cells");
     SVO_CUDA(cudaSetDevice(ctx->cfg.device));
+    {
+        const svo_status ws = wait_ingest(ctx);
+        if (ws != SVO_OK) return ws;
+    }
     if (occupancy) {
         std::memcpy(ctx->h_occupancy, occupancy, (size_t)rows * cols);
         SVO_CUDA(cudaMemcpyAsync(ctx->d_occupancy, ctx->h_occupancy, (size_t)rows * cols, cudaMemcpyHostToDevice,
@@ -383,6 +493,7 @@ svo_status svo_sparse_align_stage(svo_ctx* ctx, const svo_align_job* jobs, int n
     const svo_status st = ensure_scratch(ctx, prm->patch_size * prm->patch_size);
     if (st != SVO_OK) return st;
     // the pinned buffers may still be read by the previous batch's H2D
+    SVO_CUDA(cudaEventSynchronize(ctx->ev_jobs_h2d));
     SVO_CUDA(cudaStreamSynchronize(ctx->stream));
     // page-locked caller buffers (svo_host_alloc) are DMA'd in place -- they must stay untouched until the fetch;
     // pageable ones are copied to the context's pinned mirrors first
@@ -414,17 +525,24 @@ svo_status svo_sparse_align_h2d(svo_ctx* ctx)
 {
     if (!ctx) return SVO_ERR_INVALID;
     if (ctx->staged_jobs == 0) return SVO_OK;
+    // On the COPY stream, i.e. in call order with the frame DMA: the copy engine drains one stream's queued transfers
+    // before it turns to another, so a small copy on the main stream would sit behind every frame batch that a
+    // pipelined caller has already queued (measured: the alignment then starts a whole batch late).
     SVO_CUDA(cudaMemcpyAsync(ctx->d_jobs, ctx->src_jobs, sizeof(svo_align_job) * ctx->staged_jobs, cudaMemcpyHostToDevice,
-                             ctx->stream));
+                             ctx->copy_stream));
     if (ctx->staged_feats)
         SVO_CUDA(cudaMemcpyAsync(ctx->d_feats, ctx->src_feats, sizeof(svo_align_feature) * ctx->staged_feats,
-                                 cudaMemcpyHostToDevice, ctx->stream));
+                                 cudaMemcpyHostToDevice, ctx->copy_stream));
+    SVO_CUDA(cudaEventRecord(ctx->ev_jobs_h2d, ctx->copy_stream));
+    SVO_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->ev_jobs_h2d, 0));
     return SVO_OK;
 }
 
 svo_status svo_sparse_align_launch(svo_ctx* ctx)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    const svo_status ws = wait_ingest(ctx);
+    if (ws != SVO_OK) return ws;
     return launch_sparse_align(ctx);
 }
 
@@ -507,6 +625,8 @@ svo_status svo_feature_align_h2d(svo_ctx* ctx)
 svo_status svo_feature_align_launch(svo_ctx* ctx)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    const svo_status ws = wait_ingest(ctx);
+    if (ws != SVO_OK) return ws;
     return launch_feature_align(ctx);
 }
 

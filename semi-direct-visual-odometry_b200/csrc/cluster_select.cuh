@@ -120,35 +120,53 @@ __device__ __forceinline__ uint32_t cs_cluster_nctarank()
 template <int NT>
 __host__ __device__ constexpr size_t cs_smem_bytes()
 {
-    return ((size_t)16 * NT + 3 * CS_BINS + 8 + 3 * CS_XS) * 4;
+    return ((size_t)16 * NT + 4 * CS_BINS + 32 + 3 * CS_XS) * 4;
 }
 
+#ifdef SVO_PROFILE
+#define CS_T(i)                          \
+    do {                                 \
+        const long long t__ = clock64(); \
+        sc.prof[i] += t__ - sc.tlast;    \
+        sc.tlast = t__;                  \
+    } while (0)
+#else
+#define CS_T(i)
+#endif
+
 struct Bracket {  // uniform over the cluster
-    uint32_t center;
-    int shift;    // log2 of the bin width of sweep A; bracket = center -/+ (256 << shift)
-    bool valid;
+    uint32_t center;  // last result
+    int shift;        // log2 of the bin width of sweep A; bracket = center -/+ (256 << shift)
+    bool valid;       // try the bracket first
+    bool have;        // center holds a result of this level
 };
 
 template <int NT>
 struct SelCtx {  // uniform over the cluster
-    uint32_t* priv;  // [16][NT] thread-private packed 8-bit counters (64 bins); zero between uses
+    uint32_t* priv;  // [16][NT] per thread 16 words: packed 8-bit counters of a private pass, or the key stack
     uint32_t* bins;  // [3][512] round histograms
-    uint32_t* loc;   // [8]      result of the last cs_locate, broadcast from warp 0
+    uint32_t* tot;   // [512]    cluster-wide histogram of the round (C > 1)
+    uint32_t* wtot;  // [32]     per-warp totals / last non-empty bins of cs_locate
     uint32_t* xs;    // [3][CS_XS] round scalars
     int C;           // CTAs per cluster
     int cur;         // round buffer in use
     uint32_t tBelow, tAux, tMax;  // cluster totals of the last finished round
     uint32_t auxTotal;            // aux total of the round that fixed a rank (kFromAux)
+#ifdef SVO_PROFILE
+    long long prof[12], tlast;    // cycles: 0 push 1 pop A 2 finish A 3 locate A 4 pop B 5 finish B 6 locate B 7 private count
+                                  //         8 private reduce 9 private finish + scan 10 other
+#endif
 
     __device__ __forceinline__ void init(unsigned char* base, int clusterSize)
     {
         priv = reinterpret_cast<uint32_t*>(base);
         bins = priv + 16 * NT;
-        loc  = bins + 3 * CS_BINS;
-        xs   = loc + 8;
+        tot  = bins + 3 * CS_BINS;
+        wtot = tot + CS_BINS;
+        xs   = wtot + 32;
         C    = clusterSize;
         cur  = 0;
-        for (int i = threadIdx.x; i < 16 * NT + 3 * CS_BINS + 8 + 3 * CS_XS; i += NT) priv[i] = 0;
+        for (int i = threadIdx.x; i < 16 * NT + 4 * CS_BINS + 32 + 3 * CS_XS; i += NT) priv[i] = 0;
     }
     __device__ __forceinline__ uint32_t* rbins() const { return bins + cur * CS_BINS; }
     __device__ __forceinline__ uint32_t* rxs() const { return xs + cur * CS_XS; }
@@ -241,150 +259,173 @@ __device__ __forceinline__ uint4 cs_gather_sum4_cc(uint32_t la)
     return s;
 }
 
-// The 512-bin histogram of the round (summed over the C CTAs through distributed shared memory) is scanned by WARP 0
-// of every CTA -- 16 redundant scans cost more issue slots than one scan plus a barrier: the bin holding rank kin, the
-// rank inside it and the last non-empty bin before it, broadcast through sc.loc.  Lane l owns the four bin quads
-// 4 (32 j + l) .. + 3, j = 0..3 (conflict-free 16-byte loads).  prefixBefore >= 0: kin is relative to the entries in
-// bins [0, prefixBefore).
+// Locate rank kin in the 512-bin histogram of the round (summed over the C CTAs through distributed shared memory):
+// the bin holding it, the rank inside the bin and the last non-empty bin before it.  Two levels, one barrier:
+// thread t totals bins [t BPT, (t+1) BPT) (BPT = 512 / NT) and publishes the cluster sums, every warp publishes its
+// total and its last non-empty bin; after the barrier EVERY warp scans the NT/32 warp totals and the 32 thread totals of
+// the target warp redundantly -- short dependent chains, no second barrier, identical results in all CTAs.
+// prefixBefore >= 0: kin is relative to the entries in bins [0, prefixBefore).
 template <int NT>
 __device__ __forceinline__ Located cs_locate(const uint32_t* hist, uint32_t kin, int prefixBefore, SelCtx<NT>& sc)
 {
-    const int lane = threadIdx.x & 31;
-    if (threadIdx.x < 32) {
-        uint32_t c[4][4];
-        if (sc.C == 1) {
-            const uint4* h4 = reinterpret_cast<const uint4*>(hist);
+    constexpr int NW  = NT / 32;
+    constexpr int BPT = CS_BINS / NT;
+    static_assert(BPT == 1 || BPT == 2 || BPT == 4 || BPT == 8, "NT must be 64 .. 512");
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // ---- level 1: this thread's bins ----
+    uint32_t c[BPT];
+    if (sc.C == 1) {
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint4 q = h4[j * 32 + lane];
-                c[j][0] = q.x, c[j][1] = q.y, c[j][2] = q.z, c[j][3] = q.w;
-            }
+        for (int j = 0; j < BPT; j++) c[j] = hist[tid * BPT + j];
+    } else {
+        const uint32_t la = cs_smem_u32(hist + tid * BPT);
+        if (BPT == 1) {
+            c[0] = cs_gather_sum(la, sc.C);
         } else {
-            const uint32_t la = cs_smem_u32(hist) + 16u * lane;
 #pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const uint32_t aj = la + 512u * j;
-                const uint4 q = sc.C == 2 ? cs_gather_sum4_cc<2>(aj) : (sc.C == 4 ? cs_gather_sum4_cc<4>(aj) : cs_gather_sum4_cc<8>(aj));
-                c[j][0] = q.x, c[j][1] = q.y, c[j][2] = q.z, c[j][3] = q.w;
+            for (int j = 0; j < BPT; j += 2) {
+                const uint2 q = cs_gather_sum2(la + 4u * j, sc.C);
+                c[j]          = q.x;
+                c[j + 1]      = q.y;
             }
         }
-        uint32_t g[4];
 #pragma unroll
-        for (int j = 0; j < 4; j++) g[j] = c[j][0] + c[j][1] + c[j][2] + c[j][3];
-        // two packed inclusive scans over the lanes (every total is <= 2^16 - 1: at most 2^16 - 1 keys per cluster)
-        uint32_t w0 = g[0] | (g[1] << 16), w1 = g[2] | (g[3] << 16);
+        for (int j = 0; j < BPT; j++) sc.tot[tid * BPT + j] = c[j];
+    }
+    const uint32_t* T = sc.C == 1 ? hist : sc.tot;  // the cluster-wide histogram, local after the barrier
+    uint32_t ssum = 0, lastp1 = 0;                  // lastp1: 1 + last non-empty bin of the thread, 0 if none
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t t0 = __shfl_up_sync(CS_FULL, w0, o), t1 = __shfl_up_sync(CS_FULL, w1, o);
-            if (lane >= o) {
-                w0 += t0;
-                w1 += t1;
-            }
-        }
-        const uint32_t incl[4] = {w0 & 0xffffu, w0 >> 16, w1 & 0xffffu, w1 >> 16};
-        const uint32_t e0 = __shfl_sync(CS_FULL, w0, 31), e1 = __shfl_sync(CS_FULL, w1, 31);
-        const uint32_t T[4] = {e0 & 0xffffu, e0 >> 16, e1 & 0xffffu, e1 >> 16};
-        const uint32_t base[5] = {0u, T[0], T[0] + T[1], T[0] + T[1] + T[2], T[0] + T[1] + T[2] + T[3]};
-        if (prefixBefore >= 0) {
-            const int jo = prefixBefore >> 7, lo = (prefixBefore >> 2) & 31, eo = prefixBefore & 3;
-            uint32_t mine = 0, bj = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (j == jo) {
-                    mine = incl[j] - g[j] + (eo > 0 ? c[j][0] : 0u) + (eo > 1 ? c[j][1] : 0u) + (eo > 2 ? c[j][2] : 0u);
-                    bj   = base[j];
-                }
-            kin += bj + __shfl_sync(CS_FULL, mine, lo);
-        }
-        const uint32_t total = base[4];
-        uint32_t bin = 0, rank = 0, pred = CS_NONE;
-        const bool found = kin < total;
-        if (found) {
-            const int js = (kin >= base[1]) + (kin >= base[2]) + (kin >= base[3]);  // quad row holding the rank
-            uint32_t inclS = 0, gS = 0, cS[4] = {0u, 0u, 0u, 0u}, baseS = 0;
-#pragma unroll
-            for (int j = 0; j < 4; j++)
-                if (j == js) {
-                    inclS = incl[j], gS = g[j], baseS = base[j];
-                    cS[0] = c[j][0], cS[1] = c[j][1], cS[2] = c[j][2], cS[3] = c[j][3];
-                }
-            const uint32_t kr = kin - baseS;                                   // rank inside row js
-            const int tl      = __popc(__ballot_sync(CS_FULL, inclS <= kr));  // first lane whose inclusive total exceeds it
-            // inside the quad: every lane evaluates its own four bins; lane tl's answer counts
-            const uint32_t kk = kr - (inclS - gS);
-            uint32_t run = 0, be = 0, brk = 0, lastnz = CS_NONE, predIn = CS_NONE;
-#pragma unroll
-            for (int e = 0; e < 4; e++) {
-                if (kk >= run && kk < run + cS[e]) {
-                    be     = e;
-                    brk    = kk - run;
-                    predIn = lastnz;
-                }
-                run += cS[e];
-                if (cS[e]) lastnz = e;
-            }
-            bin  = (uint32_t)(128 * js + 4 * tl) + __shfl_sync(CS_FULL, be, tl);
-            rank = __shfl_sync(CS_FULL, brk, tl);
-            const uint32_t pin = __shfl_sync(CS_FULL, predIn, tl);
-            if (pin != CS_NONE) {
-                pred = (uint32_t)(128 * js + 4 * tl) + pin;
-            } else {
-                const uint32_t lower = __ballot_sync(CS_FULL, gS != 0) & ((1u << tl) - 1u);
-                if (lower) {  // an earlier quad of the same row
-                    const int pl = 31 - __clz(lower);
-                    pred         = (uint32_t)(128 * js + 4 * pl) + __shfl_sync(CS_FULL, lastnz, pl);
-                } else {      // the last non-empty quad of an earlier row
-#pragma unroll
-                    for (int j = 3; j >= 0; j--) {
-                        if (j < js && pred == CS_NONE && T[j] != 0) {
-                            const uint32_t nz = __ballot_sync(CS_FULL, g[j] != 0);
-                            const int pl      = 31 - __clz(nz);
-                            const uint32_t ln = c[j][3] ? 3u : (c[j][2] ? 2u : (c[j][1] ? 1u : 0u));
-                            pred              = (uint32_t)(128 * j + 4 * pl) + __shfl_sync(CS_FULL, ln, pl);
-                        }
-                    }
-                }
-            }
-        }
-        if (lane == 0) {
-            sc.loc[0] = total;
-            sc.loc[1] = bin;
-            sc.loc[2] = rank;
-            sc.loc[3] = pred;
-            sc.loc[4] = found ? 1u : 0u;
-        }
+    for (int j = 0; j < BPT; j++) {
+        ssum += c[j];
+        if (c[j]) lastp1 = (uint32_t)(tid * BPT + j + 1);
+    }
+    const uint32_t wsum  = __reduce_add_sync(CS_FULL, ssum);
+    const uint32_t wlast = __reduce_max_sync(CS_FULL, lastp1);
+    if (lane == 0) {
+        sc.wtot[warp]      = wsum;
+        sc.wtot[16 + warp] = wlast;
     }
     __syncthreads();
+    // ---- level 2: the warp totals ----
+    const uint32_t wi    = lane < NW ? sc.wtot[lane] : 0u;
+    const uint32_t wl    = lane < NW ? sc.wtot[16 + lane] : 0u;
+    const uint32_t wincl = cs_warp_incl_scan(wi, lane);
     Located L;
-    L.total = sc.loc[0];
-    L.bin   = sc.loc[1];
-    L.rank  = sc.loc[2];
-    L.pred  = sc.loc[3];
-    L.found = sc.loc[4] != 0;
+    L.total = __shfl_sync(CS_FULL, wincl, 31);
+    L.bin = 0, L.rank = 0, L.pred = CS_NONE;
+    if (prefixBefore >= 0) {
+        // entries in bins [0, prefixBefore): whole warps, whole threads of the partial warp, bins of the partial thread
+        const int pt = prefixBefore / BPT, pe = prefixBefore % BPT;
+        const int pw = pt >> 5, pl = pt & 31;
+        const uint32_t wholeBelow = pw > 0 ? __shfl_sync(CS_FULL, wincl, (pw - 1) & 31) : 0u;
+        uint32_t part = 0;
+        if (pw < NW) {
+            uint32_t ts = 0, tp = 0;  // thread (pw, lane): its total, and its first pe bins
+#pragma unroll
+            for (int j = 0; j < BPT; j++) {
+                const uint32_t v = T[(pw * 32 + lane) * BPT + j];
+                ts += v;
+                tp += j < pe ? v : 0u;
+            }
+            part = __reduce_add_sync(CS_FULL, lane < pl ? ts : (lane == pl ? tp : 0u));
+        }
+        kin += wholeBelow + part;
+    }
+    L.found = kin < L.total;
+    if (!L.found) return L;
+    // target warp: first warp whose inclusive total exceeds kin
+    const int tw         = __popc(__ballot_sync(CS_FULL, lane < NW && wincl <= kin));
+    const uint32_t wbase = tw > 0 ? __shfl_sync(CS_FULL, wincl, tw - 1) : 0u;
+    uint32_t tc[BPT], ts = 0, tlastp1 = 0;  // thread (tw, lane)
+#pragma unroll
+    for (int j = 0; j < BPT; j++) {
+        tc[j] = T[(tw * 32 + lane) * BPT + j];
+        ts += tc[j];
+        if (tc[j]) tlastp1 = (uint32_t)((tw * 32 + lane) * BPT + j + 1);
+    }
+    const uint32_t tincl = cs_warp_incl_scan(ts, lane) + wbase;
+    const int tl         = __popc(__ballot_sync(CS_FULL, tincl <= kin));  // target thread of the warp
+    // inside the target thread: every lane evaluates its own bins, lane tl's answer counts
+    const uint32_t kk = kin - (tincl - ts);
+    uint32_t run = 0, be = 0, brk = 0, predIn = 0, seen = 0;
+#pragma unroll
+    for (int j = 0; j < BPT; j++) {
+        if (kk >= run && kk < run + tc[j]) {
+            be     = j;
+            brk    = kk - run;
+            predIn = seen;
+        }
+        run += tc[j];
+        if (tc[j]) seen = (uint32_t)((tw * 32 + lane) * BPT + j + 1);
+    }
+    L.bin  = (uint32_t)((tw * 32 + tl) * BPT) + __shfl_sync(CS_FULL, be, tl);
+    L.rank = __shfl_sync(CS_FULL, brk, tl);
+    // last non-empty bin before the target: inside the thread, else lower threads of the warp, else lower warps
+    uint32_t p1 = __shfl_sync(CS_FULL, predIn, tl);
+    if (p1 == 0) p1 = __reduce_max_sync(CS_FULL, lane < tl ? tlastp1 : 0u);
+    if (p1 == 0) p1 = __reduce_max_sync(CS_FULL, lane < tw ? wl : 0u);
+    L.pred = p1 ? p1 - 1u : CS_NONE;
     return L;
 }
 
+__device__ __forceinline__ void cs_sts_u16(uint32_t addr, uint32_t v)
+{
+    asm volatile("st.shared.u16 [%0], %1;" ::"r"(addr), "h"((unsigned short)v) : "memory");
+}
+__device__ __forceinline__ uint32_t cs_lds_u16(uint32_t addr)
+{
+    unsigned short v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory");
+    return (uint32_t)v;
+}
+
+// The keys of a thread that fall inside the bracket [lo, lo + 65536) at most, as 16-bit offsets from lo, in a
+// thread-private stack of 32 slots in shared memory (the 16 words per thread of sc.priv, [slot][NT] halfwords).
+// Registers cannot be indexed dynamically; the stack can, so the atomics of both sweeps loop over the FEW keys inside
+// the bracket instead of branching around a predicated atomic for each of the AREA keys.
+struct KeyStack {
+    uint32_t base;  // shared-memory byte address of slot 0 of this thread
+    uint32_t n;     // keys on the stack
+    uint32_t lo;    // bracket start the offsets refer to
+};
+
 // Sweep A: 512 bins of width 2^shift from lo; also counts the keys below lo.  Returns 0 on a hit, -1 / +1 when the
 // k-th key lies below / above the bracket.  kFromAux: k = (cluster total of aux) * AREA / 2, known after the barrier.
+// Push pass: branch-free, one unconditional 16-bit store per key whose slot is kept only when the key is inside.
 template <int AREA, int NT>
 __device__ __forceinline__ int cs_sweep_a(const uint32_t (&key)[AREA], bool live, uint32_t lo, int shift, int& k, bool kFromAux,
-                                          SelCtx<NT>& sc, Located* out)
+                                          SelCtx<NT>& sc, Located* out, KeyStack& ks)
 {
+    static_assert(AREA <= 32, "the key stack holds 32 halfwords per thread");
     const int lane = threadIdx.x & 31;
     uint32_t below       = 0;
-    const uint32_t width = 512u << shift;
-    const uint32_t cur32 = cs_smem_u32(sc.rbins());
+    const uint32_t width = 512u << shift;  // <= 65536: offsets fit 16 bits
+    CS_T(10);
+    ks.base = cs_smem_u32(sc.priv) + 2u * threadIdx.x;
+    ks.lo   = lo;
+    uint32_t ptr = ks.base;
     if (live) {
 #pragma unroll
         for (int i = 0; i < AREA; i++) {
             const uint32_t t = key[i] - lo;  // keys below lo wrap to >= 2^31 (keys are < 2^27)
             below += t >> 31;
-            cs_red_inc_if_below(cur32 + ((t >> shift) << 2), t, width);
+            cs_sts_u16(ptr, t);
+            ptr += t < width ? 2u * NT : 0u;
         }
+    }
+    ks.n = (ptr - ks.base) / (2u * NT);
+    CS_T(0);
+    {   // histogram the keys on the stack
+        uint32_t* cur        = sc.rbins();
+        const uint32_t nmax = __reduce_max_sync(CS_FULL, ks.n);
+        for (uint32_t j = 0; j < nmax; j++)
+            if (j < ks.n) atomicAdd(&cur[cs_lds_u16(ks.base + j * 2u * NT) >> shift], 1u);
     }
     below = __reduce_add_sync(CS_FULL, below);
     if (lane == 0 && below) atomicAdd(&sc.rxs()[0], below);
+    CS_T(1);
     const uint32_t* hist = sc.finish_round();
+    CS_T(2);
     if (kFromAux) {
         sc.auxTotal = sc.tAux;
         k           = (int)(sc.tAux * (uint32_t)AREA / 2u);
@@ -392,28 +433,36 @@ __device__ __forceinline__ int cs_sweep_a(const uint32_t (&key)[AREA], bool live
     const int kin = k - (int)sc.tBelow;
     if (kin < 0) return -1;
     *out = cs_locate<NT>(hist, (uint32_t)kin, -1, sc);
+    CS_T(3);
     return out->found ? 0 : 1;
 }
 
 // Sweep B: the chosen bin [lo2, lo2 + W), W <= 128, resolved to single keys.  The 512 unit bins start up to 287
-// keys BELOW lo2, so that the predecessor of the target is normally inside the window too.  rankA = rank of the
-// target among the keys >= lo2.
-template <int AREA, int NT>
-__device__ __forceinline__ void cs_sweep_b(const uint32_t (&key)[AREA], bool live, uint32_t lo2, uint32_t rankA, SelCtx<NT>& sc,
-                                           uint32_t* keyOut, uint32_t* predOut, bool* hasPred)
+// keys BELOW lo2, so that the predecessor of the target is normally inside the window too (keys below the bracket are
+// not on the stack: a predecessor there is found by cs_max_below).  rankA = rank of the target among the keys >= lo2.
+template <int NT>
+__device__ __forceinline__ void cs_sweep_b(const KeyStack& ks, uint32_t lo2, uint32_t rankA, SelCtx<NT>& sc, uint32_t* keyOut,
+                                           uint32_t* predOut, bool* hasPred)
 {
-    const uint32_t ws    = lo2 >= 256u ? ((lo2 - 256u) & ~31u) : 0u;  // window start
-    const uint32_t off   = lo2 - ws;                                   // 0 .. 287
-    const uint32_t cur32 = cs_smem_u32(sc.rbins());
-    if (live) {
-#pragma unroll
-        for (int i = 0; i < AREA; i++) {
-            const uint32_t t = key[i] - ws;
-            cs_red_inc_if_below(cur32 + (t << 2), t, 512u);
+    const uint32_t ws  = lo2 >= 256u ? ((lo2 - 256u) & ~31u) : 0u;  // window start
+    const uint32_t off = lo2 - ws;                                   // 0 .. 287
+    const uint32_t rel = ks.lo - ws;                                 // stack offset -> window offset (wraps when ws > lo)
+    CS_T(10);
+    {
+        uint32_t* cur        = sc.rbins();
+        const uint32_t nmax = __reduce_max_sync(CS_FULL, ks.n);
+        for (uint32_t j = 0; j < nmax; j++) {
+            if (j < ks.n) {
+                const uint32_t u = cs_lds_u16(ks.base + j * 2u * NT) + rel;
+                if (u < 512u) atomicAdd(&cur[u], 1u);
+            }
         }
     }
+    CS_T(4);
     const uint32_t* hist = sc.finish_round();
+    CS_T(5);
     const Located L      = cs_locate<NT>(hist, rankA, (int)off, sc);
+    CS_T(6);
     *keyOut  = ws + L.bin;
     *hasPred = L.rank > 0 || L.pred != CS_NONE;
     *predOut = L.rank > 0 ? ws + L.bin : ws + L.pred;
@@ -442,7 +491,8 @@ __device__ __forceinline__ int cs_bracket_select(const uint32_t (&key)[AREA], bo
                                                  bool needPred, SelCtx<NT>& sc, uint32_t* keyOut, uint32_t* predOut)
 {
     Located A;
-    const int rc = cs_sweep_a<AREA, NT>(key, live, lo, shift, k, kFromAux, sc, &A);
+    KeyStack ks;
+    const int rc = cs_sweep_a<AREA, NT>(key, live, lo, shift, k, kFromAux, sc, &A, ks);
     if (rc != 0) return rc;
     bool hasPred;
     if (shift == 0) {
@@ -450,7 +500,7 @@ __device__ __forceinline__ int cs_bracket_select(const uint32_t (&key)[AREA], bo
         hasPred  = A.rank > 0 || A.pred != CS_NONE;
         *predOut = A.rank > 0 ? lo + A.bin : lo + A.pred;
     } else {
-        cs_sweep_b<AREA, NT>(key, live, lo + (A.bin << shift), A.rank, sc, keyOut, predOut, &hasPred);
+        cs_sweep_b<NT>(ks, lo + (A.bin << shift), A.rank, sc, keyOut, predOut, &hasPred);
     }
     if (needPred && k > 0 && !hasPred) *predOut = cs_max_below<AREA, NT>(key, live, *keyOut, sc);  // rare: predecessor far below
     return 0;
@@ -464,6 +514,9 @@ __device__ __forceinline__ uint32_t cs_private_coarse(const uint32_t (&key)[AREA
 {
     constexpr int NW = NT / 32;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    CS_T(10);
+#pragma unroll
+    for (int j = 0; j < 16; j++) sc.priv[j * NT + tid] = 0;  // this thread's column: the key stacks live here too
     if (live) {
 #pragma unroll
         for (int i = 0; i < AREA; i++) {
@@ -471,14 +524,14 @@ __device__ __forceinline__ uint32_t cs_private_coarse(const uint32_t (&key)[AREA
             sc.priv[(d >> 2) * NT + tid] += 1u << ((d & 3u) * 8u);
         }
     }
+    CS_T(7);
     __syncthreads();
     uint32_t* x = sc.rxs();
     for (int row = warp; row < 16; row += NW) {  // word row `row` = bins 4 row .. 4 row + 3, reduced over all NT columns
         uint32_t lo = 0, hi = 0;
 #pragma unroll
         for (int j = 0; j < NT / 32; j++) {
-            const uint32_t wv                 = sc.priv[row * NT + lane + 32 * j];
-            sc.priv[row * NT + lane + 32 * j] = 0;
+            const uint32_t wv = sc.priv[row * NT + lane + 32 * j];
             lo += wv & 0x00ff00ffu;
             hi += (wv >> 8) & 0x00ff00ffu;
         }
@@ -491,6 +544,7 @@ __device__ __forceinline__ uint32_t cs_private_coarse(const uint32_t (&key)[AREA
             x[8 + row * 4 + 3] = hi >> 16;
         }
     }
+    CS_T(8);
     sc.finish_round();
     if (kFromAux) {
         sc.auxTotal = sc.tAux;
@@ -516,6 +570,7 @@ __device__ __forceinline__ uint32_t cs_private_coarse(const uint32_t (&key)[AREA
         mine = 2 * lane + 1;
     const uint32_t bin = __reduce_min_sync(CS_FULL, mine);
     *below             = __shfl_sync(CS_FULL, (bin & 1u) ? excl + c0 : excl, (int)((bin >> 1) & 31u));
+    CS_T(9);
     return bin;
 }
 
@@ -587,16 +642,19 @@ __device__ __forceinline__ bool cs_tiered_select(const uint32_t (&key)[AREA], bo
         have = false;  // hot miss: go cold
     }
     // next bracket: centred on this result, half-width >= 4x the last movement, at most +/- 2^15 keys (1/2 intensity
-    // unit; wider brackets pay ~2 cycles per key inside them)
-    const uint32_t moved = br.valid ? (kOut > br.center ? kOut - br.center : br.center - kOut) : 0u;
-    int sh               = 4;
-    if (br.valid) {
-        const uint32_t want = 4u * min(moved, 1u << 20) + 64u;
-        sh                  = 0;
+    // unit; wider brackets pay ~2 cycles per key inside them).  The evaluation after the first one of a level follows
+    // the largest step of the level: no bracket then, the movement it shows sizes the next one.
+    if (br.have) {
+        const uint32_t moved = kOut > br.center ? kOut - br.center : br.center - kOut;
+        const uint32_t want  = 4u * min(moved, 1u << 20) + 64u;
+        int sh               = 0;
         while ((256u << sh) < want && sh < 8) sh++;
+        br.valid = sh <= 7;
+        br.shift = min(sh, 7);
+    } else {
+        br.valid = false;
     }
-    br.valid  = sh <= 7;
-    br.shift  = min(sh, 7);
+    br.have   = true;
     br.center = kOut;
     *keyOut   = kOut;
     *predOut  = needPred() ? pred : kOut;

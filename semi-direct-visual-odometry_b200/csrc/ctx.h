@@ -43,6 +43,18 @@ struct svo_ctx {
     // stream -> k_repack + pyramid kernels on the main stream; two buffers so the DMA of chunk i+1 overlaps the
     // kernels of chunk i
     cudaStream_t copy_stream;
+    cudaStream_t ingest_stream;  // svo_frames_prefetch: repack + pyramid kernels, concurrent with the main stream
+    cudaStream_t pyr_stream;     // where launch_repack / launch_pyramid_build enqueue (main or ingest stream)
+    cudaEvent_t ev_ingest_done;  // ingest stream: the last prefetch is complete
+    bool ingest_pending;         // the main stream has not waited for ev_ingest_done yet
+    // svo_frames_prefetch from page-locked memory: two whole-batch dense staging buffers, so that the DMA of batch
+    // k+1 never waits for a kernel (it needs no SM while the alignment of batch k owns them)
+    uint8_t* d_pf_stage[2];
+    size_t pf_stage_bytes[2];
+    cudaEvent_t ev_pf_consumed[2];  // ingest stream: the repack kernels have read d_pf_stage[b]
+    cudaEvent_t ev_pf_chunk[64];    // copy stream: a chunk landed
+    int pf_next, pf_chunk_next;
+    cudaEvent_t ev_jobs_h2d;        // copy stream: the jobs / features of the staged alignment batch are on the device
     uint8_t* h_img_stage[2];     // pinned, dense frames
     uint8_t* d_img_stage[2];     // device, dense frames (+ slack)
     int stage_frames;            // frames per buffer

@@ -45,7 +45,7 @@ __device__ __forceinline__ void quat_to_R(const double q[4], double R[9])
 }
 
 // pose <- pose * exp(-dx);  dx = (upsilon, omega)   [ImageAlignment::update, src/image_alignment.cpp:372-380]
-__device__ inline void pose_update_right_exp_neg(Pose& p, const double dx[6])
+static __device__ __noinline__ void pose_update_right_exp_neg(Pose& p, const double dx[6])
 {
     double ups[3] = {-dx[0], -dx[1], -dx[2]};
     double om[3]  = {-dx[3], -dx[4], -dx[5]};
@@ -116,7 +116,7 @@ __device__ __forceinline__ void pose_camera_in_world(const Pose& T, double C[3])
 // LDLT with symmetric pivoting on the largest |diagonal| and the D^-1 rule of Eigen's solve
 // (pivots not above the smallest normal double give 0).  A: n x n row-major (n <= 6), destroyed.
 template <int N>
-__device__ inline void ldlt_solve(double* A, const double* b, double* x)
+__device__ __noinline__ void ldlt_solve(double* A, const double* b, double* x)
 {
     int perm[N];
 #pragma unroll

@@ -85,17 +85,194 @@ __device__ __forceinline__ int reflect101(int i, int n)
     return i;
 }
 
-// cv::pyrDown, one level, for both stacks of n frames.  A block produces a TX x TY output tile:
-// the (2TX+3) x (2TY+3) source tile is staged in shared memory (reflect-101 applied while loading),
-// the horizontal [1 4 6 4 1] pass runs into a second shared buffer (16-bit), the vertical pass
-// writes (sum + 128) >> 8.  grid: (ceil(dw/TX), ceil(dh/TY), 2 * n_frames)
+// ------------------------------------------------------------------------------------------------------------
+// cv::pyrDown of both stacks, one level per launch, word-vectorised.  A CTA (256 threads) produces a 64 x 16 output
+// tile of the image AND of the gradient stack.  BASE (level 0 -> 1) reads ONLY the level-0 image: the gradient
+// (Simd::AbsGradientSaturatedSum) of the tile is computed in shared memory with SIMD-in-word byte arithmetic, its
+// exclusive 128 x 32 area is written out as gradient level 0 with 16-byte stores, and both tiles are decimated -- so a
+// frame's level-0 image is read from HBM once and the level-0 gradient never re-read.
+//   stage 1  aligned 32-bit loads of the source tile(s) (rows/columns outside the image are skipped)
+//   stage 2  BASE: gradient words from three image rows (funnel shifts + __vabsdiffu4 + __vaddus4), border pixels 0
+//   stage 3  BORDER_REFLECT_101: the <= 2 rows / columns a 5-tap kernel reaches outside the image are mirrored inside
+//            shared memory (border CTAs only)
+//   stage 4  horizontal [1 4 6 4 1] into 16-bit sums, two outputs per thread from three words
+//   stage 5  vertical [1 4 6 4 1], (sum + 128) >> 8, four outputs per thread, one 32-bit store
+// Tile columns are words; word 4 of a tile row holds source columns 2 ox .. 2 ox + 3 (so the exclusive area starts
+// 16-byte aligned in shared memory), word 3 the four columns before, word 36 the four after.
+// ------------------------------------------------------------------------------------------------------------
+constexpr int PT_X = 64, PT_Y = 16;      // output tile
+constexpr int PT_ROWS = 2 * PT_Y + 3;    // 35 source rows feed the vertical taps
+constexpr int PT_PW = 40;                // tile row pitch in words (multiple of 4: 16-byte aligned rows)
+constexpr int PT_W0 = 3, PT_W1 = 37;     // loaded word columns [PT_W0, PT_W1)
+
+template <bool BASE>
+__global__ void __launch_bounds__(256) k_pyr_level(const uint8_t* __restrict__ src_img, const uint8_t* __restrict__ src_grad,
+                                                   uint8_t* __restrict__ dst_img, uint8_t* __restrict__ dst_grad,
+                                                   uint8_t* __restrict__ grad0,  // BASE: gradient level 0 (written)
+                                                   int sw, int sh, int spitch, long long sstride, int dw, int dh, int dpitch,
+                                                   long long dstride)
+{
+    constexpr int IROWS = BASE ? PT_ROWS + 2 : PT_ROWS;  // BASE: one more image row above and below for the gradient
+    __shared__ __align__(16) uint32_t tI[IROWS][PT_PW];
+    __shared__ __align__(16) uint32_t tG[PT_ROWS][PT_PW];
+    __shared__ __align__(16) uint16_t hI[PT_ROWS][PT_X];
+    __shared__ __align__(16) uint16_t hG[PT_ROWS][PT_X];
+    const int tid   = threadIdx.x;
+    const int frame = blockIdx.z;
+    const int ox = blockIdx.x * PT_X, oy = blockIdx.y * PT_Y;
+    const int x00 = 2 * ox - 16;                  // source column of tile word 0, byte 0
+    const int y00 = 2 * oy - 2;                   // source row of tG / hI row 0
+    const int iy0 = BASE ? y00 - 1 : y00;         // source row of tI row 0
+    const uint8_t* sI = src_img + (long long)frame * sstride;
+    const uint8_t* sG = BASE ? nullptr : src_grad + (long long)frame * sstride;
+    const int spw = spitch >> 2;
+
+    // ---- stage 1: loads ----
+    for (int i = tid; i < IROWS * (PT_W1 - PT_W0); i += 256) {
+        const int r = i / (PT_W1 - PT_W0), wc = PT_W0 + i - r * (PT_W1 - PT_W0);
+        const int y = iy0 + r, xw = (x00 >> 2) + wc;  // source word column
+        uint32_t v  = 0;
+        if (y >= 0 && y < sh && xw >= 0 && xw < spw) v = __ldg(reinterpret_cast<const uint32_t*>(sI + (long long)y * spitch) + xw);
+        tI[r][wc] = v;
+    }
+    if (!BASE) {
+        for (int i = tid; i < PT_ROWS * (PT_W1 - PT_W0); i += 256) {
+            const int r = i / (PT_W1 - PT_W0), wc = PT_W0 + i - r * (PT_W1 - PT_W0);
+            const int y = y00 + r, xw = (x00 >> 2) + wc;
+            uint32_t v  = 0;
+            if (y >= 0 && y < sh && xw >= 0 && xw < spw) v = __ldg(reinterpret_cast<const uint32_t*>(sG + (long long)y * spitch) + xw);
+            tG[r][wc] = v;
+        }
+    }
+    __syncthreads();
+
+    // ---- stage 2 (BASE): gradient of the tile ----
+    if (BASE) {
+        for (int i = tid; i < PT_ROWS * (PT_W1 - PT_W0); i += 256) {
+            const int r = i / (PT_W1 - PT_W0), wc = PT_W0 + i - r * (PT_W1 - PT_W0);
+            const int y = y00 + r, x0 = x00 + 4 * wc;
+            uint32_t out = 0;
+            if (y > 0 && y < sh - 1 && x0 + 3 >= 0 && x0 < sw) {
+                const uint32_t c = tI[r + 1][wc];
+                const uint32_t l = wc > PT_W0 ? tI[r + 1][wc - 1] : 0u;  // the first / last loaded word only serves
+                const uint32_t q = wc + 1 < PT_W1 ? tI[r + 1][wc + 1] : 0u;  // columns whose neighbours lie inside it
+                const uint32_t left  = __funnelshift_r(l, c, 24);  // columns x-1 .. x+2
+                const uint32_t right = __funnelshift_r(c, q, 8);   // columns x+1 .. x+4
+                out = __vaddus4(__vabsdiffu4(right, left), __vabsdiffu4(tI[r + 2][wc], tI[r][wc]));
+                // first / last column of the image and everything beyond it: 0 (SimdLib.h:856-884)
+                uint32_t mask = 0xffffffffu;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (x0 + k <= 0 || x0 + k >= sw - 1) mask &= ~(0xffu << (8 * k));
+                out &= mask;
+            }
+            tG[r][wc] = out;
+        }
+        __syncthreads();
+    }
+
+    // ---- stage 3: BORDER_REFLECT_101 inside shared memory (border CTAs only) ----
+    const int xlo = 2 * ox - 2, xhi = 2 * ox + 2 * PT_X;  // source columns / rows the taps of this tile reach
+    const int ylo = y00, yhi = y00 + PT_ROWS - 1;
+    if (xlo < 0 || xhi >= sw || ylo < 0 || yhi >= sh) {
+        uint8_t* bI = reinterpret_cast<uint8_t*>(&tI[BASE ? 1 : 0][0]);  // row 0 = source row y00 in both tiles
+        uint8_t* bG = reinterpret_cast<uint8_t*>(&tG[0][0]);
+        // columns first (in-image rows), then whole rows (which then carry the mirrored columns)
+        for (int i = tid; i < PT_ROWS * 4; i += 256) {
+            const int r = i >> 2, k = i & 3;  // k: 0,1 -> columns -2,-1;  2,3 -> columns sw, sw+1
+            const int x = k < 2 ? k - 2 : sw + (k - 2);
+            const int y = y00 + r;
+            if (x >= xlo && x <= xhi && (x < 0 || x >= sw) && y >= 0 && y < sh) {
+                const int xs = reflect101(x, sw);
+                bI[r * PT_PW * 4 + (x - x00)] = bI[r * PT_PW * 4 + (xs - x00)];
+                bG[r * PT_PW * 4 + (x - x00)] = bG[r * PT_PW * 4 + (xs - x00)];
+            }
+        }
+        __syncthreads();
+        for (int i = tid; i < 4 * (PT_W1 - PT_W0); i += 256) {
+            const int k = i / (PT_W1 - PT_W0), wc = PT_W0 + i - k * (PT_W1 - PT_W0);
+            const int y = k < 2 ? k - 2 : sh + (k - 2);
+            if (y >= ylo && y <= yhi && (y < 0 || y >= sh)) {
+                const int ys = reflect101(y, sh);
+                tI[(BASE ? 1 : 0) + y - y00][wc] = tI[(BASE ? 1 : 0) + ys - y00][wc];
+                tG[y - y00][wc]                  = tG[ys - y00][wc];
+            }
+        }
+        __syncthreads();
+    }
+
+    // ---- BASE: gradient level 0, the exclusive 128 x 32 area, 16-byte stores ----
+    if (BASE) {
+        const int j = tid >> 3, q = tid & 7;  // 32 rows x 8 segments of 16 bytes
+        const int y = 2 * oy + j, x = 2 * ox + 16 * q;
+        if (y < sh && x < spitch) {
+            uint4 v = *reinterpret_cast<const uint4*>(&tG[2 + j][4 + 4 * q]);
+            // nothing but zeros beyond the image width (columns inside the row padding)
+            uint32_t* vv = reinterpret_cast<uint32_t*>(&v);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int rem = sw - (x + 4 * k);
+                if (rem <= 0)
+                    vv[k] = 0u;
+                else if (rem < 4)
+                    vv[k] &= (1u << (8 * rem)) - 1u;
+            }
+            *reinterpret_cast<uint4*>(grad0 + (long long)frame * sstride + (long long)y * spitch + x) = v;
+        }
+    }
+
+    // ---- stage 4: horizontal pass, outputs (tx, tx + 1) from tile bytes 2 tx + 14 .. 2 tx + 20 ----
+    for (int i = tid; i < 2 * PT_ROWS * (PT_X / 2); i += 256) {
+        const int st = i / (PT_ROWS * (PT_X / 2));  // 0 image, 1 gradient
+        const int j  = i - st * (PT_ROWS * (PT_X / 2));
+        const int r = j / (PT_X / 2), tp = j - r * (PT_X / 2);  // tx = 2 tp
+        const uint32_t* row = st ? &tG[r][0] : &tI[(BASE ? 1 : 0) + r][0];
+        const uint32_t w0 = row[3 + tp], w1 = row[4 + tp], w2 = row[5 + tp];  // tile bytes 4 tp + 12 .. 4 tp + 23
+        // taps of output tx: bytes 2, 3 of w0 and 0, 1, 2 of w1; of tx + 1: bytes 0 .. 3 of w1 and 0 of w2 (dp4a: four
+        // byte products per instruction)
+        const uint32_t h0 = __dp4a(w0, 0x04010000u, __dp4a(w1, 0x00010406u, 0u));
+        const uint32_t h1 = __dp4a(w1, 0x04060401u, w2 & 0xffu);
+        uint16_t* hrow    = st ? &hG[r][0] : &hI[r][0];
+        *reinterpret_cast<uint32_t*>(hrow + 2 * tp) = h0 | (h1 << 16);
+    }
+    __syncthreads();
+
+    // ---- stage 5: vertical pass, four outputs per thread ----
+    for (int i = tid; i < 2 * PT_Y * (PT_X / 4); i += 256) {
+        const int st = i / (PT_Y * (PT_X / 4));
+        const int j  = i - st * (PT_Y * (PT_X / 4));
+        const int ty = j / (PT_X / 4), tq = j - ty * (PT_X / 4);
+        const int x = ox + 4 * tq, y = oy + ty;
+        if (y >= dh || x >= dpitch) continue;
+        const uint16_t(*h)[PT_X] = st ? hG : hI;
+        // two 16-bit lanes per register: the horizontal sums are <= 4,080, the weighted column sum + 128 <= 65,408
+        uint32_t a0 = 0x00800080u, a1 = 0x00800080u;
+#pragma unroll
+        for (int k = 0; k < 5; k++) {
+            const uint2 v    = *reinterpret_cast<const uint2*>(&h[2 * ty + k][4 * tq]);
+            const uint32_t c = k == 0 || k == 4 ? 1u : (k == 2 ? 6u : 4u);
+            a0 += c * v.x;
+            a1 += c * v.y;
+        }
+        uint32_t out = __byte_perm(a0, a1, 0x7531);  // the high byte of each lane = (sum + 128) >> 8
+        if (x + 3 >= dw) {                            // zeros in the row padding
+            const int rem = dw - x;
+            out           = rem <= 0 ? 0u : (out & ((1u << (8 * rem)) - 1u));
+        }
+        uint8_t* d = (st ? dst_grad : dst_img) + (long long)frame * dstride + (long long)y * dpitch + x;
+        *reinterpret_cast<uint32_t*>(d) = out;
+    }
+}
+
+// cv::pyrDown, one level, both stacks, byte-wise: only for levels smaller than 8 x 8, where the reflection can wrap
+// more than once.  grid: (ceil(dw/TX), ceil(dh/TY), 2 * n_frames)
 constexpr int TX = 64, TY = 8;
 constexpr int SW = 2 * TX + 3, SH = 2 * TY + 3;
 
-__global__ void __launch_bounds__(256) k_pyrdown(const uint8_t* __restrict__ src_img, uint8_t* __restrict__ dst_img,
-                                                 const uint8_t* __restrict__ src_grad, uint8_t* __restrict__ dst_grad,
-                                                 int sw, int sh, int spitch, long long sstride, int dw, int dh,
-                                                 int dpitch, long long dstride)
+__global__ void __launch_bounds__(256) k_pyrdown_small(const uint8_t* __restrict__ src_img, uint8_t* __restrict__ dst_img,
+                                                       const uint8_t* __restrict__ src_grad, uint8_t* __restrict__ dst_grad,
+                                                       int sw, int sh, int spitch, long long sstride, int dw, int dh,
+                                                       int dpitch, long long dstride)
 {
     __shared__ uint8_t tile[SH][SW + 1];
     __shared__ uint16_t hsum[SH][TX];
@@ -137,22 +314,46 @@ svo_status launch_pyramid_build(svo_ctx* ctx, int first_slot, int n)
 {
     const PyramidArena& a = ctx->arena;
     const LevelGeom& g0   = a.geom[0];
-    {
-        dim3 grid((g0.pitch / 4 + 127) / 128, g0.h, n);
-        k_abs_gradient<<<grid, 128, 0, ctx->stream>>>(a.img[0] + first_slot * g0.plane_stride,
-                                                      a.grad[0] + first_slot * g0.plane_stride, g0.w, g0.h, g0.pitch,
-                                                      g0.plane_stride);
-        ctx->launches++;
-    }
+    bool grad0_done       = false;
     for (int l = 1; l < a.levels; l++) {
         const LevelGeom& s = a.geom[l - 1];
         const LevelGeom& d = a.geom[l];
-        dim3 grid((d.w + TX - 1) / TX, (d.h + TY - 1) / TY, 2 * n);
-        k_pyrdown<<<grid, 256, 0, ctx->stream>>>(a.img[l - 1] + first_slot * s.plane_stride,
-                                                 a.img[l] + first_slot * d.plane_stride,
-                                                 a.grad[l - 1] + first_slot * s.plane_stride,
-                                                 a.grad[l] + first_slot * d.plane_stride, s.w, s.h, s.pitch,
-                                                 s.plane_stride, d.w, d.h, d.pitch, d.plane_stride);
+        if (s.w >= 8 && s.h >= 8) {
+            dim3 grid((d.w + PT_X - 1) / PT_X, (d.h + PT_Y - 1) / PT_Y, n);
+            if (l == 1) {  // fused: gradient level 0 + level 1 of both stacks from one read of the level-0 image
+                k_pyr_level<true><<<grid, 256, 0, ctx->pyr_stream>>>(
+                    a.img[0] + first_slot * s.plane_stride, nullptr, a.img[1] + first_slot * d.plane_stride,
+                    a.grad[1] + first_slot * d.plane_stride, a.grad[0] + first_slot * s.plane_stride, s.w, s.h, s.pitch,
+                    s.plane_stride, d.w, d.h, d.pitch, d.plane_stride);
+                grad0_done = true;
+            } else {
+                k_pyr_level<false><<<grid, 256, 0, ctx->pyr_stream>>>(
+                    a.img[l - 1] + first_slot * s.plane_stride, a.grad[l - 1] + first_slot * s.plane_stride,
+                    a.img[l] + first_slot * d.plane_stride, a.grad[l] + first_slot * d.plane_stride, nullptr, s.w, s.h,
+                    s.pitch, s.plane_stride, d.w, d.h, d.pitch, d.plane_stride);
+            }
+        } else {
+            if (l == 1) {
+                dim3 g((g0.pitch / 4 + 127) / 128, g0.h, n);
+                k_abs_gradient<<<g, 128, 0, ctx->pyr_stream>>>(a.img[0] + first_slot * g0.plane_stride,
+                                                             a.grad[0] + first_slot * g0.plane_stride, g0.w, g0.h, g0.pitch,
+                                                             g0.plane_stride);
+                ctx->launches++;
+                grad0_done = true;
+            }
+            dim3 grid((d.w + TX - 1) / TX, (d.h + TY - 1) / TY, 2 * n);
+            k_pyrdown_small<<<grid, 256, 0, ctx->pyr_stream>>>(a.img[l - 1] + first_slot * s.plane_stride,
+                                                           a.img[l] + first_slot * d.plane_stride,
+                                                           a.grad[l - 1] + first_slot * s.plane_stride,
+                                                           a.grad[l] + first_slot * d.plane_stride, s.w, s.h, s.pitch,
+                                                           s.plane_stride, d.w, d.h, d.pitch, d.plane_stride);
+        }
+        ctx->launches++;
+    }
+    if (!grad0_done) {  // a single-level pyramid still has its gradient image
+        dim3 g((g0.pitch / 4 + 127) / 128, g0.h, n);
+        k_abs_gradient<<<g, 128, 0, ctx->pyr_stream>>>(a.img[0] + first_slot * g0.plane_stride,
+                                                     a.grad[0] + first_slot * g0.plane_stride, g0.w, g0.h, g0.pitch, g0.plane_stride);
         ctx->launches++;
     }
     SVO_CUDA(cudaGetLastError());
@@ -163,7 +364,7 @@ svo_status launch_repack(svo_ctx* ctx, const uint8_t* dsrc, long long src_pitch,
 {
     const LevelGeom& g = ctx->arena.geom[0];
     dim3 grid((g.pitch / 16 + 127) / 128, g.h, n);
-    k_repack<<<grid, 128, 0, ctx->stream>>>(dsrc, src_pitch, src_frame_stride, ctx->arena.img[0] + (int64_t)first_slot * g.plane_stride,
+    k_repack<<<grid, 128, 0, ctx->pyr_stream>>>(dsrc, src_pitch, src_frame_stride, ctx->arena.img[0] + (int64_t)first_slot * g.plane_stride,
                                             g.w, g.h, g.pitch, g.plane_stride);
     ctx->launches++;
     SVO_CUDA(cudaGetLastError());

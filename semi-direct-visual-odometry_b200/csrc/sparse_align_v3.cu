@@ -206,6 +206,10 @@ __global__ void __launch_bounds__(NT, V3Occ<NT>::MINB) k_align_cluster(const V3A
     sp += (size_t)3 * NT * 8;
     SelCtx<NT> sc;
     sc.init(sp, C);
+#ifdef SVO_PROFILE
+    for (int i = 0; i < 12; i++) sc.prof[i] = 0;
+    sc.tlast = clock64();
+#endif
     sp += cs_smem_bytes<NT>();
     sp          = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sp) + 15) & ~uintptr_t(15));
     double* red = reinterpret_cast<double*>(sp);  // [NW][32]
@@ -331,7 +335,7 @@ __global__ void __launch_bounds__(NT, V3Occ<NT>::MINB) k_align_cluster(const V3A
         uint32_t winLo[G::FW], winHi[G::FW];
         int wx = 0, wy = 0;
         bool winValid = false;
-        Bracket brMed{0u, 4, false}, brMad{0u, 4, false};  // selection brackets carried between evaluations
+        Bracket brMed{0u, 4, false, false}, brMad{0u, 4, false, false};  // selection brackets carried between evaluations
 
         // ================= evaluate (computeResiduals + tukeyWeighting + normal equations) =================
 #ifdef SVO_PROFILE
@@ -438,14 +442,24 @@ __global__ void __launch_bounds__(NT, V3Occ<NT>::MINB) k_align_cluster(const V3A
             uint32_t negMask = 0;            // sign of (2 q - med2) per patch pixel, to undo the MAD key transform below
             int mid          = 0;            // numValid / 2: element `mid` of the sorted N-vector (invalid rows sort last)
             int numValid     = 0;
-            {
-                uint32_t kHi, kLo, dHi, dLo;
+            // ONE call site for both order statistics (median of r, then median of |r - med|): the selection code
+            // is large and the kernel is bound by instruction fetch as much as by issue
+#pragma unroll 1
+            for (int s = 0; s < 2; s++) {
+                Bracket b = s ? brMad : brMed;
+                uint32_t kHi, kLo;
                 int tier;
                 // mean of elements mid-1 and mid when N is even: the selection returns both
-                if (cs_tiered_select<G::AREA, NT>(key, vis, 512 - 32, mid, true, N, brMed, sc, &kHi, &kLo, &tier)) {
+                const bool ok = cs_tiered_select<G::AREA, NT>(key, vis, s ? 0 : 512 - 32, mid, s == 0, N, b, sc, &kHi, &kLo, &tier);
+                if (s)
+                    brMad = b;
+                else
+                    brMed = b;
+                if (!ok) break;  // no visible pixel (s == 0 only)
+                tierCount += tier == 1 ? 1 : (tier == 2 ? 0x100 : 0x10000);
+                if (s == 0) {
                     numValid = (int)sc.auxTotal * G::AREA;
-                    tierCount += tier == 1 ? 1 : (tier == 2 ? 0x100 : 0x10000);
-                    med2 = ((int)kHi - (1 << 25)) + ((int)kLo - (1 << 25));
+                    med2     = ((int)kHi - (1 << 25)) + ((int)kLo - (1 << 25));
                     // keys in place: |2 q - med2|, deviations in half fixed-point units (2^-17)
 #pragma unroll
                     for (int i = 0; i < G::AREA; i++) {
@@ -453,9 +467,8 @@ __global__ void __launch_bounds__(NT, V3Occ<NT>::MINB) k_align_cluster(const V3A
                         negMask |= (d < 0 ? 1u : 0u) << i;
                         key[i] = (uint32_t)abs(d);
                     }
-                    cs_tiered_select<G::AREA, NT>(key, vis, 0, mid, false, N, brMad, sc, &dHi, &dLo, &tier);
-                    tierCount += tier == 1 ? 1 : (tier == 2 ? 0x100 : 0x10000);
-                    const double mad = 0.5 * ((double)dHi + (double)dLo);
+                } else {
+                    const double mad = 0.5 * ((double)kHi + (double)kLo);
                     sigma            = 1.482602218505602 * mad * (1.0 / 131072.0);
                     if (sigma <= DBL_EPSILON) sigma = DBL_EPSILON;
                 }
@@ -705,8 +718,10 @@ __global__ void __launch_bounds__(NT, V3Occ<NT>::MINB) k_align_cluster(const V3A
             if (ctrl->done) break;
         }
 #ifdef SVO_PROFILE
-        if (a.dbg && job == 0 && crank == 0 && tid == 33)
+        if (a.dbg && job == 0 && crank == 0 && tid == 33) {
             for (int i = 0; i < 8; i++) a.dbg[si * 8 + i] = tph[i];
+            for (int i = 0; i < 12; i++) a.dbg[32 + i] = sc.prof[i];  // selection phases, summed over the levels so far
+        }
 #endif
         if (tid == 0) {
             ctrl->evals_total += ctrl->evals_level;

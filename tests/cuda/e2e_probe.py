@@ -43,3 +43,13 @@ with torch.cuda.stream(stream):
     print("torch 1D pinned->device 478MB: %.2f ms" % T(lambda: a.copy_(src, non_blocking=True)))
     pag = np.array(frames[n:])  # pageable copy
     print("upload from pageable (staged): %.2f ms" % T(lambda: ctx.upload(n, pag)))
+    # ingest pipeline pieces
+    print("prefetch 1024 cur frames (ingest streams): %.2f ms" % T(lambda: ctx.prefetch(n, frames[n:])))
+    half = torch.empty(n * h * w // 2, dtype=torch.uint8, device="cuda")
+    for mb in (4, 15, 64, 256):
+        nb = mb << 20
+        chunks = [(i, min(nb, src.numel() - i)) for i in range(0, src.numel(), nb)]
+        def f():
+            for o, m in chunks:
+                a[o:o + m].copy_(src[o:o + m], non_blocking=True)
+        print("torch pinned->device 478MB in %d MB chunks: %.2f ms" % (mb, T(f)))

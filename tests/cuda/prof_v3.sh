@@ -1,13 +1,9 @@
+# ncu --set full capture of one k_align_cluster launch + hot source lines; usage: prof_v3.sh <tag> <launch-skip> [env...]
 set -x
+tag=$1; skip=$2; shift 2
 B="python bench.py --pairs 148 --steps 1 --warmup 1 --no-cpu-baseline"
-prof() { # name skip env
-  env $3 ncu --set full --clock-control none --import-source on -k regex:k_align_cluster --launch-skip $2 --launch-count 1 -f -o gpurun_out/prof_$1 $B > gpurun_out/ncu_$1.log 2>&1
-  ncu -i gpurun_out/prof_$1.ncu-rep --page raw --csv > gpurun_out/raw_$1.csv 2>/dev/null
-  ncu -i gpurun_out/prof_$1.ncu-rep --page source --csv --print-source cuda,sass > gpurun_out/src_$1.csv 2>/dev/null
-  python profiles/hot_lines.py gpurun_out/src_$1.csv 60 > gpurun_out/hot_$1.txt
-  rm -f gpurun_out/src_$1.csv
-}
-prof r1f_nt256_c2 2 "SVO_ALIGN_NT=256"
-prof r1f_single_nt64_c8 10 "A=1"
-prof r1f_nt512_c1 2 "SVO_ALIGN_NT=512"
-ls -la gpurun_out/
+env "$@" ncu --set full --clock-control none --import-source on -k regex:k_align_cluster --launch-skip $skip --launch-count 1 -f -o gpurun_out/prof_$tag $B > gpurun_out/ncu_$tag.log 2>&1
+ncu -i gpurun_out/prof_$tag.ncu-rep --page raw --csv > gpurun_out/raw_$tag.csv 2>/dev/null
+ncu -i gpurun_out/prof_$tag.ncu-rep --page source --csv --print-source cuda,sass > gpurun_out/src_$tag.csv 2>/dev/null
+python profiles/hot_lines.py gpurun_out/src_$tag.csv 70 > gpurun_out/hot_$tag.txt
+rm -f gpurun_out/src_$tag.csv
