@@ -231,6 +231,41 @@ svo_status svo_feature_align_launch(svo_ctx* ctx);
 svo_status svo_feature_align_d2h(svo_ctx* ctx);
 svo_status svo_feature_align_fetch(svo_ctx* ctx, svo_fa_result* results);
 
+/* ---------------------------------------------------------------------------------------------
+ * The per-frame front end as ONE CUDA graph launch: what System::processNewFrame runs for a new camera image between
+ * Frame::Frame (src/system.cpp:36, src/frame.cpp:26) and the candidate matching of Map::reprojectMap /
+ * addCandidateToFrame (src/system.cpp:313-330, src/map.cpp:595-627):
+ *   pyramids of the new image -> gradientMagnitudeByValue on it -> ImageAlignment::align(ref, new) ->
+ *   Frame::world2image of every tracked point with the ALIGNED pose + isInFrame(px, 3) (src/map.cpp:601-602) ->
+ *   FeatureAlignment::align of those candidates against their owner frame's gradient image.
+ * The graph is captured once per (slots, parameters) configuration and cached in the context.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t ref_slot, kf_slot, cur_slot; /* frame slots; the new image is written to cur_slot */
+    int32_t cell;                        /* FeatureSelection cell size (config/config.json: 30) */
+    uint32_t thr;                        /* gradient threshold (50) */
+    int32_t max_features;                /* capacity of the captured graph: n_ref + n_kf <= max_features */
+    svo_align_params align;              /* patch 4 or 5 */
+    svo_fa_params fa;
+} svo_frontend_params;
+
+typedef struct {
+    svo_align_result align; /* curFrame->m_absPose after ImageAlignment::align, its return value and status */
+    int32_t n_selected;     /* features gradientMagnitudeByValue found on the new frame */
+    int32_t n_candidates;   /* tracked features that reprojected into the new frame and were aligned */
+} svo_frontend_result;
+
+/* job: n_ref, n_kf and the three poses are used (slots come from prm, feat_offset is 0).  feats: n_feats records, n_ref
+ * of the reference frame then n_kf of the last keyframe.  occupancy: as svo_select_grid, nullable.  selected: the new
+ * features, cell raster order.  refined: n_feats records, one per feature: px = the refined pixel position in the new
+ * frame; features without a point or not reprojected into the frame have status SVO_ST_FAILED, iterations 0 and a NaN
+ * rmse.  Synchronous.  img may be svo_frontend_image_buffer(ctx) (page-locked, w*h bytes dense): no staging copy. */
+svo_status svo_frontend_run(svo_ctx* ctx, const svo_frontend_params* prm, const uint8_t* img, int pitch,
+                            const svo_align_job* job, const svo_align_feature* feats, int n_feats,
+                            const uint8_t* occupancy, svo_frontend_result* result, svo_feature_px* selected,
+                            int max_selected, svo_fa_result* refined);
+uint8_t* svo_frontend_image_buffer(svo_ctx* ctx);
+
 #ifdef __cplusplus
 }
 #endif

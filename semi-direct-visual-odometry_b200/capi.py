@@ -14,6 +14,7 @@ LIB_PATH = os.environ.get("SVO_B200_LIB", os.path.join(_HERE, "libsvo_b200.so"))
 
 OK, ERR_INVALID, ERR_CUDA, ERR_CAPACITY, ERR_NO_DEVICE, ERR_UNSUPPORTED = 0, -1, -2, -3, -4, -5
 LM_FAITHFUL, LM_ITERATED, GN = 0, 1, 2
+ST_SUCCESS, ST_FAILED = 0, 9  # Optimizer::Status (include/optimizer.hpp:21-33), the two the harness tests against
 MAX_LEVELS = 8
 
 # every symbol include/svo_b200.h declares (tests check that the library exports all of them)
@@ -24,7 +25,7 @@ SYMBOLS = [
     "svo_sparse_align_h2d", "svo_sparse_align_launch", "svo_sparse_align_d2h", "svo_sparse_align_fetch",
     "svo_sparse_align_results_device", "svo_debug_cycles",
     "svo_feature_align", "svo_feature_align_stage", "svo_feature_align_h2d", "svo_feature_align_launch",
-    "svo_feature_align_d2h", "svo_feature_align_fetch",
+    "svo_feature_align_d2h", "svo_feature_align_fetch", "svo_frontend_run", "svo_frontend_image_buffer",
 ]
 
 
@@ -43,6 +44,11 @@ class FaParams(C.Structure):
     _fields_ = [("patch_size", C.c_int32), ("mode", C.c_int32), ("max_iter", C.c_int32), ("reserved", C.c_int32)]
 
 
+class FrontendParams(C.Structure):
+    _fields_ = [("ref_slot", C.c_int32), ("kf_slot", C.c_int32), ("cur_slot", C.c_int32), ("cell", C.c_int32),
+                ("thr", C.c_uint32), ("max_features", C.c_int32), ("align", AlignParams), ("fa", FaParams)]
+
+
 FEATURE_PX_DTYPE = np.dtype([("x", "<i4"), ("y", "<i4"), ("magnitude", "<i4")])
 ALIGN_FEATURE_DTYPE = np.dtype([("px", "<f8", 2), ("bearing", "<f8", 3), ("point", "<f8", 3), ("has_point", "<i4"),
                                 ("reserved", "<i4")])
@@ -51,6 +57,7 @@ ALIGN_JOB_DTYPE = np.dtype([("ref_slot", "<i4"), ("kf_slot", "<i4"), ("cur_slot"
                             ("T_cur", "<f8", 7)])
 ALIGN_RESULT_DTYPE = np.dtype([("T_cur", "<f8", 7), ("rmse", "<f8"), ("status", "<i4"), ("evaluations", "<i4"),
                                ("iterations", "<i4"), ("reserved", "<i4")])
+FRONTEND_RESULT_DTYPE = np.dtype([("align", ALIGN_RESULT_DTYPE), ("n_selected", "<i4"), ("n_candidates", "<i4")])
 ALIGN_STATS_DTYPE = np.dtype([("H", "<f8", (6, 6)), ("g", "<f8", 6), ("dx", "<f8", 6), ("chi2", "<f8"), ("sigma", "<f8"),
                               ("lam", "<f8"), ("pose_after", "<f8", 7), ("rmse", "<f8"), ("n_px", "<i4"),
                               ("status", "<i4"), ("iterations", "<i4"), ("evaluations", "<i4")])
@@ -109,6 +116,9 @@ def load():
     L.svo_sparse_align_results_device.argtypes = [vp]
     L.svo_debug_cycles.argtypes = [vp, vp]
     L.svo_sparse_align_results_device.restype = vp
+    L.svo_frontend_run.argtypes = [vp, C.POINTER(FrontendParams), vp, i, vp, vp, i, vp, vp, vp, i, vp]
+    L.svo_frontend_image_buffer.argtypes = [vp]
+    L.svo_frontend_image_buffer.restype = vp
     L.svo_feature_align.argtypes = [vp, vp, i, C.POINTER(FaParams), vp]
     L.svo_feature_align_stage.argtypes = [vp, vp, i, C.POINTER(FaParams)]
     L.svo_feature_align_fetch.argtypes = [vp, vp]
@@ -294,6 +304,30 @@ class Context:
     @property
     def results_device_ptr(self):
         return self.L.svo_sparse_align_results_device(self.h)
+
+    # ---- the whole per-frame front end, one CUDA graph launch ----
+    def frontend_run(self, img, job, feats, ref_slot, kf_slot, cur_slot, cell=30, thr=50, max_features=512, patch_size=5,
+                     min_level=0, max_level=3, mode=LM_FAITHFUL, max_iter=20, fa_patch=7, fa_mode=LM_FAITHFUL, fa_max_iter=20,
+                     occupancy=None):
+        """returns (align result record, selected features, refined per-feature records)"""
+        img = np.ascontiguousarray(img, dtype=np.uint8)
+        assert img.shape == (self.height, self.width)
+        job = np.ascontiguousarray(job, dtype=ALIGN_JOB_DTYPE).reshape(-1)
+        feats = np.ascontiguousarray(feats, dtype=ALIGN_FEATURE_DTYPE).reshape(-1)
+        prm = FrontendParams(ref_slot, kf_slot, cur_slot, cell, thr, max_features,
+                             AlignParams(patch_size, min_level, max_level, mode, max_iter, 0),
+                             FaParams(fa_patch, fa_mode, fa_max_iter, 0))
+        rows, cols = self.height // cell + 1, self.width // cell + 1
+        occ = None
+        if occupancy is not None:
+            occ = np.ascontiguousarray(np.asarray(occupancy).reshape(-1), dtype=np.uint8)
+            assert occ.size == rows * cols
+        res = np.zeros(1, FRONTEND_RESULT_DTYPE)
+        sel = np.zeros(rows * cols, FEATURE_PX_DTYPE)
+        ref = np.zeros(max(1, feats.size), FA_RESULT_DTYPE)
+        self._check(self.L.svo_frontend_run(self.h, C.byref(prm), img.ctypes.data, img.strides[0], _ptr(job), _ptr(feats),
+                                            feats.size, _ptr(occ), _ptr(res), _ptr(sel), sel.size, _ptr(ref)))
+        return res[0], sel[:int(res[0]["n_selected"])].copy(), ref[:feats.size]
 
     # ---- FeatureAlignment::align ----
     def feature_align(self, items, patch_size=7, mode=LM_FAITHFUL, max_iter=20):

@@ -22,6 +22,7 @@ void release(svo_ctx* ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->cfg.device);
     if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+    frontend_release(ctx);
     for (int l = 0; l < SVO_MAX_LEVELS; l++) {
         if (ctx->arena.img[l]) cudaFree(ctx->arena.img[l]);
         if (ctx->arena.grad[l]) cudaFree(ctx->arena.grad[l]);

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <string>
+#include <vector>
 
 #include "../../include/svo_b200.h"
 
@@ -25,6 +26,13 @@ struct ArenaView {
     const uint8_t* grad[SVO_MAX_LEVELS];
     int w[SVO_MAX_LEVELS], h[SVO_MAX_LEVELS], pitch[SVO_MAX_LEVELS];
     long long plane_stride[SVO_MAX_LEVELS];
+};
+
+// svo_frontend_run: one captured CUDA graph per (slots, parameters) configuration
+struct FrontendGraph {
+    svo_frontend_params prm;
+    cudaGraph_t graph;
+    cudaGraphExec_t exec;
 };
 
 struct svo_ctx {
@@ -95,6 +103,13 @@ struct svo_ctx {
     svo_align_params staged_params;
     int last_align_nt, last_align_c;    // shape of the last cluster launch (threads per CTA, CTAs per pair)
 
+    // front-end graphs
+    FrontendGraph fe_graphs[8];
+    int fe_count;
+    int fe_kernel_nodes;           // kernel nodes of the last instantiated front-end graph
+    svo_align_result* h_fe_align;  // pinned
+    svo_fa_result* h_fe_fa;        // pinned, max_features records
+
     // feature alignment batch
     svo_fa_item* h_fa_items;     // pinned
     svo_fa_result* h_fa_results; // pinned
@@ -140,6 +155,7 @@ svo_status launch_repack(svo_ctx* ctx, const uint8_t* dsrc, long long src_pitch,
 svo_status launch_grid_select(svo_ctx* ctx, int slot, int cell, uint32_t thr, int rows, int cols);
 svo_status launch_sparse_align(svo_ctx* ctx);
 svo_status launch_feature_align(svo_ctx* ctx);
+void frontend_release(svo_ctx* ctx);
 size_t sparse_align_smem_bytes(int nthreads, int max_features, int patch_area);
 bool sparse_align_v3_supported(const svo_ctx* ctx, int maxF);
 svo_status launch_sparse_align_v3(svo_ctx* ctx, int maxF);

@@ -76,6 +76,18 @@ __global__ void __launch_bounds__(128) k_feature_align(const FaArgs a)
     const int lane = threadIdx.x & 31;
     if (item >= a.n) return;
     const svo_fa_item it = a.items[item];
+    if (it.ref_slot < 0) {  // slot without a candidate (svo_frontend_run: no 3D point / not reprojected into the frame)
+        if (lane == 0) {
+            svo_fa_result res;
+            res.px[0]       = it.px[0];
+            res.px[1]       = it.px[1];
+            res.rmse        = __longlong_as_double(0x7ff8000000000000LL);
+            res.status      = SVO_ST_FAILED;
+            res.iterations  = 0;
+            a.results[item] = res;
+        }
+        return;
+    }
     const int P = a.prm.patch_size, area = P * P, half = P / 2, pb = -half;
     const int w = a.view.w[0], h = a.view.h[0], pitch = a.view.pitch[0];
     const uint8_t* refG = a.view.grad[0] + (long long)it.ref_slot * a.view.plane_stride[0];

@@ -336,3 +336,53 @@ def test_sparse_align_generic_sizes(pkg, orc, synth, pair_cache):
         res, stats = ctx.sparse_align(_job(pkg, big), big["feats"], mode=pkg.capi.GN, max_iter=30)
     _check_levels(stats[0][:1], lv[:1], synth, False)
     assert synth.rotation_angle(res[0]["T_cur"], T) < ROT_TOL and np.abs(res[0]["T_cur"][4:] - T[4:]).max() < TRANS_TOL
+
+
+# ------------------------------------------------------------------------------------------------
+# the per-frame front end as one CUDA graph (BASELINE config 3)
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode", ["LM_FAITHFUL", "GN"])
+def test_frontend_graph_matches_composition(pkg, orc, synth, pair_cache, mode):
+    """svo_frontend_run == upload + select_grid + sparse_align + (reprojection) + feature_align called one by one
+    (each of which is checked against the oracle above), twice in a row (cached graph), and the pose == the oracle's."""
+    pair = pair_cache(6, 500)
+    capi = pkg.capi
+    m = getattr(capi, mode)
+    n = len(pair["feats"])
+    with _ctx(pkg, pair, max_features=512) as ctx:
+        ctx.upload(0, pair["ref"])
+        job = _job(pkg, pair, 0, 0, 1)
+        # --- composition ---
+        ctx.upload(1, pair["cur"])
+        sel = ctx.select_grid(1, 30, 50)
+        res, _ = ctx.sparse_align(job, pair["feats"], mode=m, max_iter=30, want_stats=False)
+        R, t = synth.se3_Rt(res[0]["T_cur"])
+        pc = pair["feats"]["point"] @ R.T + t
+        K = pair["K"]
+        uv = np.stack([K[0] * (pc[:, 0] / pc[:, 2]) + K[2], K[1] * (pc[:, 1] / pc[:, 2]) + K[3]], 1)
+        ok = (pc[:, 2] > 0) & (uv[:, 0] >= 3) & (uv[:, 1] >= 3) & (uv[:, 0] < pair["w"] - 3) & (uv[:, 1] < pair["h"] - 3) \
+            & (pair["feats"]["has_point"] != 0)
+        items = np.zeros(n, capi.FA_ITEM_DTYPE)
+        items["ref_slot"], items["cur_slot"] = 0, 1
+        items["ref_px"], items["px"] = pair["feats"]["px"], uv
+        items["A"] = (1, 0, 0, 1)
+        fa = ctx.feature_align(items[ok], patch_size=7, mode=capi.LM_FAITHFUL)
+        # --- one graph launch, into another slot; then again (graph cache) ---
+        for rep in range(2):
+            out, gsel, gfa = ctx.frontend_run(pair["cur"], job, pair["feats"], 0, 0, 2, cell=30, thr=50, max_features=512,
+                                              mode=m, max_iter=30, fa_patch=7, fa_mode=capi.LM_FAITHFUL)
+            assert np.array_equal(np.stack([gsel["x"], gsel["y"], gsel["magnitude"]], 1),
+                                  np.stack([sel["x"], sel["y"], sel["magnitude"]], 1))
+            assert np.array_equal(out["align"]["T_cur"], res[0]["T_cur"]) and out["align"]["status"] == res[0]["status"]
+            assert out["align"]["rmse"] == res[0]["rmse"]
+            assert out["n_candidates"] == int(ok.sum())
+            skipped = (gfa["status"] == capi.ST_FAILED) & (gfa["iterations"] == 0)
+            assert np.array_equal(~skipped, ok)
+            assert np.abs(gfa["px"][ok] - fa["px"]).max() < 1e-6
+            assert np.allclose(gfa["rmse"][ok], fa["rmse"], rtol=1e-6, equal_nan=True)
+            assert np.array_equal(gfa["status"][ok], fa["status"])
+        # the new frame's pyramids are in the slot the graph wrote
+        assert np.array_equal(ctx.download(2, 3, 1), ctx.download(1, 3, 1))
+    rmse, T, status, lv = _oracle_align(orc, pair, _pyrs(orc, pair), getattr(orc, mode), max_iter=30)
+    assert synth.rotation_angle(out["align"]["T_cur"], T) < ROT_TOL
+    assert np.abs(out["align"]["T_cur"][4:] - T[4:]).max() < TRANS_TOL
