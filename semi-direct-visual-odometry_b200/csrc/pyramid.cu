@@ -91,7 +91,7 @@ __device__ __forceinline__ int reflect101(int i, int n)
 // (Simd::AbsGradientSaturatedSum) of the tile is computed in shared memory with SIMD-in-word byte arithmetic, its
 // exclusive 128 x 32 area is written out as gradient level 0 with 16-byte stores, and both tiles are decimated -- so a
 // frame's level-0 image is read from HBM once and the level-0 gradient never re-read.
-//   stage 1  aligned 32-bit loads of the source tile(s) (rows/columns outside the image are skipped)
+//   stage 1  aligned 128-bit loads of the source tile(s) (rows/columns outside the image are skipped)
 //   stage 2  BASE: gradient words from three image rows (funnel shifts + __vabsdiffu4 + __vaddus4), border pixels 0
 //   stage 3  BORDER_REFLECT_101: the <= 2 rows / columns a 5-tap kernel reaches outside the image are mirrored inside
 //            shared memory (border CTAs only)
@@ -127,21 +127,23 @@ __global__ void __launch_bounds__(256) k_pyr_level(const uint8_t* __restrict__ s
     const uint8_t* sG = BASE ? nullptr : src_grad + (long long)frame * sstride;
     const int spw = spitch >> 2;
 
-    // ---- stage 1: loads ----
-    for (int i = tid; i < IROWS * (PT_W1 - PT_W0); i += 256) {
-        const int r = i / (PT_W1 - PT_W0), wc = PT_W0 + i - r * (PT_W1 - PT_W0);
-        const int y = iy0 + r, xw = (x00 >> 2) + wc;  // source word column
-        uint32_t v  = 0;
-        if (y >= 0 && y < sh && xw >= 0 && xw < spw) v = __ldg(reinterpret_cast<const uint32_t*>(sI + (long long)y * spitch) + xw);
-        tI[r][wc] = v;
+    // ---- stage 1: loads, 16 bytes each (10 per tile row; the first and last reach past the words the taps need and
+    // are dropped where they would leave the pitched row) ----
+    const int spq = spitch >> 4;  // 16-byte groups per source row
+    for (int i = tid; i < IROWS * (PT_PW / 4); i += 256) {
+        const int r = i / (PT_PW / 4), qc = i - r * (PT_PW / 4);
+        const int y = iy0 + r, xq = (x00 >> 4) + qc;  // source 16-byte column
+        uint4 v     = make_uint4(0u, 0u, 0u, 0u);
+        if (y >= 0 && y < sh && xq >= 0 && xq < spq) v = __ldg(reinterpret_cast<const uint4*>(sI + (long long)y * spitch) + xq);
+        *reinterpret_cast<uint4*>(&tI[r][4 * qc]) = v;
     }
     if (!BASE) {
-        for (int i = tid; i < PT_ROWS * (PT_W1 - PT_W0); i += 256) {
-            const int r = i / (PT_W1 - PT_W0), wc = PT_W0 + i - r * (PT_W1 - PT_W0);
-            const int y = y00 + r, xw = (x00 >> 2) + wc;
-            uint32_t v  = 0;
-            if (y >= 0 && y < sh && xw >= 0 && xw < spw) v = __ldg(reinterpret_cast<const uint32_t*>(sG + (long long)y * spitch) + xw);
-            tG[r][wc] = v;
+        for (int i = tid; i < PT_ROWS * (PT_PW / 4); i += 256) {
+            const int r = i / (PT_PW / 4), qc = i - r * (PT_PW / 4);
+            const int y = y00 + r, xq = (x00 >> 4) + qc;
+            uint4 v     = make_uint4(0u, 0u, 0u, 0u);
+            if (y >= 0 && y < sh && xq >= 0 && xq < spq) v = __ldg(reinterpret_cast<const uint4*>(sG + (long long)y * spitch) + xq);
+            *reinterpret_cast<uint4*>(&tG[r][4 * qc]) = v;
         }
     }
     __syncthreads();
@@ -154,17 +156,19 @@ __global__ void __launch_bounds__(256) k_pyr_level(const uint8_t* __restrict__ s
             uint32_t out = 0;
             if (y > 0 && y < sh - 1 && x0 + 3 >= 0 && x0 < sw) {
                 const uint32_t c = tI[r + 1][wc];
-                const uint32_t l = wc > PT_W0 ? tI[r + 1][wc - 1] : 0u;  // the first / last loaded word only serves
-                const uint32_t q = wc + 1 < PT_W1 ? tI[r + 1][wc + 1] : 0u;  // columns whose neighbours lie inside it
+                const uint32_t l = tI[r + 1][wc - 1];  // words PT_W0 - 1 and PT_W1 exist in the tile (16-byte loads)
+                const uint32_t q = tI[r + 1][wc + 1];
                 const uint32_t left  = __funnelshift_r(l, c, 24);  // columns x-1 .. x+2
                 const uint32_t right = __funnelshift_r(c, q, 8);   // columns x+1 .. x+4
                 out = __vaddus4(__vabsdiffu4(right, left), __vabsdiffu4(tI[r + 2][wc], tI[r][wc]));
                 // first / last column of the image and everything beyond it: 0 (SimdLib.h:856-884)
-                uint32_t mask = 0xffffffffu;
+                if (x0 <= 0 || x0 + 3 >= sw - 1) {
+                    uint32_t mask = 0xffffffffu;
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (x0 + k <= 0 || x0 + k >= sw - 1) mask &= ~(0xffu << (8 * k));
-                out &= mask;
+                    for (int k = 0; k < 4; k++)
+                        if (x0 + k <= 0 || x0 + k >= sw - 1) mask &= ~(0xffu << (8 * k));
+                    out &= mask;
+                }
             }
             tG[r][wc] = out;
         }
