@@ -239,6 +239,9 @@ def run_b200(a, rank, world):
 
         gather_buf = None
         if world > 1:
+            # this rank's block of the global pair range (weak scaling: n pairs per rank), shard.py is the tested logic
+            lo, hi = pkg.shard.shard_range(world * n, rank, world)
+            assert (lo, hi) == (rank * n, rank * n + n)
             res_dev = torch.as_tensor(DevArray(ctx.results_device_ptr, n * capi.ALIGN_RESULT_DTYPE.itemsize), device="cuda")
             gather_buf = [torch.empty_like(res_dev) for _ in range(world)] if rank == 0 else None
 
@@ -254,7 +257,7 @@ def run_b200(a, rank, world):
         def step_value():
             ctx.sparse_align_launch()
             if world > 1:
-                dist.gather(res_dev, gather_buf, dst=0)
+                pkg.shard.gather_records(res_dev, dist, dst=0, out=gather_buf)
 
         for _ in range(a.warmup):
             step_value()
@@ -271,7 +274,7 @@ def run_b200(a, rank, world):
             ctx.sparse_align_launch()
             ev1[k].record(stream)
             if world > 1:
-                dist.gather(res_dev, gather_buf, dst=0)
+                pkg.shard.gather_records(res_dev, dist, dst=0, out=gather_buf)
         t_end.record(stream)
         barrier()
         tw1 = time.perf_counter()

@@ -6,5 +6,5 @@ plus the reference-shaped C++ host classes in host/.  `capi` is the ctypes harne
 it with importlib.import_module("semi-direct-visual-odometry_b200") (the repo root on sys.path).
 Nothing in this package touches oracle/ -- that is test infrastructure.
 """
-from . import capi, synth  # noqa: F401
+from . import capi, shard, synth  # noqa: F401
 from .capi import Context, SvoError, load  # noqa: F401
