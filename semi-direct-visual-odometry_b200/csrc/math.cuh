@@ -52,24 +52,24 @@ static __device__ __noinline__ void pose_update_right_exp_neg(Pose& p, const dou
     const double th2 = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
     const double th  = sqrt(th2);
     double imag, real, a, b;
+    // ONE sincos and ONE reciprocal on the serial path of the solver (every other thread of the CTA waits for this):
+    // sin th = 2 s c, cos th = 1 - 2 s^2 from the half angle; 1/th feeds sin(th/2)/th, (1-cos th)/th^2, (th-sin th)/th^3
     if (th2 < 1e-20) {
         const double th4 = th2 * th2;
         imag = 0.5 - th2 / 48.0 + th4 / 3840.0;
         real = 1.0 - th2 / 8.0 + th4 / 384.0;
+        a    = 0.5;
+        b    = 1.0 / 6.0;
     } else {
-        double s, c;
-        sincos(0.5 * th, &s, &c);
-        imag = s / th;
-        real = c;
-    }
-    if (th < 1e-10) {
-        a = 0.5;
-        b = 1.0 / 6.0;
-    } else {
-        double s, c;
-        sincos(th, &s, &c);
-        a = (1.0 - c) / th2;
-        b = (th - s) / (th2 * th);
+        double sh, ch;
+        sincos(0.5 * th, &sh, &ch);
+        const double r  = 1.0 / th;
+        const double r2 = r * r;
+        imag            = sh * r;
+        real            = ch;
+        const double s  = 2.0 * sh * ch;   // sin th
+        a               = 2.0 * sh * sh * r2;  // (1 - cos th) / th^2
+        b               = (th - s) * r2 * r;
     }
     double eq[4] = {imag * om[0], imag * om[1], imag * om[2], real};
     double c1[3], c2[3], et[3];
@@ -89,9 +89,9 @@ static __device__ __noinline__ void pose_update_right_exp_neg(Pose& p, const dou
     r[1] = aw * eq[1] + ay * eq[3] + az * eq[0] - ax * eq[2];
     r[2] = aw * eq[2] + az * eq[3] + ax * eq[1] - ay * eq[0];
     r[3] = aw * eq[3] - ax * eq[0] - ay * eq[1] - az * eq[2];
-    const double n = sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3]);
+    const double ninv = 1.0 / sqrt(r[0] * r[0] + r[1] * r[1] + r[2] * r[2] + r[3] * r[3]);
 #pragma unroll
-    for (int i = 0; i < 4; i++) p.q[i] = r[i] / n;
+    for (int i = 0; i < 4; i++) p.q[i] = r[i] * ninv;
 }
 
 // inverse transform of a point: R^T (p - t)
