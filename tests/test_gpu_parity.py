@@ -386,3 +386,51 @@ def test_frontend_graph_matches_composition(pkg, orc, synth, pair_cache, mode):
     rmse, T, status, lv = _oracle_align(orc, pair, _pyrs(orc, pair), getattr(orc, mode), max_iter=30)
     assert synth.rotation_angle(out["align"]["T_cur"], T) < ROT_TOL
     assert np.abs(out["align"]["T_cur"][4:] - T[4:]).max() < TRANS_TOL
+
+
+def test_prefetch_matches_upload_and_orders_readers(pkg, orc, synth, pair_cache):
+    """svo_frames_prefetch (ingest streams, whole-batch staging) builds the same pyramids as svo_frames_upload, from
+    page-locked and from pageable memory, and every later reader of the slots is ordered after it."""
+    pair = pair_cache(7, 200)
+    h, w = pair["h"], pair["w"]
+    rng = np.random.default_rng(3)
+    many = rng.integers(0, 256, (70, h, w), dtype=np.uint8)   # more than one 64-frame chunk
+    many[0], many[1] = pair["ref"], pair["cur"]
+    with _ctx(pkg, pair, max_frames=160, max_features=256) as ctx:
+        pin = ctx.pinned(many.nbytes)
+        pa = pin.array.reshape(many.shape)
+        pa[:] = many
+        ctx.upload(0, many)                      # reference result in slots 0..69
+        ctx.prefetch(80, pa)                     # page-locked source: whole-batch DMA path
+        job = _job(pkg, pair, 80, 80, 81)
+        res_p, _ = ctx.sparse_align(job, pair["feats"], mode=pkg.capi.LM_FAITHFUL)   # must wait for the ingest
+        res_u, _ = ctx.sparse_align(_job(pkg, pair, 0, 0, 1), pair["feats"], mode=pkg.capi.LM_FAITHFUL)
+        assert np.array_equal(res_p["T_cur"], res_u["T_cur"])
+        for s in (0, 1, 63, 64, 69):
+            for lvl, which in ((0, 1), (1, 0), (3, 1)):
+                assert np.array_equal(ctx.download(80 + s, lvl, which), ctx.download(s, lvl, which)), (s, lvl, which)
+        ctx.prefetch(80, many[:3])               # pageable source: staged ring path, twice in a row into the same slots
+        ctx.prefetch(80, pa[3:6])
+        assert np.array_equal(ctx.download(80, 2, 0), ctx.download(3, 2, 0))
+        assert np.array_equal(ctx.download(82, 2, 1), ctx.download(5, 2, 1))
+        pin.free()
+
+
+def test_frontend_argument_errors(pkg, pair_cache):
+    pair = pair_cache(6, 500)
+    capi = pkg.capi
+    with _ctx(pkg, pair, max_features=512, max_fa_items=256) as ctx:
+        ctx.upload(0, pair["ref"])
+        job = _job(pkg, pair, 0, 0, 1)
+        with pytest.raises(pkg.SvoError):   # feature alignment capacity below max_features
+            ctx.frontend_run(pair["cur"], job, pair["feats"], 0, 0, 1, max_features=512)
+        with pytest.raises(pkg.SvoError):   # patch size outside the captured fast path
+            ctx.frontend_run(pair["cur"], job, pair["feats"][:200], 0, 0, 1, max_features=256, patch_size=7)
+        with pytest.raises(pkg.SvoError):   # more features than the graph's capacity
+            ctx.frontend_run(pair["cur"], job, pair["feats"], 0, 0, 1, max_features=256)
+        with pytest.raises(pkg.SvoError):   # bad slot
+            ctx.frontend_run(pair["cur"], job, pair["feats"][:200], 0, 0, 77, max_features=256)
+        j2 = job.copy()
+        j2[0]["n_ref"] = 200
+        out, sel, ref = ctx.frontend_run(pair["cur"], j2, pair["feats"][:200], 0, 0, 1, max_features=256)
+        assert out["align"]["status"] == capi.ST_SUCCESS and len(ref) == 200
