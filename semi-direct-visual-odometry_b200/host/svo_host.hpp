@@ -457,4 +457,108 @@ private:
     int32_t m_level;
 };
 
+// ------------------------------------------------------------------------------------------------------------
+// The hot section of System::processNewFrame as ONE CUDA graph launch (svo_frontend_run): the new frame's pyramids
+// (Frame::Frame, src/system.cpp:36), gradientMagnitudeByValue on it (src/system.cpp:252-253), ImageAlignment::align
+// (src/system.cpp:313) and, with the aligned pose, the projection + FeatureAlignment::align of every tracked point
+// (Map::addCandidateToFrame, src/map.cpp:595-610).  The reference makes these calls one after the other, each with its
+// own host round trip; results are written where the reference's calls would put them.
+class FrontEnd final
+{
+public:
+    FrontEnd(uint32_t patchSize, int32_t minLevel, int32_t maxLevel, int32_t cellSize, uint32_t gradientThreshold,
+             uint32_t featurePatchSize = 7, int32_t maxFeatures = 2048)
+        : m_patchSize(patchSize), m_minLevel(minLevel), m_maxLevel(maxLevel), m_cellSize(cellSize), m_threshold(gradientThreshold),
+          m_featurePatchSize(featurePatchSize), m_maxFeatures(maxFeatures)
+    {
+    }
+    FrontEnd(const FrontEnd&)            = delete;
+    FrontEnd& operator=(const FrontEnd&) = delete;
+
+    struct NewFeature {  // what the loop of src/feature_selection.cpp:135-141 turns into a Feature
+        Vec2 pixelPosition;
+        double gradientMagnitude;
+    };
+    struct Result {
+        double alignError   = 0;  // return value of ImageAlignment::align
+        int32_t alignStatus = SVO_ST_SUCCESS;
+        std::vector<NewFeature> newFeatures;  // cell raster order
+        // one entry per tracked feature (refFrame's, then its last keyframe's)
+        std::vector<bool> matched;            // had a point, reprojected into the frame and was aligned
+        std::vector<Vec2> pixelPosition;      // FeatureAlignment::align's in/out pixelPos
+        std::vector<double> matchError;       // its return value (the caller tests `< 50.0`, src/map.cpp:609)
+    };
+
+    // curFrame->m_absPose holds the prior on entry (src/system.cpp:309) and the aligned pose on return.  The graph
+    // rebuilds curFrame's pyramid from its base image in the slot the Frame already owns.
+    Result run(std::shared_ptr<Frame>& refFrame, std::shared_ptr<Frame>& curFrame, const std::vector<bool>* occupancy = nullptr)
+    {
+        const auto& lastKF = refFrame->m_lastKeyframe;
+        if (!lastKF) throw std::invalid_argument("FrontEnd::run: refFrame->m_lastKeyframe is null");
+        const auto& dev = curFrame->m_imagePyramid.device();
+        std::vector<svo_align_feature> feats;
+        auto pack = [&feats](const std::vector<std::shared_ptr<Feature>>& features) {
+            for (const auto& f : features) {
+                svo_align_feature a{};
+                a.px[0] = f->m_pixelPosition.x();
+                a.px[1] = f->m_pixelPosition.y();
+                for (int i = 0; i < 3; i++) a.bearing[i] = f->m_bearingVec[i];
+                a.has_point = f->m_point != nullptr;
+                if (f->m_point)
+                    for (int i = 0; i < 3; i++) a.point[i] = f->m_point->m_position[i];
+                feats.push_back(a);
+            }
+        };
+        pack(refFrame->m_features);
+        pack(lastKF->m_features);
+        svo_align_job job{};
+        job.n_ref = (int32_t)refFrame->numberObservation();
+        job.n_kf  = (int32_t)lastKF->numberObservation();
+        refFrame->m_absPose.params(job.T_ref);
+        lastKF->m_absPose.params(job.T_kf);
+        curFrame->m_absPose.params(job.T_cur);
+        svo_frontend_params prm{};
+        prm.ref_slot     = refFrame->m_imagePyramid.slot();
+        prm.kf_slot      = lastKF->m_imagePyramid.slot();
+        prm.cur_slot     = curFrame->m_imagePyramid.slot();
+        prm.cell         = m_cellSize;
+        prm.thr          = m_threshold;
+        prm.max_features = m_maxFeatures;
+        prm.align        = svo_align_params{(int32_t)m_patchSize, m_minLevel, m_maxLevel, m_mode, (int32_t)m_maxIteration, 0};
+        prm.fa           = svo_fa_params{(int32_t)m_featurePatchSize, m_featureMode, (int32_t)m_maxIteration, 0};
+        const Mat8& img  = curFrame->m_imagePyramid.getBaseImage();
+        const int rows = img.rows / m_cellSize + 1, cols = img.cols / m_cellSize + 1;
+        std::vector<uint8_t> occ;
+        if (occupancy) occ.assign(occupancy->begin(), occupancy->end());
+        std::vector<svo_feature_px> sel((size_t)rows * cols);
+        std::vector<svo_fa_result> refined(feats.size() ? feats.size() : 1);
+        svo_frontend_result out{};
+        dev->check(svo_frontend_run(dev->ctx(), &prm, img.ptr(), img.cols, &job, feats.data(), (int)feats.size(),
+                                    occupancy ? occ.data() : nullptr, &out, sel.data(), (int)sel.size(), refined.data()),
+                   "svo_frontend_run");
+        Result r;
+        r.alignError        = out.align.rmse;
+        r.alignStatus       = out.align.status;
+        curFrame->m_absPose = SE3::fromParams(out.align.T_cur);
+        for (int i = 0; i < out.n_selected; i++)
+            r.newFeatures.push_back({Vec2((double)sel[i].x, (double)sel[i].y), (double)sel[i].magnitude});
+        for (size_t i = 0; i < feats.size(); i++) {
+            r.matched.push_back(!(refined[i].status == SVO_ST_FAILED && refined[i].iterations == 0));
+            r.pixelPosition.push_back(Vec2(refined[i].px[0], refined[i].px[1]));
+            r.matchError.push_back(refined[i].rmse);
+        }
+        return r;
+    }
+
+    int32_t m_mode          = SVO_LM_FAITHFUL;
+    int32_t m_featureMode   = SVO_LM_FAITHFUL;
+    uint32_t m_maxIteration = 20;
+
+private:
+    uint32_t m_patchSize;
+    int32_t m_minLevel, m_maxLevel, m_cellSize;
+    uint32_t m_threshold, m_featurePatchSize;
+    int32_t m_maxFeatures;
+};
+
 }  // namespace svo

@@ -195,6 +195,57 @@ int main(int argc, char** argv)
             }
         }
     }
+    // ---- FrontEnd: the same stages as ONE graph launch == the calls above made one by one ----
+    {
+        ImageAlignment aligner(5, 0, 3, 6);
+        cur->m_absPose   = ref->m_absPose;
+        const double err = aligner.align(ref, cur);
+        double want[7];
+        cur->m_absPose.params(want);
+        auto probe = std::make_shared<Frame>(camera, curImg, 4, 9, kf);
+        FeatureSelection sel2(w, h, 30);
+        sel2.gradientMagnitudeByValue(probe, 50, true);
+        FeatureAlignment fa(7, 0, 3);
+        std::vector<FeatureAlignment::Item> items;
+        std::vector<size_t> which;
+        for (size_t i = 0; i < ref->m_features.size(); i++) {
+            const auto& f = ref->m_features[i];
+            if (!f->m_point) continue;
+            const Vec3 pc = cur->m_absPose * f->m_point->m_position;
+            const Vec2 px = camera->project2d(pc);
+            if (pc.z() > 0 && camera->isInFrame(px, 3.0)) {
+                items.push_back({f, cur, px});
+                which.push_back(i);
+            }
+        }
+        std::vector<Vec2> px;
+        std::vector<double> e;
+        fa.alignBatch(items, px, e);
+
+        auto cur2       = std::make_shared<Frame>(camera, curImg, 4, 10, kf);
+        cur2->m_absPose = ref->m_absPose;
+        FrontEnd fe(5, 0, 3, 30, 50, 7, 2048);
+        const FrontEnd::Result r = fe.run(ref, cur2);
+        double got[7];
+        cur2->m_absPose.params(got);
+        for (int i = 0; i < 7; i++) CHECK(got[i] == want[i]);
+        CHECK(r.alignError == err);
+        CHECK(r.newFeatures.size() == probe->numberObservation());
+        for (size_t i = 0; i < r.newFeatures.size() && i < probe->numberObservation(); i++)
+            CHECK(r.newFeatures[i].pixelPosition.x() == probe->m_features[i]->m_pixelPosition.x() &&
+                  r.newFeatures[i].pixelPosition.y() == probe->m_features[i]->m_pixelPosition.y());
+        size_t nMatched = 0;
+        for (bool b : r.matched) nMatched += b;
+        CHECK(nMatched == items.size());
+        for (size_t k = 0; k < which.size(); k++) {
+            const size_t i = which[k];
+            CHECK(r.matched[i]);
+            CHECK(std::fabs(r.pixelPosition[i].x() - px[k].x()) < 1e-6 && std::fabs(r.pixelPosition[i].y() - px[k].y()) < 1e-6);
+            CHECK((std::isnan(r.matchError[i]) && std::isnan(e[k])) || std::fabs(r.matchError[i] - e[k]) < 1e-6 * (1.0 + std::fabs(e[k])));
+        }
+        std::printf("FrontEnd: %zu new features, %zu of %zu tracked features matched, rmse %.6f\n", r.newFeatures.size(), nMatched,
+                    r.matched.size(), r.alignError);
+    }
     Device::current().reset();
     std::printf(g_fail ? "FAILED (%d checks)\n" : "ALL HOST-CLASS CHECKS PASSED\n", g_fail);
     return g_fail ? 1 : 0;
