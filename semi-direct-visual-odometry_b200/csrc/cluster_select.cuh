@@ -643,7 +643,7 @@ __device__ __forceinline__ bool cs_tiered_select(const uint32_t (&key)[AREA], bo
     }
     // next bracket: centred on this result, half-width >= 4x the last movement, at most +/- 2^15 keys (1/2 intensity
     // unit; wider brackets pay ~2 cycles per key inside them).  The evaluation after the first one of a level follows
-    // the largest step of the level: no bracket then, the movement it shows sizes the next one.
+    // the largest step of the level and nothing is known about the movement yet: the widest bracket.
     if (br.have) {
         const uint32_t moved = kOut > br.center ? kOut - br.center : br.center - kOut;
         const uint32_t want  = 4u * min(moved, 1u << 20) + 64u;
@@ -652,7 +652,8 @@ __device__ __forceinline__ bool cs_tiered_select(const uint32_t (&key)[AREA], bo
         br.valid = sh <= 7;
         br.shift = min(sh, 7);
     } else {
-        br.valid = false;
+        br.valid = true;
+        br.shift = 7;
     }
     br.have   = true;
     br.center = kOut;

@@ -288,6 +288,7 @@ __global__ void __launch_bounds__(NT, V3Occ<NT>::MINB) k_align_cluster(const V3A
     const double fx0 = a.K[0], fy0 = a.K[1], cx0 = a.K[2], cy0 = a.K[3];
     const int border = P / 2 + 2;
     uint32_t tierCount = 0;  // diagnostics: hot | cold << 8 | generic << 16 selections
+    Bracket brMed{0u, 7, false, false}, brMad{0u, 7, false, false};
 
 #pragma unroll 1
     for (int level = a.prm.max_level, si = 0; level >= a.prm.min_level; level--, si++) {
@@ -335,7 +336,17 @@ __global__ void __launch_bounds__(NT, V3Occ<NT>::MINB) k_align_cluster(const V3A
         uint32_t winLo[G::FW], winHi[G::FW];
         int wx = 0, wy = 0;
         bool winValid = false;
-        Bracket brMed{0u, 4, false, false}, brMad{0u, 4, false, false};  // selection brackets carried between evaluations
+        // selection brackets carried between evaluations; a new level starts from the previous level's last result
+        // with the widest bracket (the residual distribution of the finer level is a refinement of the coarser one)
+        if (si == 0) {
+            brMed = Bracket{0u, 7, false, false};
+            brMad = Bracket{0u, 7, false, false};
+        } else {
+            brMed.valid = brMed.have;
+            brMad.valid = brMad.have;
+            brMed.shift = brMad.shift = 7;
+            brMed.have = brMad.have = false;
+        }
 
         // ================= evaluate (computeResiduals + tukeyWeighting + normal equations) =================
 #ifdef SVO_PROFILE
