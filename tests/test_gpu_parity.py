@@ -434,3 +434,33 @@ def test_frontend_argument_errors(pkg, pair_cache):
         j2[0]["n_ref"] = 200
         out, sel, ref = ctx.frontend_run(pair["cur"], j2, pair["feats"][:200], 0, 0, 1, max_features=256)
         assert out["align"]["status"] == capi.ST_SUCCESS and len(ref) == 200
+
+
+@pytest.mark.parametrize("shape", ["fast", "cluster4", "cluster8"])
+def test_sparse_align_repeatable_bitwise(pkg, synth, monkeypatch, shape):
+    """A data race in the selection rounds or the cluster exchange shows up as run-to-run differences: 48 pairs x 3
+    launches must agree bit for bit (per launch shape), in GN mode where every evaluation feeds the next."""
+    for k in ("SVO_ALIGN_GENERIC", "SVO_ALIGN_NT", "SVO_ALIGN_C"):
+        monkeypatch.delenv(k, raising=False)
+    if shape == "cluster4":
+        monkeypatch.setenv("SVO_ALIGN_NT", "128")
+    elif shape == "cluster8":
+        monkeypatch.setenv("SVO_ALIGN_NT", "64")
+    n = 48
+    batch = synth.make_batch(n, 500)
+    capi = pkg.capi
+    with pkg.Context(batch["w"], batch["h"], batch["K"], levels=4, max_frames=2 * n, max_jobs=n, max_features=512,
+                     max_fa_items=16) as ctx:
+        ctx.upload(0, batch["ref"])
+        ctx.upload(n, batch["cur"])
+        jobs = capi.make_jobs(n)
+        ident = np.array([0, 0, 0, 1, 0, 0, 0], dtype=np.float64)
+        jobs["ref_slot"], jobs["kf_slot"], jobs["cur_slot"] = np.arange(n), np.arange(n), np.arange(n) + n
+        jobs["n_ref"], jobs["n_kf"], jobs["feat_offset"] = batch["n_feat"], 0, batch["feat_offset"]
+        jobs["T_ref"], jobs["T_kf"], jobs["T_cur"] = ident, ident, ident
+        runs = [ctx.sparse_align(jobs, batch["feats"], mode=capi.GN, max_iter=30, want_stats=False)[0] for _ in range(3)]
+    for r in runs[1:]:
+        assert np.array_equal(r["T_cur"], runs[0]["T_cur"])
+        assert np.array_equal(r["evaluations"], runs[0]["evaluations"]) and np.array_equal(r["rmse"], runs[0]["rmse"])
+    rot = np.array([synth.rotation_angle(runs[0][i]["T_cur"], batch["T_true"][i]) for i in range(n)])
+    assert np.median(rot) < 1e-4 and (rot < 1e-3).all()
