@@ -9,6 +9,7 @@
             one step (what the reference executes) and <= 30 iterations
   config 2  the whole per-frame front end as one CUDA graph launch (svo_frontend_run)
   config 3  1,024 pairs x 1,000 features (bench.py --features 1000)
+  config 5  (the first "next" component) depth-filter epipolar search: 2,000 seeds, 7x7 patches
 
 Prints one JSON line per measurement; every line carries `roofline` (algorithmic bytes of SURVEY 8d / device time
 against the measured HBM peak) and `cpu_baseline` (the oracle port, bounded sample).  Needs a GPU.
@@ -64,7 +65,7 @@ def wall_time(fn, reps):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="0,1,2,3")
+    ap.add_argument("--configs", default="0,1,2,3,5")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     want = set(int(x) for x in a.configs.split(","))
@@ -240,6 +241,48 @@ def main():
                       "roofline": roof(bytes_, us),
                       "cpu_baseline": {"value": cpu_us, "unit": "us", "cores": 1, "kind": "port",
                                        "sample": "the same frame through the oracle stages (pyramid, grid argmax, alignment, %d feature alignments), once" % n}})
+        # ---------------- "next" row f3: epipolar search of the depth filter ----------------
+        if 5 in want:
+            wide = synth.make_pair(8, 500, motion_scale=3.0)   # a longer baseline: segments of tens of pixels
+            ctx.upload(2, np.stack([wide["ref"], wide["cur"]]))
+            rng = np.random.default_rng(5)
+            ns = 2000
+            idx = np.arange(ns) % len(wide["feats"])
+            f = wide["feats"][idx]
+            d_true = np.linalg.norm(f["point"], axis=1)
+            items = np.zeros(ns, capi.EPI_ITEM_DTYPE)
+            items["ref_slot"], items["cur_slot"] = 2, 3
+            items["T_rel"] = synth.se3_mul(wide["T_cur_true"], synth.se3_inv(wide["T_ref"]))
+            items["px"], items["bearing"] = f["px"], f["bearing"]
+            items["depth"] = d_true * rng.uniform(0.8, 1.25, ns)
+            items["min_depth"], items["max_depth"] = d_true * 0.5, d_true * 2.0
+            r = ctx.epipolar_match(items)
+            for _ in range(3):
+                ctx.epipolar_match(items)
+            e2e_us = wall_time(lambda: ctx.epipolar_match(items), 20)
+            steps = r["steps"].astype(np.float64)
+            bytes_ = float((49 * 4 + steps * 49 * 4 + 128 + 40).sum())  # 4 taps per patch pixel and step, item in, result out
+            nsamp = 300
+            t0 = time.perf_counter()
+            agree = 0
+            for i in range(nsamp):
+                it = items[i]
+                o = orc.epipolar_match(wide["ref"], wide["cur"], K, it["T_rel"], it["px"], it["bearing"], it["depth"], it["min_depth"],
+                                       it["max_depth"])
+                agree += int(o["found"] == bool(r[i]["found"]) and (not o["found"] or abs(o["depth"] - r[i]["depth"]) <= 1e-9 * o["depth"]))
+            cpu_us = (time.perf_counter() - t0) * 1e6 / nsamp * ns
+            ok = r["found"] == 1
+            emit({"config": {"workload": "next row f3: depth-filter epipolar search (algorithm::matchEpipolarConstraint), %d seeds, 7x7 "
+                                         "patches, depth interval [0.5, 2] x true depth, %.1f one-pixel steps per seed" % (ns, steps.mean())},
+                  "metric": "us_per_batch_epipolar_match", "unit": "us", "higher_is_better": False, "value": e2e_us, "dtype": "f64 geometry, "
+                  "float bilinear taps, uint8 patches", "seeds_per_sec": ns / (e2e_us * 1e-6), "found_fraction": float(ok.mean()),
+                  "median_rel_depth_error": float(np.median(np.abs(r["depth"][ok] - d_true[ok]) / d_true[ok])),
+                  "oracle_agreement_sample": "%d of %d" % (agree, nsamp),
+                  "e2e": {"value": e2e_us, "unit": "us", "h2d_bytes_per_step": int(items.nbytes), "d2h_bytes_per_step": int(r.nbytes),
+                          "what": "svo_epipolar_match (seeds H2D, one kernel, results D2H), host wall clock, median of 20"},
+                  "roofline": roof(bytes_, e2e_us),
+                  "cpu_baseline": {"value": cpu_us, "unit": "us", "cores": 1, "kind": "port",
+                                   "sample": "first %d of the %d seeds through the oracle port, scaled to the batch" % (nsamp, ns)}})
         pin.free()
         ctx.close()
 

@@ -232,6 +232,39 @@ svo_status svo_feature_align_d2h(svo_ctx* ctx);
 svo_status svo_feature_align_fetch(svo_ctx* ctx, svo_fa_result* results);
 
 /* ---------------------------------------------------------------------------------------------
+ * algorithm::matchEpipolarConstraint(refFrame, curFrame, refFeature, patchSize, initialDepth, minDepth, maxDepth,
+ * estimatedDepth) (src/algorithm.cpp:412-551), batched: one item per depth-filter seed and frame, as
+ * DepthEstimator::updateFilters calls it serially (src/depth_estimator.cpp:245).  Runs on IMAGE level 0.
+ * the first component next to the alignment path, same parity bar.
+ * ------------------------------------------------------------------------------------------- */
+enum { SVO_MEAN_EIGEN_U8 = 0, /* what computeScore executes: Eigen's mean() of a Matrix<uint8_t> sums and divides in
+                                 uint8 arithmetic, (sum mod 256) / area (src/algorithm.cpp:400-401) */
+       SVO_MEAN_EXACT = 1 };  /* the arithmetic mean the code evidently meant */
+typedef struct {
+    int32_t ref_slot;   /* depthFilter.m_feature->m_frame->m_imagePyramid */
+    int32_t cur_slot;   /* frame->m_imagePyramid */
+    double T_rel[7];    /* algorithm::computeRelativePose(ref, cur) = T_cur * T_ref^-1 (src/algorithm.cpp:705-709) */
+    double px[2];       /* refFeature->m_pixelPosition */
+    double bearing[3];  /* refFeature->m_bearingVec */
+    double depth;       /* initialDepth = 1 / mu */
+    double min_depth;   /* 1 / (mu + var) */
+    double max_depth;   /* 1 / max(mu - var, 1e-7) */
+} svo_epi_item;
+typedef struct {
+    int32_t patch_size; /* 7; odd */
+    int32_t mean_mode;  /* SVO_MEAN_EIGEN_U8 (reference behaviour) | SVO_MEAN_EXACT */
+} svo_epi_params;
+typedef struct {
+    double depth;   /* estimatedDepth, valid when found */
+    double px[2];   /* best location on the epipolar segment (its midpoint when the segment is shorter than 2 px) */
+    double score;   /* minimum score over the steps (DBL_MAX when none was scored) */
+    int32_t found;  /* the function's return value */
+    int32_t steps;  /* 1-pixel steps walked (0: short-segment branch) */
+} svo_epi_result;
+svo_status svo_epipolar_match(svo_ctx* ctx, const svo_epi_item* items, int n, const svo_epi_params* params,
+                              svo_epi_result* results);
+
+/* ---------------------------------------------------------------------------------------------
  * The per-frame front end as ONE CUDA graph launch: what System::processNewFrame runs for a new camera image between
  * Frame::Frame (src/system.cpp:36, src/frame.cpp:26) and the candidate matching of Map::reprojectMap /
  * addCandidateToFrame (src/system.cpp:313-330, src/map.cpp:595-627):

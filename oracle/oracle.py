@@ -50,6 +50,18 @@ class FaParams(C.Structure):
     _fields_ = [("patch_size", C.c_int32), ("mode", C.c_int32), ("max_iter", C.c_int32), ("median_mode", C.c_int32)]
 
 
+class EpiParams(C.Structure):
+    _fields_ = [("patch_size", C.c_int32), ("mean_mode", C.c_int32)]
+
+
+class EpiResult(C.Structure):
+    _fields_ = [("depth", C.c_double), ("px", C.c_double * 2), ("score", C.c_double), ("found", C.c_int32),
+                ("steps", C.c_int32)]
+
+
+MEAN_EIGEN_U8, MEAN_EXACT = 0, 1
+
+
 def build(force=False):
     """Compile the oracle with the committed Makefile (g++ only)."""
     src = os.path.join(_HERE, "svo_oracle.cpp")
@@ -103,6 +115,9 @@ def lib():
     L.orc_feature_align.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.POINTER(FaParams), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]
     L.orc_feature_align.restype = C.c_double
+    L.orc_epipolar_match.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                     C.c_double, C.c_double, C.c_double, C.POINTER(EpiParams), C.POINTER(EpiResult)]
+    L.orc_epipolar_match.restype = None
     L.orc_hardware_threads.restype = C.c_int
     _lib = L
     return L
@@ -312,6 +327,19 @@ def feature_align(ref_grad, cur_grad, ref_px, px_start, A=None, patch_size=7, mo
     rmse = lib().orc_feature_align(_p(ref_grad), _p(cur_grad), w, h, _p(rp), _p(Aa) if Aa is not None else None, _p(px),
                                    C.byref(prm), C.byref(st), C.byref(it))
     return rmse, px, st.value, it.value
+
+
+def epipolar_match(ref_img, cur_img, K, T_rel, ref_px, ref_bearing, depth, min_depth, max_depth, patch_size=7,
+                   mean_mode=MEAN_EIGEN_U8):
+    """algorithm::matchEpipolarConstraint for one seed.  Returns dict(found, depth, px, score, steps)."""
+    ref_img, cur_img = _c8(ref_img), _c8(cur_img)
+    h, w = ref_img.shape
+    Kk, Tr, rp, rb = _f8(K, 4), _f8(T_rel, 7), _f8(ref_px, 2), _f8(ref_bearing, 3)
+    prm = EpiParams(patch_size, mean_mode)
+    out = EpiResult()
+    lib().orc_epipolar_match(_p(ref_img), _p(cur_img), w, h, _p(Kk), _p(Tr), _p(rp), _p(rb), float(depth), float(min_depth),
+                             float(max_depth), C.byref(prm), C.byref(out))
+    return dict(found=bool(out.found), depth=out.depth, px=np.array([out.px[0], out.px[1]]), score=out.score, steps=out.steps)
 
 
 def hardware_threads():

@@ -977,6 +977,166 @@ double orc_feature_align(const uint8_t* refGrad, const uint8_t* curGrad, int w, 
     return out.second;
 }
 
+// ------------------------------------------------------------------------------------------------
+// epipolar search, src/algorithm.cpp:335-551, :682-703
+// ------------------------------------------------------------------------------------------------
+namespace {
+struct Cam {
+    double fx, fy, cx, cy;
+    int w, h;
+    void project(const double p[3], double uv[2]) const  // PinholeCamera::project2d, src/pinhole_camera.cpp:55-56
+    {
+        uv[0] = fx * (p[0] / p[2]) + cx;
+        uv[1] = fy * (p[1] / p[2]) + cy;
+    }
+    void bearing(double x, double y, double b[3]) const  // inverseProject2d, :81-101 (normalised)
+    {
+        b[0] = (x - cx) / fx;
+        b[1] = (y - cy) / fy;
+        b[2] = 1.0;
+        const double n = std::sqrt(b[0] * b[0] + b[1] * b[1] + b[2] * b[2]);
+        for (int i = 0; i < 3; i++) b[i] /= n;
+    }
+    bool inFrame(double x, double y, double bd) const { return x >= bd && y >= bd && x < w - bd && y < h - bd; }  // :163-169
+};
+
+// curFrame->camera2image(relativePose * refFrame->image2camera(px, depth))
+void projectAtDepth(const Cam& cam, const SE3& Trel, double x, double y, double depth, double uv[2])
+{
+    double b[3], pc[3], pr[3];
+    cam.bearing(x, y, b);
+    for (int i = 0; i < 3; i++) pr[i] = b[i] * depth;
+    act(Trel, pr, pc);
+    cam.project(pc, uv);
+}
+
+// algorithm::applyAffineWarp, :369-394: leaves `data` untouched when the location is out of frame
+void applyAffineWarp(const uint8_t* img, const Cam& cam, const double loc[2], int half, const double A[4], uint8_t* data)
+{
+    const double bx = A[0] * half + A[1] * half, by = A[2] * half + A[3] * half;
+    const double maxBoundary = std::ceil(std::max(std::fabs(bx), std::fabs(by))) + 2;
+    if (!cam.inFrame(loc[0], loc[1], maxBoundary)) return;
+    int idx = 0;
+    for (int i = -half; i <= half; i++)
+        for (int j = -half; j <= half; j++) {
+            const double x = loc[0] + (A[0] * j + A[1] * i), y = loc[1] + (A[2] * j + A[3] * i);
+            data[idx++]    = (uint8_t)bilinearFloat(img, cam.w, x, y);  // float -> uint8: truncation
+        }
+}
+
+// algorithm::computeScore, :396-410 (mean-removed sum of absolute differences, despite the name)
+double computeScore(const uint8_t* ref, const uint8_t* cur, int n, int meanMode)
+{
+    double refMean, curMean;
+    if (meanMode == ORC_MEAN_EIGEN_U8) {  // Eigen: Scalar(redux(sum)) / Scalar(size()) with Scalar = uint8_t
+        uint8_t sr = 0, sc = 0;
+        for (int i = 0; i < n; i++) {
+            sr = (uint8_t)(sr + ref[i]);
+            sc = (uint8_t)(sc + cur[i]);
+        }
+        refMean = (double)(uint8_t)(sr / (uint8_t)n);
+        curMean = (double)(uint8_t)(sc / (uint8_t)n);
+    } else {
+        double sr = 0, sc = 0;
+        for (int i = 0; i < n; i++) {
+            sr += ref[i];
+            sc += cur[i];
+        }
+        refMean = sr / n;
+        curMean = sc / n;
+    }
+    double sum = 0.0;
+    for (int i = 0; i < n; i++) sum += std::fabs((ref[i] - refMean) - (cur[i] - curMean));
+    return sum;
+}
+
+// algorithm::depthFromTriangulation, :682-703
+bool depthFromTriangulation(const SE3& Trel, const double bref[3], const double bcur[3], double* depth)
+{
+    double a0[3];
+    rotate(Trel.q, bref, a0);  // R * bea_ref
+    const double a1[3] = {-bcur[0], -bcur[1], -bcur[2]};
+    const double m00 = a0[0] * a0[0] + a0[1] * a0[1] + a0[2] * a0[2];
+    const double m01 = a0[0] * a1[0] + a0[1] * a1[1] + a0[2] * a1[2];
+    const double m11 = a1[0] * a1[0] + a1[1] * a1[1] + a1[2] * a1[2];
+    const double det = m00 * m11 - m01 * m01;
+    if (det < 0.000001) return false;
+    const double r0 = a0[0] * Trel.t[0] + a0[1] * Trel.t[1] + a0[2] * Trel.t[2];  // A^T t
+    const double r1 = a1[0] * Trel.t[0] + a1[1] * Trel.t[1] + a1[2] * Trel.t[2];
+    // depths = -AtA^-1 A^T t, closed-form 2x2 inverse (Eigen's inverse() for fixed 2x2)
+    const double d0 = -((m11 * r0 - m01 * r1) / det);
+    *depth          = std::fabs(d0);
+    return true;
+}
+}  // namespace
+
+void orc_epipolar_match(const uint8_t* refImg, const uint8_t* curImg, int w, int h, const double K[4], const double Trel7[7],
+                        const double refPx[2], const double refBearing[3], double depth, double minDepth, double maxDepth,
+                        const orc_epi_params* prm, orc_epi_result* out)
+{
+    const Cam cam{K[0], K[1], K[2], K[3], w, h};
+    const SE3 Trel = fromParams(Trel7);
+    const int P = prm->patch_size, half = P / 2, area = P * P;
+    const uint32_t thresholdZSSD = (uint32_t)area * 128;  // :427
+    out->depth = 0, out->px[0] = out->px[1] = 0, out->score = DBL_MAX, out->found = 0, out->steps = 0;
+    double locMin[2], locMax[2];
+    projectAtDepth(cam, Trel, refPx[0], refPx[1], minDepth, locMin);
+    projectAtDepth(cam, Trel, refPx[0], refPx[1], maxDepth, locMax);
+    auto clampLoc = [&](double* l) {  // :435-451
+        l[0] = l[0] >= 0 ? l[0] : 0.0;
+        l[0] = l[0] < w ? l[0] : w - 1;
+        l[1] = l[1] >= 0 ? l[1] : 0.0;
+        l[1] = l[1] < h ? l[1] : h - 1;
+    };
+    clampLoc(locMin);
+    clampLoc(locMax);
+    const double epi[2] = {locMax[0] - locMin[0], locMax[1] - locMin[1]};
+    // getAffineWarp at the initial depth, :335-367 (halfPatchSize is unsigned there)
+    double A[4];
+    {
+        double c[2], du[2], dv[2];
+        projectAtDepth(cam, Trel, refPx[0], refPx[1], depth, c);
+        projectAtDepth(cam, Trel, refPx[0] + half, refPx[1], depth, du);
+        projectAtDepth(cam, Trel, refPx[0], refPx[1] + half, depth, dv);
+        A[0] = (du[0] - c[0]) / half;  // column 0 = duDiff / half
+        A[2] = (du[1] - c[1]) / half;
+        A[1] = (dv[0] - c[0]) / half;  // column 1 = dvDiff / half
+        A[3] = (dv[1] - c[1]) / half;
+    }
+    const double norm = std::sqrt(epi[0] * epi[0] + epi[1] * epi[1]);
+    std::vector<uint8_t> refPatch(area, 0), curPatch(area, 0);
+    const double I2[4] = {1, 0, 0, 1};
+    applyAffineWarp(refImg, cam, refPx, half, I2, refPatch.data());  // :464-467
+    if (norm < 2.0) {  // :469-483
+        const double c[2] = {(locMax[0] + locMin[0]) / 2.0, (locMax[1] + locMin[1]) / 2.0};
+        double bc[3];
+        cam.bearing(c[0], c[1], bc);
+        out->px[0] = c[0], out->px[1] = c[1];
+        out->found = depthFromTriangulation(Trel, refBearing, bc, &out->depth) ? 1 : 0;
+        return;
+    }
+    const uint32_t pixelStep = (uint32_t)std::ceil(norm);  // :498
+    const double step[2]     = {epi[0] / norm, epi[1] / norm};
+    double minScore = DBL_MAX, best[2] = {0, 0};
+    for (uint32_t i = 0; i < pixelStep; i++) {  // :509-523; an out-of-frame step scores the PREVIOUS patch again
+        const double loc[2] = {locMin[0] + i * step[0], locMin[1] + i * step[1]};
+        applyAffineWarp(curImg, cam, loc, half, A, curPatch.data());
+        const double z = computeScore(refPatch.data(), curPatch.data(), area, prm->mean_mode);
+        if (z < minScore) {
+            minScore = z;
+            best[0] = loc[0], best[1] = loc[1];
+        }
+    }
+    out->steps = (int32_t)pixelStep;
+    out->score = minScore;
+    out->px[0] = best[0], out->px[1] = best[1];
+    if (minScore < thresholdZSSD) {  // :526-548
+        double bc[3];
+        cam.bearing(best[0], best[1], bc);
+        out->found = depthFromTriangulation(Trel, refBearing, bc, &out->depth) ? 1 : 0;
+    }
+}
+
 int orc_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }
 
 }  // extern "C"

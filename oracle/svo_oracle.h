@@ -143,6 +143,28 @@ double orc_feature_align(const uint8_t* ref_grad, const uint8_t* cur_grad, int w
                          const double* A, double px_inout[2], const orc_fa_params* params, int32_t* status_out,
                          int32_t* iterations_out);
 
+/* ---- epipolar search of the depth filter: algorithm::matchEpipolarConstraint (src/algorithm.cpp:412-551), with
+ * getAffineWarp (:335-367), applyAffineWarp (:369-394), computeScore (:396-410) and depthFromTriangulation
+ * (:682-703).  Called per depth-filter seed from DepthEstimator::updateFilters (src/depth_estimator.cpp:245). ---- */
+enum { ORC_MEAN_EIGEN_U8 = 0, ORC_MEAN_EXACT = 1 };
+typedef struct {
+    int32_t patch_size; /* 7 (src/depth_estimator.cpp:245) */
+    int32_t mean_mode;  /* ORC_MEAN_EIGEN_U8: what computeScore executes -- Eigen's mean() on a Matrix<uint8_t> sums and
+                           divides in uint8 arithmetic ((sum mod 256) / area, an integer); ORC_MEAN_EXACT: the real mean */
+} orc_epi_params;
+typedef struct {
+    double depth;    /* estimatedDepth (valid when found) */
+    double px[2];    /* bestLocation on the epipolar line (the segment midpoint when the segment is shorter than 2 px) */
+    double score;    /* minimum score over the steps (DBL_MAX when no step was scored) */
+    int32_t found;   /* the function's return value */
+    int32_t steps;   /* pixelStep (0 for the short-segment branch) */
+} orc_epi_result;
+/* ref_img / cur_img: image level 0 (w x h, pitch w).  T_rel = computeRelativePose(ref, cur) = T_cur T_ref^-1.
+ * ref_px, ref_bearing: refFeature->m_pixelPosition / m_bearingVec. */
+void orc_epipolar_match(const uint8_t* ref_img, const uint8_t* cur_img, int w, int h, const double K[4], const double T_rel[7],
+                        const double ref_px[2], const double ref_bearing[3], double depth, double min_depth, double max_depth,
+                        const orc_epi_params* params, orc_epi_result* out);
+
 int orc_hardware_threads(void);
 
 #ifdef __cplusplus

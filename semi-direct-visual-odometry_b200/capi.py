@@ -26,6 +26,7 @@ SYMBOLS = [
     "svo_sparse_align_results_device", "svo_debug_cycles",
     "svo_feature_align", "svo_feature_align_stage", "svo_feature_align_h2d", "svo_feature_align_launch",
     "svo_feature_align_d2h", "svo_feature_align_fetch", "svo_frontend_run", "svo_frontend_image_buffer",
+    "svo_epipolar_match",
 ]
 
 
@@ -63,6 +64,16 @@ ALIGN_STATS_DTYPE = np.dtype([("H", "<f8", (6, 6)), ("g", "<f8", 6), ("dx", "<f8
                               ("status", "<i4"), ("iterations", "<i4"), ("evaluations", "<i4")])
 FA_ITEM_DTYPE = np.dtype([("ref_slot", "<i4"), ("cur_slot", "<i4"), ("ref_px", "<f8", 2), ("px", "<f8", 2),
                           ("A", "<f8", 4), ("use_affine", "<i4"), ("reserved", "<i4")])
+EPI_ITEM_DTYPE = np.dtype([("ref_slot", "<i4"), ("cur_slot", "<i4"), ("T_rel", "<f8", 7), ("px", "<f8", 2), ("bearing", "<f8", 3),
+                           ("depth", "<f8"), ("min_depth", "<f8"), ("max_depth", "<f8")])
+EPI_RESULT_DTYPE = np.dtype([("depth", "<f8"), ("px", "<f8", 2), ("score", "<f8"), ("found", "<i4"), ("steps", "<i4")])
+MEAN_EIGEN_U8, MEAN_EXACT = 0, 1
+
+
+class EpiParams(C.Structure):
+    _fields_ = [("patch_size", C.c_int32), ("mean_mode", C.c_int32)]
+
+
 FA_RESULT_DTYPE = np.dtype([("px", "<f8", 2), ("rmse", "<f8"), ("status", "<i4"), ("iterations", "<i4")])
 assert ALIGN_FEATURE_DTYPE.itemsize == 72 and ALIGN_JOB_DTYPE.itemsize == 192 and ALIGN_RESULT_DTYPE.itemsize == 80
 assert ALIGN_STATS_DTYPE.itemsize == 488 and FA_ITEM_DTYPE.itemsize == 80 and FA_RESULT_DTYPE.itemsize == 32
@@ -116,6 +127,7 @@ def load():
     L.svo_sparse_align_results_device.argtypes = [vp]
     L.svo_debug_cycles.argtypes = [vp, vp]
     L.svo_sparse_align_results_device.restype = vp
+    L.svo_epipolar_match.argtypes = [vp, vp, i, C.POINTER(EpiParams), vp]
     L.svo_frontend_run.argtypes = [vp, C.POINTER(FrontendParams), vp, i, vp, vp, i, vp, vp, vp, i, vp]
     L.svo_frontend_image_buffer.argtypes = [vp]
     L.svo_frontend_image_buffer.restype = vp
@@ -304,6 +316,14 @@ class Context:
     @property
     def results_device_ptr(self):
         return self.L.svo_sparse_align_results_device(self.h)
+
+    # ---- algorithm::matchEpipolarConstraint, batched over depth-filter seeds ----
+    def epipolar_match(self, items, patch_size=7, mean_mode=MEAN_EIGEN_U8):
+        items = np.ascontiguousarray(items, dtype=EPI_ITEM_DTYPE).reshape(-1)
+        prm = EpiParams(patch_size, mean_mode)
+        res = np.zeros(items.size, EPI_RESULT_DTYPE)
+        self._check(self.L.svo_epipolar_match(self.h, _ptr(items), items.size, C.byref(prm), _ptr(res)))
+        return res
 
     # ---- the whole per-frame front end, one CUDA graph launch ----
     def frontend_run(self, img, job, feats, ref_slot, kf_slot, cur_slot, cell=30, thr=50, max_features=512, patch_size=5,

@@ -66,6 +66,10 @@ void release(svo_ctx* ctx)
     cudaFree(ctx->d_scratch_jac);
     cudaFree(ctx->d_scratch2);
     cudaFree(ctx->d_dbg);
+    cudaFreeHost(ctx->h_epi_items);
+    cudaFreeHost(ctx->h_epi_results);
+    cudaFree(ctx->d_epi_items);
+    cudaFree(ctx->d_epi_results);
     cudaFreeHost(ctx->h_fa_items);
     cudaFreeHost(ctx->h_fa_results);
     cudaFree(ctx->d_fa_items);
@@ -163,6 +167,10 @@ svo_status init(svo_ctx* ctx)
     SVO_CUDA(cudaHostAlloc(&ctx->h_fa_results, sizeof(svo_fa_result) * nf, cudaHostAllocDefault));
     SVO_CUDA(cudaMalloc(&ctx->d_fa_items, sizeof(svo_fa_item) * nf));
     SVO_CUDA(cudaMalloc(&ctx->d_fa_results, sizeof(svo_fa_result) * nf));
+    SVO_CUDA(cudaHostAlloc(&ctx->h_epi_items, sizeof(svo_epi_item) * nf, cudaHostAllocDefault));
+    SVO_CUDA(cudaHostAlloc(&ctx->h_epi_results, sizeof(svo_epi_result) * nf, cudaHostAllocDefault));
+    SVO_CUDA(cudaMalloc(&ctx->d_epi_items, sizeof(svo_epi_item) * nf));
+    SVO_CUDA(cudaMalloc(&ctx->d_epi_results, sizeof(svo_epi_result) * nf));
     SVO_CUDA(cudaStreamSynchronize(ctx->stream));
     return SVO_OK;
 }
@@ -656,6 +664,34 @@ svo_status svo_feature_align(svo_ctx* ctx, const svo_fa_item* items, int n, cons
     if ((st = svo_feature_align_launch(ctx)) != SVO_OK) return st;
     if ((st = svo_feature_align_d2h(ctx)) != SVO_OK) return st;
     return svo_feature_align_fetch(ctx, results);
+}
+
+// ------------------------------------------------------------------------------------------------
+// epipolar search (depth filter)
+// ------------------------------------------------------------------------------------------------
+svo_status svo_epipolar_match(svo_ctx* ctx, const svo_epi_item* items, int n, const svo_epi_params* prm, svo_epi_result* results)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    if (n < 0 || !prm || (n > 0 && (!items || !results))) SVO_FAIL(SVO_ERR_INVALID, "svo_epipolar_match: null argument");
+    if (n > ctx->cfg.max_fa_items) SVO_FAIL(SVO_ERR_CAPACITY, "svo_epipolar_match: more seeds than max_fa_items");
+    if (prm->patch_size < 1 || prm->patch_size > 8 || !(prm->patch_size & 1) || prm->mean_mode < SVO_MEAN_EIGEN_U8 ||
+        prm->mean_mode > SVO_MEAN_EXACT)
+        SVO_FAIL(SVO_ERR_INVALID, "svo_epipolar_match: patch_size must be odd, 1..7; mean_mode valid");
+    for (int i = 0; i < n; i++)
+        if (bad_slot(ctx, items[i].ref_slot) || bad_slot(ctx, items[i].cur_slot))
+            SVO_FAIL(SVO_ERR_INVALID, "svo_epipolar_match: frame slot out of range");
+    if (n == 0) return SVO_OK;
+    SVO_CUDA(cudaSetDevice(ctx->cfg.device));
+    SVO_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(ctx->h_epi_items, items, sizeof(svo_epi_item) * n);
+    svo_status st = wait_ingest(ctx);
+    if (st != SVO_OK) return st;
+    SVO_CUDA(cudaMemcpyAsync(ctx->d_epi_items, ctx->h_epi_items, sizeof(svo_epi_item) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if ((st = launch_epipolar_match(ctx, n, *prm)) != SVO_OK) return st;
+    SVO_CUDA(cudaMemcpyAsync(ctx->h_epi_results, ctx->d_epi_results, sizeof(svo_epi_result) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    SVO_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(results, ctx->h_epi_results, sizeof(svo_epi_result) * n);
+    return SVO_OK;
 }
 
 }  // extern "C"

@@ -110,6 +110,12 @@ struct svo_ctx {
     svo_align_result* h_fe_align;  // pinned
     svo_fa_result* h_fe_fa;        // pinned, max_features records
 
+    // epipolar search batch (depth-filter seeds), capacity max_fa_items
+    svo_epi_item* h_epi_items;      // pinned
+    svo_epi_result* h_epi_results;  // pinned
+    svo_epi_item* d_epi_items;
+    svo_epi_result* d_epi_results;
+
     // feature alignment batch
     svo_fa_item* h_fa_items;     // pinned
     svo_fa_result* h_fa_results; // pinned
@@ -155,6 +161,7 @@ svo_status launch_repack(svo_ctx* ctx, const uint8_t* dsrc, long long src_pitch,
 svo_status launch_grid_select(svo_ctx* ctx, int slot, int cell, uint32_t thr, int rows, int cols);
 svo_status launch_sparse_align(svo_ctx* ctx);
 svo_status launch_feature_align(svo_ctx* ctx);
+svo_status launch_epipolar_match(svo_ctx* ctx, int n, const svo_epi_params& prm);
 void frontend_release(svo_ctx* ctx);
 size_t sparse_align_smem_bytes(int nthreads, int max_features, int patch_area);
 bool sparse_align_v3_supported(const svo_ctx* ctx, int maxF);

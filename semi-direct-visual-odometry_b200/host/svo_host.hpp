@@ -561,4 +561,61 @@ private:
     int32_t m_maxFeatures;
 };
 
+// ------------------------------------------------------------------------------------------------------------
+// algorithm::matchEpipolarConstraint (src/algorithm.cpp:412-551), the depth filter's epipolar search
+// (DepthEstimator::updateFilters, src/depth_estimator.cpp:245): same signature for one seed, plus the batched form
+// that replaces the serial loop over the depth filters of a frame.
+namespace algorithm
+{
+struct EpipolarSeed {
+    std::shared_ptr<Feature> refFeature;  // depthFilter.m_feature (its frame is the reference frame)
+    double initialDepth, minDepth, maxDepth;
+};
+
+inline void matchEpipolarConstraintBatch(const std::shared_ptr<Frame>& curFrame, const std::vector<EpipolarSeed>& seeds,
+                                         uint32_t patchSize, std::vector<bool>& found, std::vector<double>& estimatedDepth,
+                                         int32_t meanMode = SVO_MEAN_EIGEN_U8)
+{
+    found.assign(seeds.size(), false);
+    estimatedDepth.assign(seeds.size(), 0.0);
+    if (seeds.empty()) return;
+    const auto& dev = curFrame->m_imagePyramid.device();
+    std::vector<svo_epi_item> items(seeds.size());
+    for (size_t i = 0; i < seeds.size(); i++) {
+        const auto& f        = seeds[i].refFeature;
+        const auto& refFrame = f->m_frame;
+        svo_epi_item it{};
+        it.ref_slot = refFrame->m_imagePyramid.slot();
+        it.cur_slot = curFrame->m_imagePyramid.slot();
+        (curFrame->m_absPose * refFrame->m_absPose.inverse()).params(it.T_rel);  // computeRelativePose, :705-709
+        it.px[0] = f->m_pixelPosition.x();
+        it.px[1] = f->m_pixelPosition.y();
+        for (int k = 0; k < 3; k++) it.bearing[k] = f->m_bearingVec[k];
+        it.depth     = seeds[i].initialDepth;
+        it.min_depth = seeds[i].minDepth;
+        it.max_depth = seeds[i].maxDepth;
+        items[i]     = it;
+    }
+    svo_epi_params prm{(int32_t)patchSize, meanMode};
+    std::vector<svo_epi_result> res(seeds.size());
+    dev->check(svo_epipolar_match(dev->ctx(), items.data(), (int)items.size(), &prm, res.data()), "svo_epipolar_match");
+    for (size_t i = 0; i < seeds.size(); i++) {
+        found[i]          = res[i].found != 0;
+        estimatedDepth[i] = res[i].depth;
+    }
+}
+
+inline bool matchEpipolarConstraint(const std::shared_ptr<Frame>& refFrame, const std::shared_ptr<Frame>& curFrame,
+                                    std::shared_ptr<Feature>& refFeature, const uint32_t patchSize, const double initialDepth,
+                                    const double minDepth, const double maxDepth, double& estimatedDepth)
+{
+    if (refFeature->m_frame != refFrame) throw std::invalid_argument("matchEpipolarConstraint: refFeature does not belong to refFrame");
+    std::vector<bool> found;
+    std::vector<double> depth;
+    matchEpipolarConstraintBatch(curFrame, {EpipolarSeed{refFeature, initialDepth, minDepth, maxDepth}}, patchSize, found, depth);
+    if (found[0]) estimatedDepth = depth[0];  // the reference leaves it untouched on failure
+    return found[0];
+}
+}  // namespace algorithm
+
 }  // namespace svo

@@ -246,6 +246,41 @@ int main(int argc, char** argv)
         std::printf("FrontEnd: %zu new features, %zu of %zu tracked features matched, rmse %.6f\n", r.newFeatures.size(), nMatched,
                     r.matched.size(), r.alignError);
     }
+    // ---- algorithm::matchEpipolarConstraint (depth filter), single call and batch vs the oracle ----
+    {
+        cur->m_absPose = SE3::fromParams(&std::vector<double>{std::atof(argv[5]), std::atof(argv[6]), std::atof(argv[7]), std::atof(argv[8]),
+                                                              std::atof(argv[9]), std::atof(argv[10]), std::atof(argv[11])}[0]);
+        double Trel[7];
+        (cur->m_absPose * ref->m_absPose.inverse()).params(Trel);
+        std::vector<algorithm::EpipolarSeed> seeds;
+        for (size_t i = 0; i < ref->m_features.size() && seeds.size() < 64; i++) {
+            const auto& f = ref->m_features[i];
+            if (!f->m_point) continue;
+            const double d = (ref->m_absPose * f->m_point->m_position).norm();
+            seeds.push_back({f, d * 1.1, d * 0.6, d * 1.7});
+        }
+        std::vector<bool> found;
+        std::vector<double> depth;
+        algorithm::matchEpipolarConstraintBatch(cur, seeds, 7, found, depth);
+        size_t nFound = 0;
+        for (size_t i = 0; i < seeds.size(); i++) {
+            const auto& f = seeds[i].refFeature;
+            const double px[2] = {f->m_pixelPosition.x(), f->m_pixelPosition.y()};
+            const double b[3]  = {f->m_bearingVec[0], f->m_bearingVec[1], f->m_bearingVec[2]};
+            orc_epi_params prm{7, ORC_MEAN_EIGEN_U8};
+            orc_epi_result o{};
+            orc_epipolar_match(refImg.ptr(), curImg.ptr(), w, h, K, Trel, px, b, seeds[i].initialDepth, seeds[i].minDepth,
+                               seeds[i].maxDepth, &prm, &o);
+            CHECK(found[i] == (o.found != 0));
+            if (o.found) CHECK(std::fabs(depth[i] - o.depth) <= 1e-9 * o.depth);
+            nFound += found[i];
+        }
+        double est = -1.0;
+        auto f0    = seeds[0].refFeature;
+        const bool ok = algorithm::matchEpipolarConstraint(ref, cur, f0, 7, seeds[0].initialDepth, seeds[0].minDepth, seeds[0].maxDepth, est);
+        CHECK(ok == found[0] && (!ok || est == depth[0]));
+        std::printf("matchEpipolarConstraint: %zu of %zu seeds matched\n", nFound, seeds.size());
+    }
     Device::current().reset();
     std::printf(g_fail ? "FAILED (%d checks)\n" : "ALL HOST-CLASS CHECKS PASSED\n", g_fail);
     return g_fail ? 1 : 0;

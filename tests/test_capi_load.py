@@ -32,17 +32,20 @@ def test_struct_layouts_match_header(pkg, tmp_path):
     """sizeof/offsetof from a C compile of the header == the numpy/ctypes mirrors."""
     prog = tmp_path / "layout.c"
     prog.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "svo_b200.h"\nint main(void){'
-                    'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(svo_config), sizeof(svo_feature_px),'
+                    'printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n", sizeof(svo_config), sizeof(svo_feature_px),'
                     'sizeof(svo_align_feature), sizeof(svo_align_job), sizeof(svo_align_params), sizeof(svo_align_result),'
                     'sizeof(svo_align_level_stats), sizeof(svo_fa_item), sizeof(svo_fa_params), sizeof(svo_fa_result),'
-                    'offsetof(svo_align_level_stats, pose_after)); return 0; }\n')
+                    'offsetof(svo_align_level_stats, pose_after), sizeof(svo_frontend_params), sizeof(svo_frontend_result),'
+                    'sizeof(svo_epi_item), sizeof(svo_epi_params), sizeof(svo_epi_result), offsetof(svo_epi_item, depth)); return 0; }\n')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     c = pkg.capi
     want = [C.sizeof(c.Config), c.FEATURE_PX_DTYPE.itemsize, c.ALIGN_FEATURE_DTYPE.itemsize, c.ALIGN_JOB_DTYPE.itemsize,
             C.sizeof(c.AlignParams), c.ALIGN_RESULT_DTYPE.itemsize, c.ALIGN_STATS_DTYPE.itemsize, c.FA_ITEM_DTYPE.itemsize,
-            C.sizeof(c.FaParams), c.FA_RESULT_DTYPE.itemsize, c.ALIGN_STATS_DTYPE.fields["pose_after"][1]]
+            C.sizeof(c.FaParams), c.FA_RESULT_DTYPE.itemsize, c.ALIGN_STATS_DTYPE.fields["pose_after"][1],
+            C.sizeof(c.FrontendParams), c.FRONTEND_RESULT_DTYPE.itemsize, c.EPI_ITEM_DTYPE.itemsize, C.sizeof(c.EpiParams),
+            c.EPI_RESULT_DTYPE.itemsize, c.EPI_ITEM_DTYPE.fields["depth"][1]]
     assert got == want
 
 

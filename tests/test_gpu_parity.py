@@ -464,3 +464,60 @@ def test_sparse_align_repeatable_bitwise(pkg, synth, monkeypatch, shape):
         assert np.array_equal(r["evaluations"], runs[0]["evaluations"]) and np.array_equal(r["rmse"], runs[0]["rmse"])
     rot = np.array([synth.rotation_angle(runs[0][i]["T_cur"], batch["T_true"][i]) for i in range(n)])
     assert np.median(rot) < 1e-4 and (rot < 1e-3).all()
+
+
+# ------------------------------------------------------------------------------------------------
+# epipolar search of the depth filter: algorithm::matchEpipolarConstraint
+# ------------------------------------------------------------------------------------------------
+def _epi_items(pkg, synth, pair, rng, n, spread=(0.5, 2.0), guess=(0.8, 1.25)):
+    capi = pkg.capi
+    T_rel = synth.se3_mul(pair["T_cur_true"], synth.se3_inv(pair["T_ref"]))
+    idx = np.arange(n) % len(pair["feats"])
+    f = pair["feats"][idx]
+    Rr, tr = synth.se3_Rt(pair["T_ref"])
+    d_true = np.linalg.norm(f["point"] @ Rr.T + tr, axis=1)      # distance along the bearing in the reference camera
+    items = np.zeros(n, capi.EPI_ITEM_DTYPE)
+    items["ref_slot"], items["cur_slot"] = 0, 1
+    items["T_rel"] = T_rel
+    items["px"], items["bearing"] = f["px"], f["bearing"]
+    items["depth"] = d_true * rng.uniform(guess[0], guess[1], n)
+    items["min_depth"] = d_true * spread[0]
+    items["max_depth"] = d_true * spread[1]
+    return items, d_true
+
+
+@pytest.mark.parametrize("patch,mean_mode", [(7, "MEAN_EIGEN_U8"), (7, "MEAN_EXACT"), (5, "MEAN_EIGEN_U8")])
+def test_epipolar_match_parity(pkg, orc, synth, pair_cache, patch, mean_mode):
+    pair = pair_cache(8, 400, motion_scale=3.0)   # a longer baseline: epipolar segments of tens of pixels
+    rng = np.random.default_rng(17)
+    items, d_true = _epi_items(pkg, synth, pair, rng, 600)
+    # edge cases: a seed at the image border (reference patch stays zero), a tiny depth interval (segment < 2 px ->
+    # midpoint triangulation), an interval that leaves the image (clamped, stale-patch steps)
+    items["px"][0] = (2.0, 2.0)
+    items["min_depth"][1], items["max_depth"][1] = d_true[1] * 0.999, d_true[1] * 1.001
+    items["min_depth"][2], items["max_depth"][2] = d_true[2] * 0.02, d_true[2] * 50.0
+    items["px"][3] = (1238.0, 373.0)
+    with _ctx(pkg, pair) as ctx:
+        ctx.upload(0, np.stack([pair["ref"], pair["cur"]]))
+        got = ctx.epipolar_match(items, patch_size=patch, mean_mode=getattr(pkg.capi, mean_mode))
+    found = 0
+    for i in range(len(items)):
+        it = items[i]
+        o = orc.epipolar_match(pair["ref"], pair["cur"], pair["K"], it["T_rel"], it["px"], it["bearing"], it["depth"],
+                               it["min_depth"], it["max_depth"], patch_size=patch, mean_mode=getattr(orc, mean_mode))
+        g = got[i]
+        assert bool(g["found"]) == o["found"], i
+        assert g["steps"] == o["steps"], (i, g["steps"], o["steps"])
+        if o["steps"] > 0:
+            assert abs(g["score"] - o["score"]) <= 1e-9 * max(1.0, o["score"]), (i, g["score"], o["score"])
+        assert np.abs(g["px"] - o["px"]).max() < 1e-9, (i, g["px"], o["px"])
+        if o["found"]:
+            assert abs(g["depth"] - o["depth"]) <= 1e-9 * o["depth"], (i, g["depth"], o["depth"])
+            found += 1
+    assert got[1]["steps"] == 0 and got[1]["found"] == 1          # short segment: triangulated at the midpoint
+    assert found > 0.8 * len(items)
+    # the search recovers the depth of the rendered plane (1-pixel steps: a few per cent)
+    ok = got["found"] == 1
+    ok[:4] = False
+    rel = np.abs(got["depth"][ok] - d_true[ok]) / d_true[ok]
+    assert np.median(rel) < 0.05
