@@ -179,3 +179,126 @@ def test_align_golden(orc, pkg):
         rmse, p, st, it = orc.feature_align(gr, gc, row[0:2], row[2:4], patch_size=7, mode=orc.LM_FAITHFUL)
         assert np.allclose(p, row[4:6], atol=1e-9) and st == row[7] and it == row[8]
         assert (np.isnan(rmse) and np.isnan(row[6])) or abs(rmse - row[6]) < 1e-9
+
+
+# ------------------------------------------------------------------------------------------------
+# epipolar search of the depth filter: the restatement against independent numpy statements
+# ------------------------------------------------------------------------------------------------
+def _np_bilinear_float(img, x, y):
+    """algorithm::bilinearInterpolation (float), src/algorithm.cpp:885-894, in numpy scalars"""
+    x1, y1 = int(x), int(y)
+    a = np.float32((x1 + 1 - x) * float(img[y1, x1]) + (x - x1) * float(img[y1, x1 + 1]))
+    b = np.float32((x1 + 1 - x) * float(img[y1 + 1, x1]) + (x - x1) * float(img[y1 + 1, x1 + 1]))
+    return np.float32((y1 + 1 - y) * float(a) + (y - y1) * float(b))
+
+
+def _np_epipolar(ref, cur, K, T_rel, px, bearing, depth, dmin, dmax, P=7, eigen_mean=True):
+    """independent numpy restatement of src/algorithm.cpp:412-551 (rotation through a matrix, lstsq triangulation)"""
+    from scipy.spatial.transform import Rotation
+    h, w = ref.shape
+    R = Rotation.from_quat(T_rel[:4]).as_matrix()
+    t = np.asarray(T_rel[4:])
+    half, area = P // 2, P * P
+
+    def bear(x, y):
+        b = np.array([(x - K[2]) / K[0], (y - K[3]) / K[1], 1.0])
+        return b / np.linalg.norm(b)
+
+    def proj(x, y, d):
+        pc = R @ (bear(x, y) * d) + t
+        return np.array([K[0] * pc[0] / pc[2] + K[2], K[1] * pc[1] / pc[2] + K[3]])
+
+    def clamp(l):
+        return np.array([min(max(l[0], 0.0), w - 1) if l[0] >= w or l[0] < 0 else l[0],
+                         min(max(l[1], 0.0), h - 1) if l[1] >= h or l[1] < 0 else l[1]])
+
+    lmin, lmax = clamp(proj(px[0], px[1], dmin)), clamp(proj(px[0], px[1], dmax))
+    c = proj(px[0], px[1], depth)
+    A = np.stack([(proj(px[0] + half, px[1], depth) - c) / half, (proj(px[0], px[1] + half, depth) - c) / half], 1)
+
+    def warp(img, loc, A, data):
+        bnd = A @ np.array([half, half], dtype=np.float64)
+        mb = np.ceil(max(abs(bnd[0]), abs(bnd[1]))) + 2
+        if not (loc[0] >= mb and loc[1] >= mb and loc[0] < w - mb and loc[1] < h - mb):
+            return data
+        out = []
+        for i in range(-half, half + 1):
+            for j in range(-half, half + 1):
+                q = loc + A @ np.array([j, i], dtype=np.float64)
+                out.append(np.uint8(_np_bilinear_float(img, q[0], q[1])))
+        return np.array(out, dtype=np.uint8)
+
+    def score(r, c):
+        if eigen_mean:   # Eigen mean() on Matrix<uint8_t>: sum and division in uint8
+            rm, cm = float(np.uint8(r.sum(dtype=np.uint8) // np.uint8(area))), float(np.uint8(c.sum(dtype=np.uint8) // np.uint8(area)))
+        else:
+            rm, cm = r.astype(np.float64).mean(), c.astype(np.float64).mean()
+        return float(np.abs((r.astype(np.float64) - rm) - (c.astype(np.float64) - cm)).sum())
+
+    def tri(b_cur):
+        Am = np.stack([R @ np.asarray(bearing), -b_cur], 1)
+        if np.linalg.det(Am.T @ Am) < 1e-6:
+            return None
+        return abs(np.linalg.solve(Am.T @ Am, -(Am.T @ t))[0])
+
+    refp = warp(ref, np.asarray(px, dtype=np.float64), np.eye(2), np.zeros(area, np.uint8))
+    e = lmax - lmin
+    norm = np.linalg.norm(e)
+    if norm < 2.0:
+        mid = (lmax + lmin) / 2
+        d = tri(bear(mid[0], mid[1]))
+        return dict(found=d is not None, depth=d, px=mid, steps=0, score=None)
+    steps, step = int(np.ceil(norm)), e / norm
+    curp = np.zeros(area, np.uint8)
+    best, bl = np.inf, None
+    for i in range(steps):
+        loc = lmin + i * step
+        curp = warp(cur, loc, A, curp)
+        z = score(refp, curp)
+        if z < best:
+            best, bl = z, loc
+    d = tri(bear(bl[0], bl[1])) if best < area * 128 else None
+    return dict(found=d is not None, depth=d, px=bl, steps=steps, score=best)
+
+
+@pytest.mark.parametrize("eigen_mean", [True, False])
+def test_epipolar_match_against_numpy(orc, pkg, eigen_mean):
+    synth = pkg.synth
+    pair = synth.make_pair(8, 120, motion_scale=3.0)
+    T_rel = synth.se3_mul(pair["T_cur_true"], synth.se3_inv(pair["T_ref"]))
+    rng = np.random.default_rng(2)
+    n_found = 0
+    for i in range(0, 120, 3):
+        f = pair["feats"][i]
+        d = np.linalg.norm(f["point"])
+        lo, hi, d0 = d * rng.uniform(0.4, 0.9), d * rng.uniform(1.1, 3.0), d * rng.uniform(0.8, 1.25)
+        if i == 3:
+            lo, hi = d * 0.9995, d * 1.0005           # short segment: midpoint triangulation
+        o = orc.epipolar_match(pair["ref"], pair["cur"], pair["K"], T_rel, f["px"], f["bearing"], d0, lo, hi,
+                               mean_mode=orc.MEAN_EIGEN_U8 if eigen_mean else orc.MEAN_EXACT)
+        w = _np_epipolar(pair["ref"], pair["cur"], pair["K"], T_rel, f["px"], f["bearing"], d0, lo, hi, eigen_mean=eigen_mean)
+        assert o["found"] == w["found"] and o["steps"] == w["steps"], i
+        assert np.abs(o["px"] - w["px"]).max() < 1e-9
+        if w["score"] is not None:
+            assert abs(o["score"] - w["score"]) < 1e-6
+        if w["found"]:
+            assert abs(o["depth"] - w["depth"]) < 1e-9 * w["depth"]
+            n_found += 1
+    assert n_found > 30
+
+
+def test_epipolar_uint8_mean_quirk(orc):
+    """computeScore's means are computed in uint8 (Eigen mean() of a Matrix<uint8_t>, src/algorithm.cpp:400-401): two
+    flat patches 40 grey levels apart score 49 * |(r - rm) - (c - cm)| with rm, cm the WRAPPED means, not 0."""
+    img_r = np.full((40, 40), 100, np.uint8)
+    img_c = np.full((40, 40), 140, np.uint8)
+    K = (100.0, 100.0, 20.0, 20.0)
+    T = np.array([0, 0, 0, 1, 0.5, 0, 0], dtype=np.float64)      # pure x translation: horizontal epipolar line
+    b = np.array([0.0, 0.0, 1.0])
+    kw = dict(depth=10.0, min_depth=4.0, max_depth=40.0)
+    o_q = orc.epipolar_match(img_r, img_c, K, T, (20.0, 20.0), b, mean_mode=orc.MEAN_EIGEN_U8, **kw)
+    o_e = orc.epipolar_match(img_r, img_c, K, T, (20.0, 20.0), b, mean_mode=orc.MEAN_EXACT, **kw)
+    rm = float(np.uint8((49 * 100) % 256 // 49))     # 4900 mod 256 = 36 -> 0
+    cm = float(np.uint8((49 * 140) % 256 // 49))     # 6860 mod 256 = 204 -> 4
+    assert o_q["score"] == 49 * abs((100 - rm) - (140 - cm))
+    assert o_e["score"] == 0.0 and o_q["steps"] == o_e["steps"] > 2
