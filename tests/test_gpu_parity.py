@@ -521,3 +521,55 @@ def test_epipolar_match_parity(pkg, orc, synth, pair_cache, patch, mean_mode):
     ok[:4] = False
     rel = np.abs(got["depth"][ok] - d_true[ok]) / d_true[ok]
     assert np.median(rel) < 0.05
+
+
+# ------------------------------------------------------------------------------------------------
+# selection tiers of the fast path under degenerate residual distributions
+# ------------------------------------------------------------------------------------------------
+def _tiers(res):
+    t = int(res["reserved"])
+    return t & 0xff, (t >> 8) & 0xff, (t >> 16) & 0xff   # hot, cold, generic selections
+
+
+@pytest.mark.parametrize("shape", ["fast", "cluster4"])
+@pytest.mark.parametrize("case", ["bright", "dark", "flat", "two_level", "half_gone"])
+def test_sparse_align_degenerate_residuals(pkg, orc, synth, pair_cache, monkeypatch, shape, case):
+    """Residual distributions that leave the comfortable middle of the key range: a +90 / -120 grey-level offset between
+    the frames (medians in the clamped outer coarse bins -> the generic radix tier), a constant current frame (thousands
+    of IDENTICAL keys: every key of a thread on the key stack, one histogram bin holds everything), a two-valued frame
+    (MAD exactly on a heavy tie) and a frame pair where half the features leave the image.  GPU == oracle per level."""
+    for k in ("SVO_ALIGN_GENERIC", "SVO_ALIGN_NT", "SVO_ALIGN_C"):
+        monkeypatch.delenv(k, raising=False)
+    if shape == "cluster4":
+        monkeypatch.setenv("SVO_ALIGN_NT", "128")
+    pair = dict(pair_cache(9, 499))
+    ref, cur = pair["ref"], pair["cur"].copy()
+    T0 = pair["T_cur_init"]
+    if case == "bright":
+        ref = (ref.astype(np.int32) * 150 // 255).astype(np.uint8)
+        cur = np.clip(cur.astype(np.int32) * 150 // 255 + 90, 0, 255).astype(np.uint8)
+    elif case == "dark":
+        ref = (ref.astype(np.int32) * 120 // 255 + 130).astype(np.uint8)
+        cur = (cur.astype(np.int32) * 120 // 255 + 10).astype(np.uint8)
+    elif case == "flat":
+        cur[:] = 77
+    elif case == "two_level":
+        cur = np.where(cur > 128, 200, 40).astype(np.uint8)
+    elif case == "half_gone":   # a prior that throws half of the image out of view
+        T0 = synth.se3_mul(synth.se3_from_Rt(np.eye(3), [9.0, 0.0, 0.0]), pair["T_ref"])
+    pair["ref"], pair["kf"], pair["cur"] = ref, ref, cur
+    pyr = _pyrs(orc, pair)
+    for mode in ("LM_FAITHFUL", "GN"):
+        rmse, T, status, lv = _oracle_align(orc, pair, pyr, getattr(orc, mode), T_cur=T0, max_iter=8)
+        with _ctx(pkg, pair) as ctx:
+            ctx.upload(0, np.stack([ref, cur]))
+            res, stats = ctx.sparse_align(_job(pkg, pair, 0, 0, 1, T_cur=T0), pair["feats"], mode=getattr(pkg.capi, mode),
+                                          max_iter=8)
+        faithful = mode == "LM_FAITHFUL"
+        # sigma, n_px, chi2, H and g of the first evaluation of every level (faithful) / of the coarsest level (GN)
+        _check_levels(stats[0] if faithful else stats[0][:1], lv if faithful else lv[:1], synth, False)
+        if faithful:
+            assert synth.rotation_angle(res[0]["T_cur"], T) < 1e-4 and np.abs(res[0]["T_cur"][4:] - T[4:]).max() < 1e-3
+            hot, cold, generic = _tiers(res[0])
+            if case in ("bright", "dark"):
+                assert generic > 0, (hot, cold, generic)   # the tier under test really ran
