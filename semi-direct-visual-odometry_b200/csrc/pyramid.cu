@@ -148,29 +148,40 @@ __global__ void __launch_bounds__(256) k_pyr_level(const uint8_t* __restrict__ s
     }
     __syncthreads();
 
-    // ---- stage 2 (BASE): gradient of the tile ----
+    // ---- stage 2 (BASE): gradient of the tile.  Warp w takes tile rows w, w + 8, ...; lane l the words 3 + l (and,
+    // in a second sweep, 35 + l for l < 2): no index arithmetic per item, conflict-free rows ----
     if (BASE) {
-        for (int i = tid; i < PT_ROWS * (PT_W1 - PT_W0); i += 256) {
-            const int r = i / (PT_W1 - PT_W0), wc = PT_W0 + i - r * (PT_W1 - PT_W0);
-            const int y = y00 + r, x0 = x00 + 4 * wc;
-            uint32_t out = 0;
-            if (y > 0 && y < sh - 1 && x0 + 3 >= 0 && x0 < sw) {
-                const uint32_t c = tI[r + 1][wc];
-                const uint32_t l = tI[r + 1][wc - 1];  // words PT_W0 - 1 and PT_W1 exist in the tile (16-byte loads)
-                const uint32_t q = tI[r + 1][wc + 1];
-                const uint32_t left  = __funnelshift_r(l, c, 24);  // columns x-1 .. x+2
-                const uint32_t right = __funnelshift_r(c, q, 8);   // columns x+1 .. x+4
-                out = __vaddus4(__vabsdiffu4(right, left), __vabsdiffu4(tI[r + 2][wc], tI[r][wc]));
-                // first / last column of the image and everything beyond it: 0 (SimdLib.h:856-884)
-                if (x0 <= 0 || x0 + 3 >= sw - 1) {
-                    uint32_t mask = 0xffffffffu;
+        const int lane = tid & 31, wrp = tid >> 5;
+        const bool rowBorder = y00 <= 0 || y00 + PT_ROWS >= sh - 1;  // the tile touches the first / last image row
+#pragma unroll
+        for (int sweep = 0; sweep < 2; sweep++) {
+            const int wc = PT_W0 + 32 * sweep + lane;
+            if (wc < PT_W1) {
+                const int x0       = x00 + 4 * wc;
+                const bool inX     = x0 + 3 >= 0 && x0 < sw;
+                const bool colEdge = x0 <= 0 || x0 + 3 >= sw - 1;  // first / last image column inside this word
+                uint32_t mask      = 0xffffffffu;
+                if (colEdge) {
 #pragma unroll
                     for (int k = 0; k < 4; k++)
                         if (x0 + k <= 0 || x0 + k >= sw - 1) mask &= ~(0xffu << (8 * k));
-                    out &= mask;
+                }
+                for (int r = wrp; r < PT_ROWS; r += 8) {
+                    const uint32_t c = tI[r + 1][wc];
+                    const uint32_t l = tI[r + 1][wc - 1];  // words PT_W0 - 1 and PT_W1 exist in the tile (16-byte loads)
+                    const uint32_t q = tI[r + 1][wc + 1];
+                    const uint32_t left  = __funnelshift_r(l, c, 24);  // columns x-1 .. x+2
+                    const uint32_t right = __funnelshift_r(c, q, 8);   // columns x+1 .. x+4
+                    uint32_t out = __vaddus4(__vabsdiffu4(right, left), __vabsdiffu4(tI[r + 2][wc], tI[r][wc])) & mask;
+                    // first / last row and column of the image and everything beyond: 0 (SimdLib.h:856-884)
+                    if (!inX) out = 0u;
+                    if (rowBorder) {
+                        const int y = y00 + r;
+                        if (!(y > 0 && y < sh - 1)) out = 0u;
+                    }
+                    tG[r][wc] = out;
                 }
             }
-            tG[r][wc] = out;
         }
         __syncthreads();
     }
@@ -225,19 +236,23 @@ __global__ void __launch_bounds__(256) k_pyr_level(const uint8_t* __restrict__ s
         }
     }
 
-    // ---- stage 4: horizontal pass, outputs (tx, tx + 1) from tile bytes 2 tx + 14 .. 2 tx + 20 ----
-    for (int i = tid; i < 2 * PT_ROWS * (PT_X / 2); i += 256) {
-        const int st = i / (PT_ROWS * (PT_X / 2));  // 0 image, 1 gradient
-        const int j  = i - st * (PT_ROWS * (PT_X / 2));
-        const int r = j / (PT_X / 2), tp = j - r * (PT_X / 2);  // tx = 2 tp
-        const uint32_t* row = st ? &tG[r][0] : &tI[(BASE ? 1 : 0) + r][0];
-        const uint32_t w0 = row[3 + tp], w1 = row[4 + tp], w2 = row[5 + tp];  // tile bytes 4 tp + 12 .. 4 tp + 23
-        // taps of output tx: bytes 2, 3 of w0 and 0, 1, 2 of w1; of tx + 1: bytes 0 .. 3 of w1 and 0 of w2 (dp4a: four
-        // byte products per instruction)
-        const uint32_t h0 = __dp4a(w0, 0x04010000u, __dp4a(w1, 0x00010406u, 0u));
-        const uint32_t h1 = __dp4a(w1, 0x04060401u, w2 & 0xffu);
-        uint16_t* hrow    = st ? &hG[r][0] : &hI[r][0];
-        *reinterpret_cast<uint32_t*>(hrow + 2 * tp) = h0 | (h1 << 16);
+    // ---- stage 4: horizontal pass, outputs (tx, tx + 1) from tile bytes 2 tx + 14 .. 2 tx + 20.  Lane = output pair
+    // tp (tx = 2 tp), warp w takes rows w, w + 8, ... of both stacks ----
+    {
+        const int tp = tid & 31, wrp = tid >> 5;
+        for (int r = wrp; r < PT_ROWS; r += 8) {
+#pragma unroll
+            for (int st = 0; st < 2; st++) {
+                const uint32_t* row = st ? &tG[r][0] : &tI[(BASE ? 1 : 0) + r][0];
+                const uint32_t w0 = row[3 + tp], w1 = row[4 + tp], w2 = row[5 + tp];  // tile bytes 4 tp + 12 .. 4 tp + 23
+                // taps of output tx: bytes 2, 3 of w0 and 0, 1, 2 of w1; of tx + 1: bytes 0 .. 3 of w1 and 0 of w2
+                // (dp4a: four byte products per instruction)
+                const uint32_t h0 = __dp4a(w0, 0x04010000u, __dp4a(w1, 0x00010406u, 0u));
+                const uint32_t h1 = __dp4a(w1, 0x04060401u, w2 & 0xffu);
+                uint16_t* hrow    = st ? &hG[r][0] : &hI[r][0];
+                *reinterpret_cast<uint32_t*>(hrow + 2 * tp) = h0 | (h1 << 16);
+            }
+        }
     }
     __syncthreads();
 
