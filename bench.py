@@ -232,6 +232,10 @@ def run_b200(a, rank, world):
         ev = stats["evaluations"].astype(np.float64)
         alg_bytes = float((nvis * ((PATCH + 3) ** 2 + ev * (PATCH + 1) ** 2)).sum() + 32.0 * batch["n_feat"].sum()
                           + 256.0 * LEVELS * n)                                   # SURVEY 8(d) formula, per launch
+        # the same traffic at DRAM sector granularity: a gather of 8-byte row segments moves whole 32-byte
+        # sectors -- (P+3) reference rows per feature and level, (P+1) current rows per evaluation
+        sector_bytes = float((nvis * (32.0 * (PATCH + 3) + ev * 32.0 * (PATCH + 1))).sum() + 32.0 * batch["n_feat"].sum()
+                             + 256.0 * LEVELS * n)
         evals_total = int(res["evaluations"].sum())
         tiers = res["reserved"].astype(np.int64)  # fast-path diagnostics: selections served hot | cold << 8 | generic << 16
         sel_tiers = {"hot": int((tiers & 0xff).sum()), "cold": int(((tiers >> 8) & 0xff).sum()),
@@ -380,7 +384,8 @@ def run_b200(a, rank, world):
             "roofline": {"bound": "hbm", "kernel": "k_align_cluster", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "peak_source": peak_src, "traffic": traffic,
                          "traffic_source": "profiles/traffic_k_align_cluster.json: dram__bytes_read+write of one 148-pair launch, scaled per pair" if traffic else None,
-                         "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kern_ms,
+                         "algorithmic_bytes_per_launch": alg_bytes, "sector_bytes_per_launch": sector_bytes,
+                         "kernel_ms": kern_ms,
                          "note": "sparse gather + exact order statistics: bound by integer issue and block barriers, not by HBM (DESIGN.md 4, profiles/)"},
         }
         if world == 1 and not a.no_cpu_baseline:
