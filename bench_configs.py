@@ -10,6 +10,7 @@
   config 2  the whole per-frame front end as one CUDA graph launch (svo_frontend_run)
   config 3  1,024 pairs x 1,000 features (bench.py --features 1000)
   config 5  (the first "next" component) depth-filter epipolar search: 2,000 seeds, 7x7 patches
+  config 6  (SURVEY 8f row f2) FeatureSelection::gradientMagnitudeWithSSC on one frame, 250 / 1,000 candidates
 
 Prints one JSON line per measurement; every line carries `roofline` (algorithmic bytes of SURVEY 8d / device time
 against the measured HBM peak) and `cpu_baseline` (the oracle port, bounded sample).  Needs a GPU.
@@ -65,7 +66,7 @@ def wall_time(fn, reps):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="0,1,2,3,5")
+    ap.add_argument("--configs", default="0,1,2,3,5,6")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     want = set(int(x) for x in a.configs.split(","))
@@ -283,6 +284,31 @@ def main():
                   "roofline": roof(bytes_, e2e_us),
                   "cpu_baseline": {"value": cpu_us, "unit": "us", "cores": 1, "kind": "port",
                                    "sample": "first %d of the %d seeds through the oracle port, scaled to the batch" % (nsamp, ns)}})
+        # ---------------- "next" row f2: SSC feature selection ----------------
+        if 6 in want:
+            grad0 = ctx.download(0, 0, 1)
+            for thr, kc in ((50, 250), (20, 1000), (100, 100)):
+                got, gi = ctx.select_ssc(0, thr, kc, 30)
+                for _ in range(3):
+                    ctx.select_ssc(0, thr, kc, 30)
+                us = wall_time(lambda: ctx.select_ssc(0, thr, kc, 30), 20)
+                ts = []
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    ow, oi = orc.select_ssc(grad0, thr, kc, 30)
+                    ts.append((time.perf_counter() - t0) * 1e6)
+                same = oi == gi and np.array_equal(np.stack([got["x"], got["y"], got["magnitude"]], 1), ow)
+                bytes_ = float(h * w * (1 + gi["iterations"]) + 12 * len(got))   # the gradient image once per width + output
+                emit({"config": {"workload": "next row f2: FeatureSelection::gradientMagnitudeWithSSC, one 1241x376 frame, threshold %d, %d "
+                                             "candidates, cell 30, bucketing: %d keypoints, %d SSC widths, %d features" %
+                                             (thr, kc, gi["keypoints"], gi["iterations"], len(got))},
+                      "metric": "us_per_frame_select_ssc", "unit": "us", "higher_is_better": False, "value": us, "dtype": "u8 / int",
+                      "identical_to_oracle": bool(same),
+                      "e2e": {"value": us, "unit": "us", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(12 * 4096 + 24),
+                              "what": "svo_select_ssc on a resident frame (one kernel, features D2H), host wall clock, median of 20"},
+                      "roofline": roof(bytes_, us),
+                      "cpu_baseline": {"value": float(np.median(ts)), "unit": "us", "cores": 1, "kind": "port",
+                                       "sample": "the same frame through the oracle port (threshold scan, stable sort, SSC, bucketing), median of 3"}})
         pin.free()
         ctx.close()
 

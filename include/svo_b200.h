@@ -117,6 +117,15 @@ typedef struct {
 svo_status svo_select_grid(svo_ctx* ctx, int slot, int cell, uint32_t thr, const uint8_t* occupancy,
                            svo_feature_px* out, int max_out, int* n_out);
 
+/* FeatureSelection::gradientMagnitudeWithSSC(frame, thr, numberCandidate, useBucketing) (src/feature_selection.cpp:27-89,
+ * SSC :165-248) -- what System calls on every keyframe (src/system.cpp:81,253,429); SURVEY 8(f) row f2.  Keypoints of
+ * equal response are ordered by raster position (the reference's std::sort leaves their order unspecified).  out: features
+ * in the order the reference appends them.  info (nullable, 4 ints): keypoints above thr, last SSC width, SSC iterations,
+ * points kept before bucketing.  num_candidates <= ~3,700 (at most 4,096 points may survive the suppression).
+ * Synchronous. */
+svo_status svo_select_ssc(svo_ctx* ctx, int slot, uint32_t thr, int num_candidates, int cell, const uint8_t* occupancy,
+                          int use_bucketing, svo_feature_px* out, int max_out, int* n_out, int32_t* info);
+
 /* ---------------------------------------------------------------------------------------------
  * ImageAlignment::align(refFrame, curFrame) (src/image_alignment.cpp:25-67), batched over
  * independent frame pairs ("jobs").

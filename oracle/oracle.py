@@ -90,6 +90,9 @@ def lib():
     L.orc_grid_select.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_void_p,
                                   C.c_void_p, C.c_int]
     L.orc_grid_select.restype = C.c_int
+    L.orc_select_ssc.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_int, C.c_int, C.c_void_p, C.c_int,
+                                 C.c_void_p, C.c_int, C.c_void_p]
+    L.orc_select_ssc.restype = C.c_int
     L.orc_bilinear_double.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
     L.orc_bilinear_double.restype = C.c_double
     L.orc_bilinear_float.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_double]
@@ -193,6 +196,19 @@ def grid_select(grad, cell, thr, occupancy=None):
         assert occ.size == rows * cols
     n = lib().orc_grid_select(_p(grad), w, h, w, cell, thr, _p(occ) if occ is not None else None, _p(out), rows * cols)
     return out[:n].copy()
+
+
+def select_ssc(grad, thr, num_candidates, cell=30, occupancy=None, use_bucketing=True):
+    """FeatureSelection::gradientMagnitudeWithSSC.  Returns ((n, 3) int32 array of x, y, magnitude; info dict)."""
+    grad = _c8(grad)
+    h, w = grad.shape
+    cap = h * w
+    out = np.zeros((cap, 3), np.int32)
+    info = np.zeros(4, np.int32)
+    occ = None if occupancy is None else np.ascontiguousarray(np.asarray(occupancy).reshape(-1), dtype=np.uint8)
+    n = lib().orc_select_ssc(_p(grad), w, h, w, thr, num_candidates, cell, _p(occ) if occ is not None else None,
+                             1 if use_bucketing else 0, _p(out), cap, _p(info))
+    return out[:n].copy(), dict(keypoints=int(info[0]), width=int(info[1]), iterations=int(info[2]), ssc_points=int(info[3]))
 
 
 def bilinear_double(img, x, y):

@@ -845,6 +845,108 @@ int orc_grid_select(const uint8_t* grad, int w, int h, int pitch, int cell, uint
     return n;
 }
 
+// FeatureSelection::gradientMagnitudeWithSSC + SSC, src/feature_selection.cpp:27-89, :165-248
+int orc_select_ssc(const uint8_t* grad, int w, int h, int pitch, uint32_t thr, int numRetPoints, int cell, const uint8_t* occ,
+                   int useBucketing, int32_t* out, int maxOut, int32_t* info)
+{
+    struct KP {
+        float x, y, response;  // cv::KeyPoint: pt is Point2f, response float
+    };
+    std::vector<KP> kps;
+    for (int i = 0; i < h; i++)  // :41-51, raster order
+        for (int j = 0; j < w; j++) {
+            const uint8_t v = grad[(size_t)i * pitch + j];
+            if (v > thr) kps.push_back({(float)j, (float)i, (float)v});
+        }
+    // :54-55 std::sort by response, descending; equal responses: stable (raster order) -- see the header
+    std::stable_sort(kps.begin(), kps.end(), [](const KP& a, const KP& b) { return a.response > b.response; });
+
+    // SSC, :165-248
+    const int cols = w, rows = h;
+    std::vector<int32_t> resultVec, result;
+    int iterations = 0, widthUsed = -1;
+    {
+        const int32_t exp1   = rows + cols + 2 * numRetPoints;
+        const long long exp2 = ((long long)4 * cols + (long long)4 * numRetPoints + (long long)4 * rows * numRetPoints +
+                                (long long)rows * rows + (long long)cols * cols - (long long)2 * rows * cols +
+                                (long long)4 * rows * cols * numRetPoints);
+        const double exp3 = std::sqrt((double)exp2);
+        const double exp4 = (2 * (numRetPoints - 1));
+        const double sol1 = -std::round((exp1 + exp3) / exp4);
+        const double sol2 = -std::round((exp1 - exp3) / exp4);
+        int high = (sol1 > sol2) ? (int)sol1 : (int)sol2;
+        int low  = (int)std::sqrt((double)kps.size() / numRetPoints);
+        int width, prevWidth = -1;
+        bool complete        = false;
+        const float K        = (float)numRetPoints;
+        const float tolerance = 0.1f;
+        const uint32_t Kmin  = (uint32_t)std::round(K - (K * tolerance));
+        const uint32_t Kmax  = (uint32_t)std::round(K + (K * tolerance));
+        while (!complete) {
+            width = low + (high - low) / 2;
+            // width <= 0 divides by zero in the reference (c = 0): defined here as "stop with the previous result"
+            if (width == prevWidth || low > high || width <= 0) {
+                resultVec = result;
+                break;
+            }
+            iterations++;
+            widthUsed = width;
+            result.clear();
+            const double c            = width / 2.0;
+            const int32_t numCellCols = (int32_t)(cols / c);
+            const int32_t numCellRows = (int32_t)(rows / c);
+            std::vector<uint8_t> covered((size_t)(numCellRows + 1) * (numCellCols + 1), 0);
+            const int32_t reach = (int32_t)(width / c);
+            for (size_t i = 0; i < kps.size(); ++i) {
+                const int32_t row = (int32_t)(kps[i].y / c);
+                const int32_t col = (int32_t)(kps[i].x / c);
+                if (!covered[(size_t)row * (numCellCols + 1) + col]) {
+                    result.push_back((int32_t)i);
+                    const int32_t rowMin = row >= reach ? row - reach : 0;
+                    const int32_t rowMax = (row + reach <= numCellRows) ? row + reach : numCellRows;
+                    const int32_t colMin = col >= reach ? col - reach : 0;
+                    const int32_t colMax = (col + reach <= numCellCols) ? col + reach : numCellCols;
+                    for (int32_t r = rowMin; r <= rowMax; ++r)
+                        for (int32_t cc = colMin; cc <= colMax; ++cc) covered[(size_t)r * (numCellCols + 1) + cc] = 1;
+                }
+            }
+            if (result.size() >= Kmin && result.size() <= Kmax) {
+                resultVec = result;
+                complete  = true;
+            } else if (result.size() < Kmin)
+                high = width - 1;
+            else
+                low = width + 1;
+            prevWidth = width;
+        }
+    }
+    if (info) {
+        info[0] = (int32_t)kps.size();
+        info[1] = widthUsed;
+        info[2] = iterations;
+        info[3] = (int32_t)resultVec.size();
+    }
+    int n = 0;
+    const int gridCols = w / cell + 1, gridRows = h / cell + 1;
+    std::vector<uint8_t> grid((size_t)gridRows * gridCols, 0);
+    if (occ) std::copy(occ, occ + grid.size(), grid.begin());
+    for (size_t i = 0; i < resultVec.size(); i++) {  // :62-89
+        const KP& kp = kps[resultVec[i]];
+        if (useBucketing) {
+            const int32_t idx = (int32_t)kp.x / cell, idy = (int32_t)kp.y / cell;
+            if (grid[(size_t)idy * gridCols + idx]) continue;
+            grid[(size_t)idy * gridCols + idx] = 1;
+        }
+        if (n < maxOut) {
+            out[3 * n + 0] = (int32_t)kp.x;
+            out[3 * n + 1] = (int32_t)kp.y;
+            out[3 * n + 2] = (int32_t)kp.response;
+        }
+        n++;
+    }
+    return n;
+}
+
 double orc_bilinear_double(const uint8_t* img, int pitch, double x, double y) { return bilinearDouble(img, pitch, x, y); }
 float orc_bilinear_float(const uint8_t* img, int pitch, double x, double y) { return bilinearFloat(img, pitch, x, y); }
 double orc_median(const double* v, int n, int numValid, int mode) { return medianOf(v, n, numValid, mode); }

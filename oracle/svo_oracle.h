@@ -90,6 +90,15 @@ void orc_build_pyramid(const uint8_t* img, int w, int h, int pitch, int levels, 
 int orc_grid_select(const uint8_t* grad, int w, int h, int pitch, int cell, uint32_t thr, const uint8_t* occupancy,
                     int32_t* out_xym, int max_out);
 
+/* FeatureSelection::gradientMagnitudeWithSSC (src/feature_selection.cpp:27-89) with FeatureSelection::SSC (:165-248):
+ * every pixel with gradient > thr, sorted by response (std::sort there: the order of EQUAL responses is unspecified in
+ * the reference; here: stable, i.e. raster order -- the documented choice), suppression via square covering with a
+ * binary search over the square width, then (use_bucketing) first-come bucketing on the occupancy grid.
+ * out: (x, y, magnitude) triples in emission order.  info (nullable): [0] keypoints above thr, [1] final width,
+ * [2] SSC iterations, [3] points returned by SSC (before bucketing).  Returns the number of features. */
+int orc_select_ssc(const uint8_t* grad, int w, int h, int pitch, uint32_t thr, int num_candidates, int cell,
+                   const uint8_t* occupancy, int use_bucketing, int32_t* out, int max_out, int32_t* info);
+
 /* ---- numerics (src/algorithm.cpp:834-905, src/pinhole_camera.cpp:50-57) ---- */
 double orc_bilinear_double(const uint8_t* img, int pitch, double x, double y);
 float orc_bilinear_float(const uint8_t* img, int pitch, double x, double y);

@@ -26,7 +26,7 @@ SYMBOLS = [
     "svo_sparse_align_results_device", "svo_debug_cycles",
     "svo_feature_align", "svo_feature_align_stage", "svo_feature_align_h2d", "svo_feature_align_launch",
     "svo_feature_align_d2h", "svo_feature_align_fetch", "svo_frontend_run", "svo_frontend_image_buffer",
-    "svo_epipolar_match",
+    "svo_epipolar_match", "svo_select_ssc",
 ]
 
 
@@ -127,6 +127,7 @@ def load():
     L.svo_sparse_align_results_device.argtypes = [vp]
     L.svo_debug_cycles.argtypes = [vp, vp]
     L.svo_sparse_align_results_device.restype = vp
+    L.svo_select_ssc.argtypes = [vp, i, C.c_uint32, i, i, vp, i, vp, i, C.POINTER(i), vp]
     L.svo_epipolar_match.argtypes = [vp, vp, i, C.POINTER(EpiParams), vp]
     L.svo_frontend_run.argtypes = [vp, C.POINTER(FrontendParams), vp, i, vp, vp, i, vp, vp, vp, i, vp]
     L.svo_frontend_image_buffer.argtypes = [vp]
@@ -269,6 +270,20 @@ class Context:
         n = C.c_int()
         self._check(self.L.svo_select_grid(self.h, slot, cell, thr, _ptr(occ), _ptr(out), out.size, C.byref(n)))
         return out[:n.value].copy()
+
+    # ---- FeatureSelection::gradientMagnitudeWithSSC ----
+    def select_ssc(self, slot, thr=50, num_candidates=250, cell=30, occupancy=None, use_bucketing=True):
+        rows, cols = self.height // cell + 1, self.width // cell + 1
+        out = np.zeros(4096, FEATURE_PX_DTYPE)
+        occ = None
+        if occupancy is not None:
+            occ = np.ascontiguousarray(np.asarray(occupancy).reshape(-1), dtype=np.uint8)
+            assert occ.size == rows * cols
+        n = C.c_int()
+        info = np.zeros(4, np.int32)
+        self._check(self.L.svo_select_ssc(self.h, slot, thr, num_candidates, cell, _ptr(occ), 1 if use_bucketing else 0, _ptr(out),
+                                          out.size, C.byref(n), _ptr(info)))
+        return out[:n.value].copy(), dict(keypoints=int(info[0]), width=int(info[1]), iterations=int(info[2]), ssc_points=int(info[3]))
 
     # ---- ImageAlignment::align ----
     def sparse_align(self, jobs, feats, patch_size=5, min_level=0, max_level=3, mode=LM_FAITHFUL, max_iter=20,

@@ -47,6 +47,9 @@ void release(svo_ctx* ctx)
     for (int i = 0; i < 64; i++)
         if (ctx->ev_pf_chunk[i]) cudaEventDestroy(ctx->ev_pf_chunk[i]);
     if (ctx->ev_jobs_h2d) cudaEventDestroy(ctx->ev_jobs_h2d);
+    cudaFree(ctx->d_ssc_key);
+    cudaFree(ctx->d_ssc_state);
+    cudaFree(ctx->d_ssc_info);
     cudaFree(ctx->d_cell_best);
     cudaFree(ctx->d_occupancy);
     cudaFree(ctx->d_sel_out);
@@ -471,6 +474,42 @@ svo_status svo_select_grid(svo_ctx* ctx, int slot, int cell, uint32_t thr, const
     const int n = *ctx->h_sel_count;
     *n_out      = n;
     std::memcpy(out, ctx->h_sel_out, sizeof(svo_feature_px) * std::min(n, max_out));
+    return SVO_OK;
+}
+
+svo_status svo_select_ssc(svo_ctx* ctx, int slot, uint32_t thr, int num_candidates, int cell, const uint8_t* occupancy,
+                          int use_bucketing, svo_feature_px* out, int max_out, int* n_out, int32_t* info)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    if (!out || !n_out || max_out < 0 || bad_slot(ctx, slot) || cell < 4 || num_candidates < 2)
+        SVO_FAIL(SVO_ERR_INVALID, "svo_select_ssc: bad arguments (cell >= 4, num_candidates >= 2)");
+    const LevelGeom& g = ctx->arena.geom[0];
+    const int rows = g.h / cell + 1, cols = g.w / cell + 1;
+    if (rows * cols > ctx->sel_cap_cells) SVO_FAIL(SVO_ERR_CAPACITY, "svo_select_ssc: too many cells");
+    SVO_CUDA(cudaSetDevice(ctx->cfg.device));
+    {
+        const svo_status ws = wait_ingest(ctx);
+        if (ws != SVO_OK) return ws;
+    }
+    if (occupancy) {
+        std::memcpy(ctx->h_occupancy, occupancy, (size_t)rows * cols);
+        SVO_CUDA(cudaMemcpyAsync(ctx->d_occupancy, ctx->h_occupancy, (size_t)rows * cols, cudaMemcpyHostToDevice, ctx->stream));
+    }
+    const int cap = std::min(ctx->sel_cap_cells, 4096);  // d_sel_out holds sel_cap_cells records
+    const svo_status st = launch_select_ssc(ctx, slot, thr, num_candidates, cell, rows, cols, occupancy != nullptr, use_bucketing != 0, cap);
+    if (st != SVO_OK) return st;
+    int32_t hinfo[8];
+    SVO_CUDA(cudaMemcpyAsync(ctx->h_sel_count, ctx->d_sel_count, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SVO_CUDA(cudaMemcpyAsync(ctx->h_sel_out, ctx->d_sel_out, sizeof(svo_feature_px) * cap, cudaMemcpyDeviceToHost, ctx->stream));
+    SVO_CUDA(cudaStreamSynchronize(ctx->stream));
+    SVO_CUDA(cudaMemcpy(hinfo, ctx->d_ssc_info, sizeof(int32_t) * 5, cudaMemcpyDeviceToHost));
+    if (info)
+        for (int i = 0; i < 4; i++) info[i] = hinfo[i];
+    if (hinfo[4] == 1) SVO_FAIL(SVO_ERR_CAPACITY, "svo_select_ssc: more SSC cells than the scratch holds");
+    if (hinfo[4] == 2) SVO_FAIL(SVO_ERR_CAPACITY, "svo_select_ssc: more than 4,096 points survive the suppression (num_candidates too large)");
+    const int n = *ctx->h_sel_count;
+    *n_out      = n;
+    std::memcpy(out, ctx->h_sel_out, sizeof(svo_feature_px) * std::min(n, std::min(max_out, cap)));
     return SVO_OK;
 }
 

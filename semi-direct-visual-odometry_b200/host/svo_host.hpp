@@ -293,6 +293,26 @@ public:
         m_imgGradientMagnitude = frame->m_imagePyramid.getBaseGradientImage();  // computeImageGradient, :250-267
         resetGridOccupancy();                                                     // :145
     }
+    // src/feature_selection.cpp:27-89 (SSC :165-248): what System calls on every keyframe (src/system.cpp:81,253,429).
+    // Appends Features in the order the reference does (sorted-keypoint order; equal responses in raster order).  The
+    // reference resets the occupancy grid only in the bucketing branch (:79).
+    void gradientMagnitudeWithSSC(std::shared_ptr<Frame>& frame, uint32_t detectionThreshold, uint32_t numberCandidate,
+                                  bool useBucketing = true)
+    {
+        const auto& dev = frame->m_imagePyramid.device();
+        std::vector<uint8_t> occ(m_occupancyGrid.begin(), m_occupancyGrid.end());
+        std::vector<svo_feature_px> out(4096);
+        int n = 0;
+        dev->check(svo_select_ssc(dev->ctx(), frame->m_imagePyramid.slot(), detectionThreshold, (int)numberCandidate, m_cellSize,
+                                  occ.data(), useBucketing ? 1 : 0, out.data(), (int)out.size(), &n, nullptr),
+                   "svo_select_ssc");
+        for (int i = 0; i < n; i++) {
+            auto f = std::make_shared<Feature>(frame, Vec2(out[i].x, out[i].y), (double)out[i].magnitude, 0.0, 0);
+            frame->addFeature(f);
+        }
+        m_imgGradientMagnitude = frame->m_imagePyramid.getBaseGradientImage();  // computeImageGradient, :250-267
+        if (useBucketing) resetGridOccupancy();
+    }
     void setExistingFeatures(const std::vector<std::shared_ptr<Feature>>& features)  // :269-275
     {
         for (const auto& f : features) setCellInGridOccupancy(f->m_pixelPosition);

@@ -110,6 +110,25 @@ int main(int argc, char** argv)
         }
         CHECK(threw);
     }
+    // ---- FeatureSelection::gradientMagnitudeWithSSC (what System calls on keyframes) ----
+    {
+        auto probe = std::make_shared<Frame>(camera, refImg, 4, 7, kf);
+        FeatureSelection ssc(w, h, 30);
+        ssc.setCellInGridOccupancy(Vec2(45.0, 40.0));
+        ssc.gradientMagnitudeWithSSC(probe, 50, 250, true);
+        std::vector<uint8_t> occ((size_t)ssc.m_gridRows * ssc.m_gridCols, 0);
+        occ[(size_t)1 * ssc.m_gridCols + 1] = 1;
+        std::vector<int32_t> want(3 * 4096);
+        int32_t info[4];
+        const Mat8& g = probe->m_imagePyramid.getBaseGradientImage();
+        const int n   = orc_select_ssc(g.ptr(), w, h, w, 50, 250, 30, occ.data(), 1, want.data(), 4096, info);
+        CHECK((int)probe->numberObservation() == n && n > 0);
+        for (int i = 0; i < n && i < (int)probe->numberObservation(); i++) {
+            const auto& f = probe->m_features[i];
+            CHECK(f->m_pixelPosition.x() == want[3 * i] && f->m_pixelPosition.y() == want[3 * i + 1] && f->m_gradientMagnitude == want[3 * i + 2]);
+        }
+        std::printf("gradientMagnitudeWithSSC: %d features from %d keypoints (width %d, %d iterations)\n", n, info[0], info[1], info[2]);
+    }
     // 3D points on the plane z = 15 m (the scene the images were rendered from); every 7th feature has no point
     for (size_t i = 0; i < ref->m_features.size(); i++) {
         if (i % 7 == 3) continue;

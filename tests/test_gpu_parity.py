@@ -573,3 +573,43 @@ def test_sparse_align_degenerate_residuals(pkg, orc, synth, pair_cache, monkeypa
             hot, cold, generic = _tiers(res[0])
             if case in ("bright", "dark"):
                 assert generic > 0, (hot, cold, generic)   # the tier under test really ran
+
+
+# ------------------------------------------------------------------------------------------------
+# FeatureSelection::gradientMagnitudeWithSSC: exact indices, exact order
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("thr,k,cell,bucket", [(50, 250, 30, True), (50, 500, 30, True), (20, 1000, 30, True), (100, 100, 30, True),
+                                               (150, 300, 20, True), (50, 400, 30, False), (200, 2000, 16, True)])
+def test_select_ssc_exact(pkg, orc, pair_cache, thr, k, cell, bucket):
+    pair = pair_cache(0)
+    with _ctx(pkg, pair) as ctx:
+        ctx.upload(0, pair["ref"])
+        got, ginfo = ctx.select_ssc(0, thr, k, cell, use_bucketing=bucket)
+        grad = ctx.download(0, 0, 1)
+    want, winfo = orc.select_ssc(grad, thr, k, cell, use_bucketing=bucket)
+    assert ginfo == winfo, (ginfo, winfo)
+    assert len(got) == len(want)
+    assert np.array_equal(np.stack([got["x"], got["y"], got["magnitude"]], 1), want)
+
+
+def test_select_ssc_ties_occupancy_and_sparse(pkg, orc):
+    h, w = 376, 1241
+    rng = np.random.default_rng(21)
+    img = (rng.integers(0, 4, (h, w)) * 60).astype(np.uint8)   # few distinct gradient values: the tie order matters
+    img[:60, :90] = 17
+    sparse = np.full((h, w), 30, np.uint8)                      # a handful of keypoints only
+    for (y, x) in [(20, 30), (21, 31), (200, 700), (370, 1235), (5, 5), (100, 100)]:
+        sparse[y, x] = 250
+    with pkg.Context(w, h, (500, 500, w / 2, h / 2), levels=2, max_frames=2, max_jobs=1, max_features=16,
+                     max_fa_items=16) as ctx:
+        ctx.upload(0, np.stack([img, sparse]))
+        rows, cols = h // 30 + 1, w // 30 + 1
+        occ = (rng.random(rows * cols) < 0.3).astype(np.uint8)
+        for slot in (0, 1):
+            grad = ctx.download(slot, 0, 1)
+            for o in (None, occ):
+                for k in (50, 300):
+                    got, gi = ctx.select_ssc(slot, 40, k, 30, occupancy=o)
+                    want, wi = orc.select_ssc(grad, 40, k, 30, occupancy=o)
+                    assert gi == wi, (slot, k, gi, wi)
+                    assert np.array_equal(np.stack([got["x"], got["y"], got["magnitude"]], 1), want), (slot, k)

@@ -302,3 +302,81 @@ def test_epipolar_uint8_mean_quirk(orc):
     cm = float(np.uint8((49 * 140) % 256 // 49))     # 6860 mod 256 = 204 -> 4
     assert o_q["score"] == 49 * abs((100 - rm) - (140 - cm))
     assert o_e["score"] == 0.0 and o_q["steps"] == o_e["steps"] > 2
+
+
+# ------------------------------------------------------------------------------------------------
+# FeatureSelection::gradientMagnitudeWithSSC: the restatement against plain numpy / python
+# ------------------------------------------------------------------------------------------------
+def _py_ssc(grad, thr, K, cell, occupancy=None, use_bucketing=True):
+    """src/feature_selection.cpp:27-89 + :165-248 as a direct python loop (stable sort by response)."""
+    import math
+    h, w = grad.shape
+    ys, xs = np.nonzero(grad > thr)                       # raster order
+    resp = grad[ys, xs].astype(np.int32)
+    order = np.argsort(-resp, kind="stable")
+    ys, xs, resp = ys[order], xs[order], resp[order]
+    n = len(ys)
+    exp1 = h + w + 2 * K
+    exp2 = 4 * w + 4 * K + 4 * h * K + h * h + w * w - 2 * h * w + 4 * h * w * K
+    exp3, exp4 = math.sqrt(exp2), 2 * (K - 1)
+
+    def cround(v):   # C round(): half away from zero
+        return math.floor(abs(v) + 0.5) * (1 if v >= 0 else -1)
+    sol1, sol2 = -cround((exp1 + exp3) / exp4), -cround((exp1 - exp3) / exp4)
+    high = int(sol1) if sol1 > sol2 else int(sol2)
+    low = int(math.sqrt(n / K))
+    kmin = int(cround(float(np.float32(K) - np.float32(K) * np.float32(0.1))))
+    kmax = int(cround(float(np.float32(K) + np.float32(K) * np.float32(0.1))))
+    prev, result, res_vec, iters, wused = -1, [], [], 0, -1
+    while True:
+        width = low + int((high - low) / 2)               # C integer division truncates toward zero
+        if width == prev or low > high or width <= 0:
+            res_vec = result
+            break
+        iters, wused = iters + 1, width
+        c = width / 2.0
+        ncc, ncr = int(w / c), int(h / c)
+        covered = np.zeros((ncr + 1, ncc + 1), bool)
+        reach = int(width / c)
+        result = []
+        rows = (ys.astype(np.float32).astype(np.float64) / c).astype(np.int64)
+        cols = (xs.astype(np.float32).astype(np.float64) / c).astype(np.int64)
+        for i in range(n):
+            r, cc = rows[i], cols[i]
+            if not covered[r, cc]:
+                result.append(i)
+                covered[max(r - reach, 0):min(r + reach, ncr) + 1, max(cc - reach, 0):min(cc + reach, ncc) + 1] = True
+        if kmin <= len(result) <= kmax:
+            res_vec = result
+            break
+        if len(result) < kmin:
+            high = width - 1
+        else:
+            low = width + 1
+        prev = width
+    gcols = w // cell + 1
+    grid = np.zeros((h // cell + 1) * gcols, bool) if occupancy is None else np.asarray(occupancy).astype(bool).copy()
+    out = []
+    for i in res_vec:
+        if use_bucketing:
+            b = (ys[i] // cell) * gcols + xs[i] // cell
+            if grid[b]:
+                continue
+            grid[b] = True
+        out.append((xs[i], ys[i], resp[i]))
+    return np.array(out, np.int32).reshape(-1, 3), dict(keypoints=n, width=wused, iterations=iters, ssc_points=len(res_vec))
+
+
+@pytest.mark.parametrize("thr,k,bucket", [(120, 80, True), (60, 200, True), (60, 200, False), (200, 30, True)])
+def test_select_ssc_against_python(orc, thr, k, bucket):
+    rng = np.random.default_rng(thr + k)
+    h, w = 96, 160
+    img = rng.integers(0, 256, (h // 4, w // 4), dtype=np.uint8).repeat(4, 0).repeat(4, 1)   # blocky: many equal responses
+    img = (img.astype(np.int32) + rng.integers(0, 12, (h, w))).clip(0, 255).astype(np.uint8)
+    grad = orc.abs_gradient(img)
+    occ = (rng.random((h // 16 + 1) * (w // 16 + 1)) < 0.25).astype(np.uint8)
+    for o in (None, occ):
+        got, gi = orc.select_ssc(grad, thr, k, 16, occupancy=o, use_bucketing=bucket)
+        want, wi = _py_ssc(grad, thr, k, 16, occupancy=o, use_bucketing=bucket)
+        assert gi == wi, (gi, wi)
+        assert np.array_equal(got, want)
