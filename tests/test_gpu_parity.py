@@ -613,3 +613,34 @@ def test_select_ssc_ties_occupancy_and_sparse(pkg, orc):
                     want, wi = orc.select_ssc(grad, 40, k, 30, occupancy=o)
                     assert gi == wi, (slot, k, gi, wi)
                     assert np.array_equal(np.stack([got["x"], got["y"], got["magnitude"]], 1), want), (slot, k)
+
+
+def test_next_rows_golden_gpu(pkg, synth):
+    """The CUDA path against golden vectors that neither it nor the oracle produced (tests/golden/make_golden_next.py)."""
+    from test_oracle_numerics import _check_next_rows_golden
+    capi = pkg.capi
+
+    def ssc(img, grad, thr, k, cell, bucket):
+        h, w = img.shape
+        with pkg.Context(w, h, (500, 500, w / 2, h / 2), levels=2, max_frames=1, max_jobs=1, max_features=16, max_fa_items=16) as ctx:
+            ctx.upload(0, img)
+            assert np.array_equal(ctx.download(0, 0, 1), grad)
+            got, info = ctx.select_ssc(0, thr, k, cell, use_bucketing=bucket)
+        return np.stack([got["x"], got["y"], got["magnitude"]], 1).astype(np.int32).reshape(-1, 3), info
+
+    def epi(wide, T_rel, rows):
+        items = np.zeros(len(rows), capi.EPI_ITEM_DTYPE)
+        f = wide["feats"][rows[:, 0].astype(int)]
+        items["ref_slot"], items["cur_slot"], items["T_rel"] = 0, 1, T_rel
+        items["px"], items["bearing"] = f["px"], f["bearing"]
+        items["depth"], items["min_depth"], items["max_depth"] = rows[:, 2], rows[:, 3], rows[:, 4]
+        out = [None] * len(rows)
+        with _ctx(pkg, wide) as ctx:
+            ctx.upload(0, np.stack([wide["ref"], wide["cur"]]))
+            for mode in (1, 0):
+                sel = np.nonzero(rows[:, 1] == mode)[0]
+                r = ctx.epipolar_match(items[sel], mean_mode=capi.MEAN_EIGEN_U8 if mode else capi.MEAN_EXACT)
+                for j, i in enumerate(sel):
+                    out[i] = dict(found=bool(r[j]["found"]), steps=int(r[j]["steps"]), px=r[j]["px"], depth=r[j]["depth"], score=r[j]["score"])
+        return out
+    _check_next_rows_golden(ssc, epi, synth)

@@ -380,3 +380,39 @@ def test_select_ssc_against_python(orc, thr, k, bucket):
         want, wi = _py_ssc(grad, thr, k, 16, occupancy=o, use_bucketing=bucket)
         assert gi == wi, (gi, wi)
         assert np.array_equal(got, want)
+
+
+def _check_next_rows_golden(ssc_fn, epi_fn, synth):
+    """shared by the CPU test (oracle) and the GPU test (CUDA path): both must reproduce the golden vectors made by
+    the independent python / numpy restatements (tests/golden/make_golden_next.py)"""
+    g = np.load(os.path.join(GOLD, "next_rows_golden.npz"))
+    for tag in ("a", "b"):
+        thr, k, cell, bucket = [int(v) for v in g["ssc_%s_params" % tag]]
+        feats, info = ssc_fn(g["img"], g["grad"], thr, k, cell, bool(bucket))
+        assert [info["keypoints"], info["width"], info["iterations"], info["ssc_points"]] == list(g["ssc_%s_info" % tag])
+        assert np.array_equal(feats, g["ssc_%s_feats" % tag])
+    wide = synth.make_pair(index=int(g["epi_index"]), n_features=120, motion_scale=float(g["epi_motion_scale"]))
+    rows = g["epi_rows"]
+    res = epi_fn(wide, g["epi_T_rel"], rows)
+    for row, r in zip(rows, res):
+        assert bool(row[5]) == bool(r["found"]) and int(row[9]) == int(r["steps"])
+        assert abs(row[7] - r["px"][0]) < 1e-9 and abs(row[8] - r["px"][1]) < 1e-9
+        if row[5]:
+            assert abs(row[6] - r["depth"]) < 1e-9 * row[6]
+        if row[10] >= 0:
+            assert abs(row[10] - r["score"]) < 1e-6
+
+
+def test_next_rows_golden_oracle(orc, pkg):
+    def ssc(img, grad, thr, k, cell, bucket):
+        assert np.array_equal(orc.abs_gradient(img), grad)
+        return orc.select_ssc(grad, thr, k, cell, use_bucketing=bucket)
+
+    def epi(wide, T_rel, rows):
+        out = []
+        for row in rows:
+            f = wide["feats"][int(row[0])]
+            out.append(orc.epipolar_match(wide["ref"], wide["cur"], wide["K"], T_rel, f["px"], f["bearing"], row[2], row[3], row[4],
+                                          mean_mode=orc.MEAN_EIGEN_U8 if row[1] else orc.MEAN_EXACT))
+        return out
+    _check_next_rows_golden(ssc, epi, pkg.synth)
