@@ -416,3 +416,140 @@ def test_next_rows_golden_oracle(orc, pkg):
                                           mean_mode=orc.MEAN_EIGEN_U8 if row[1] else orc.MEAN_EXACT))
         return out
     _check_next_rows_golden(ssc, epi, pkg.synth)
+
+
+# ------------------------------------------------------------------------------------------------
+# ImageAlignment::align end to end against an INDEPENDENT numpy restatement: cv2 pyramids, rotation matrices from
+# scipy, SE3 exp through scipy.linalg.expm of the 4x4 twist, numpy.linalg.solve, numpy sort for the medians -- no code
+# shared with oracle/svo_oracle.cpp.  What the reference executes (one damped LM step per level).
+# ------------------------------------------------------------------------------------------------
+def _np_bilin(img, x, y):
+    """algorithm::bilinearInterpolationDouble, src/algorithm.cpp:896-905"""
+    x1, y1 = int(x), int(y)
+    a = (x1 + 1 - x) * float(img[y1, x1]) + (x - x1) * float(img[y1, x1 + 1])
+    b = (x1 + 1 - x) * float(img[y1 + 1, x1]) + (x - x1) * float(img[y1 + 1, x1 + 1])
+    return (y1 + 1 - y) * a + (y - y1) * b
+
+
+def _np_median_rule(values, num_valid, n_total):
+    """algorithm::computeMedian with MEDIAN_EXACT (SURVEY 9.3): values = the valid entries; invalid ones sort last"""
+    s = np.sort(values)
+    mid = num_valid // 2
+    return s[mid] if n_total % 2 == 1 else 0.5 * (s[mid - 1] + s[mid])
+
+
+def _np_align_faithful(ref_pyr, cur_pyr, feats, n_ref, T_ref, T_cur, K, P=5, levels=(3, 2, 1, 0)):
+    from scipy.linalg import expm
+    from scipy.spatial.transform import Rotation
+
+    def to_mat(T):
+        M = np.eye(4)
+        M[:3, :3] = Rotation.from_quat(T[:4]).as_matrix()
+        M[:3, 3] = T[4:]
+        return M
+    Mref, Mcur = to_mat(np.asarray(T_ref, float)), to_mat(np.asarray(T_cur, float))
+    half, area = P // 2, P * P
+    F = len(feats)
+    stats = []
+    for level in levels:
+        ref, cur = ref_pyr[level], cur_pyr[level]
+        lh, lw = ref.shape
+        scale = 1.0 / (1 << level)
+        fx, fy = K[0] / (1 << level), K[1] / (1 << level)
+        J = np.zeros((F * area, 6))
+        T_patch = np.zeros(F * area)
+        vis_ref = np.zeros(F, bool)
+        pW = np.zeros((F, 3))
+        Cref = -Mref[:3, :3].T @ Mref[:3, 3]            # Frame::cameraInWorld
+        for f in range(F):
+            ft = feats[f]
+            if not ft["has_point"]:
+                continue
+            u, v = ft["px"][0] * scale, ft["px"][1] * scale
+            uI, vI = int(np.floor(u)), int(np.floor(v))
+            b = half + 2
+            if uI - b < 0 or vI - b < 0 or uI + b >= lw or vI + b >= lh:
+                continue
+            vis_ref[f] = True
+            depth = np.linalg.norm(ft["point"] - Cref)
+            pc = ft["bearing"] * depth
+            pw = np.linalg.inv(Mref)[:3, :3] @ pc + np.linalg.inv(Mref)[:3, 3]
+            pW[f] = pw
+            x, y, z = pw
+            J0 = np.array([fx / z, 0, -fx * x / z**2, -fx * x * y / z**2, fx * x * x / z**2 + fx, -fx * y / z])
+            J1 = np.array([0, fy / z, -fy * y / z**2, -fy * y * y / z**2 - fy, fy * x * y / z**2, fy * x / z])
+            k = 0
+            for yy in range(-half, half + 1):
+                for xx in range(-half, half + 1):
+                    T_patch[f * area + k] = _np_bilin(ref, u + xx, v + yy)
+                    gx = 0.5 * (_np_bilin(ref, u + xx + 1, v + yy) - _np_bilin(ref, u + xx - 1, v + yy))
+                    gy = 0.5 * (_np_bilin(ref, u + xx, v + yy + 1) - _np_bilin(ref, u + xx, v + yy - 1))
+                    J[f * area + k] = gx * J0 + gy * J1
+                    k += 1
+        r = np.zeros(F * area)
+        valid = np.zeros(F * area, bool)
+        for f in range(F):
+            if not vis_ref[f]:
+                continue
+            pcur = Mcur[:3, :3] @ pW[f] + Mcur[:3, 3]
+            u = (K[0] * pcur[0] / pcur[2] + K[2]) * scale
+            v = (K[1] * pcur[1] / pcur[2] + K[3]) * scale
+            uI, vI = int(np.floor(u)), int(np.floor(v))
+            b = half + 2
+            if uI - b < 0 or vI - b < 0 or uI + b >= lw or vI + b >= lh:
+                continue
+            k = 0
+            for yy in range(-half, half + 1):
+                for xx in range(-half, half + 1):
+                    r[f * area + k] = _np_bilin(cur, u + xx, v + yy) - T_patch[f * area + k]
+                    valid[f * area + k] = True
+                    k += 1
+        nv = int(valid.sum())
+        med = _np_median_rule(r[valid], nv, F * area)
+        mad = _np_median_rule(np.abs(r[valid] - med), nv, F * area)
+        sigma = max(1.482602218505602 * mad, np.finfo(float).eps)
+        c = 4.6851 * sigma
+        wgt = np.where(valid & (np.abs(r) <= c), (1 - r**2 / c**2) ** 2, 0.0)
+        chi2 = float((wgt * r * r).sum())
+        H = J.T @ (wgt[:, None] * J)
+        g = J.T @ (wgt * r)
+        lam = 1e-2 * H.diagonal().max()
+        dx = np.linalg.solve(H + lam * np.eye(6), g)
+        tw = np.zeros((4, 4))                            # pose <- pose * exp(-dx), dx = (upsilon, omega)
+        ups, om = -dx[:3], -dx[3:]
+        tw[:3, :3] = np.array([[0, -om[2], om[1]], [om[2], 0, -om[0]], [-om[1], om[0], 0]])
+        tw[:3, 3] = ups
+        Mcur = Mcur @ expm(tw)
+        stats.append(dict(H=H, g=g, chi2=chi2, sigma=sigma, lam=lam, dx=dx, n_px=nv, pose=Mcur.copy(), rmse=np.sqrt(chi2 / nv)))
+    return stats
+
+
+@pytest.mark.parametrize("n_features", [101, 60])   # odd N: the reference's median is well defined; even N: MEDIAN_EXACT
+def test_align_against_independent_numpy(orc, pkg, n_features):
+    cv2 = pytest.importorskip("cv2")
+    from scipy.spatial.transform import Rotation
+    synth = pkg.synth
+    T_ref = synth.se3_from_Rt(synth.rodrigues(np.array([0.02, -0.03, 0.01])), [0.4, -0.2, 1.5])   # world != ref frame
+    pair = synth.make_pair(index=11, n_features=n_features, T_ref=tuple(T_ref))
+    T0 = synth.se3_mul(synth.se3_from_Rt(synth.rodrigues(np.array([1e-3, -2e-3, 5e-4])), [0.01, -0.02, -0.1]), pair["T_ref"])
+    feats = pair["feats"][:pair["n_ref"]]   # the numpy restatement handles the reference frame's features
+    def pyr(img):
+        out = [img]
+        for _ in range(3):
+            out.append(cv2.pyrDown(out[-1]))
+        return out
+    want = _np_align_faithful(pyr(pair["ref"]), pyr(pair["cur"]), feats, len(feats), pair["T_ref"], T0, pair["K"])
+    rp, cp = orc.build_pyramid(pair["ref"], 4)[0], orc.build_pyramid(pair["cur"], 4)[0]
+    rmse, T, status, lv = orc.sparse_align(rp, rp, cp, pair["w"], pair["h"], feats, len(feats), 0, pair["T_ref"], pair["T_ref"],
+                                           pair["K"], T0, mode=orc.LM_FAITHFUL)
+    for s, (o, w_) in enumerate(zip(lv, want)):
+        assert o["n_px"] == w_["n_px"], s
+        assert abs(o["sigma"] - w_["sigma"]) <= 1e-10 * w_["sigma"], (s, o["sigma"], w_["sigma"])
+        assert abs(o["chi2"] - w_["chi2"]) <= 1e-9 * w_["chi2"]
+        assert np.abs(o["H"] - w_["H"]).max() <= 1e-9 * np.abs(w_["H"]).max()
+        assert np.abs(o["g"] - w_["g"]).max() <= 1e-9 * np.abs(w_["H"]).max()
+        assert abs(o["lam"] - w_["lam"]) <= 1e-9 * w_["lam"]
+        assert np.abs(o["dx"] - w_["dx"]).max() <= 1e-7 * max(1e-3, np.abs(w_["dx"]).max()), (s, o["dx"], w_["dx"])
+        Ro = Rotation.from_quat(o["pose_after"][:4]).as_matrix()
+        assert np.abs(Ro - w_["pose"][:3, :3]).max() < 1e-9 and np.abs(o["pose_after"][4:] - w_["pose"][:3, 3]).max() < 1e-9, s
+    assert abs(rmse - want[-1]["rmse"]) <= 1e-9 * rmse
