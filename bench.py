@@ -285,7 +285,7 @@ def run_b200(a, rank, world):
         launches = ctx.launches - l0
         ms_total = t_start.elapsed_time(t_end)
         kern_ms = float(np.mean([ev0[k].elapsed_time(ev1[k]) for k in range(a.steps)]))
-        clocks = sampler.stop(tw0, tw1) if sampler else None
+        clocks = None  # sampled until the end of the e2e region (value + latency + e2e: all under load)
 
         # ---- single-pair latency (the "us / frame pair" of the metric): one job, resident ----
         lat_us = None
@@ -333,6 +333,7 @@ def run_b200(a, rank, world):
         barrier()
         e2e_wall_ms = 1e3 * (time.perf_counter() - tq0)
         e2e_ms = s0.elapsed_time(s1)
+        clocks = sampler.stop(tw0, time.perf_counter()) if sampler else None
         h2d = int(n * h * w + jobs.nbytes + feats.nbytes)
         d2h = int(n * capi.ALIGN_RESULT_DTYPE.itemsize)
         assert np.array_equal(r_e2e["T_cur"], res["T_cur"]), "e2e result differs from the resident run"
