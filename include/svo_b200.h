@@ -15,7 +15,9 @@
  *   - images: 8-bit gray, row-major.  Pyramids live on the device in "frame slots" of a
  *     per-context arena; a slot is what a reference Frame's m_imagePyramid is.
  *   - there is NO CPU fallback: without a CUDA device svo_create fails with SVO_ERR_NO_DEVICE.
- *   - all work is enqueued on one CUDA stream (svo_config.stream, or a private one).
+ *   - compute is enqueued on one CUDA stream (svo_config.stream, or a private one); host->device copies and the
+ *     kernels of svo_frames_prefetch run on private copy / ingest streams of the context, ordered with the main
+ *     stream by events.  Calls on one context must be serialised by the caller.
  */
 #ifndef SVO_B200_H
 #define SVO_B200_H
@@ -165,7 +167,8 @@ typedef struct {
     int32_t status;  /* Optimizer::Status of the last level */
     int32_t evaluations; /* residual evaluations over all levels */
     int32_t iterations;  /* solves over all levels */
-    int32_t reserved;
+    int32_t reserved;    /* diagnostics of the fast path: robust-scale selections served by the hot | cold << 8 |
+                            generic << 16 tier (0 from the generic kernel) */
 } svo_align_result;
 
 /* per-level diagnostics; same meaning and layout as orc_level_stats of the oracle */
