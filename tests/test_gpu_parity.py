@@ -644,3 +644,19 @@ def test_next_rows_golden_gpu(pkg, synth):
                     out[i] = dict(found=bool(r[j]["found"]), steps=int(r[j]["steps"]), px=r[j]["px"], depth=r[j]["depth"], score=r[j]["score"])
         return out
     _check_next_rows_golden(ssc, epi, synth)
+
+
+@pytest.mark.parametrize("min_level,max_level", [(1, 2), (0, 0), (2, 3), (3, 3)])
+def test_sparse_align_level_ranges(pkg, orc, synth, pair_cache, align_path, min_level, max_level):
+    """ImageAlignment(patchSize, minLevel, maxLevel, ...) with level ranges other than System's (0, 3)."""
+    pair = pair_cache(1, 333)
+    pyr = _pyrs(orc, pair)
+    rmse, T, status, lv = _oracle_align(orc, pair, pyr, orc.LM_FAITHFUL, min_level=min_level, max_level=max_level)
+    with _ctx(pkg, pair) as ctx:
+        ctx.upload(0, np.stack([pair["ref"], pair["cur"]]))
+        res, stats = ctx.sparse_align(_job(pkg, pair), pair["feats"], mode=pkg.capi.LM_FAITHFUL, min_level=min_level,
+                                      max_level=max_level)
+    assert len(lv) == max_level - min_level + 1 == stats.shape[1]
+    _check_levels(stats[0], lv, synth, True)
+    assert synth.rotation_angle(res[0]["T_cur"], T) < ROT_TOL and np.abs(res[0]["T_cur"][4:] - T[4:]).max() < TRANS_TOL
+    assert res[0]["evaluations"] == max_level - min_level + 1
