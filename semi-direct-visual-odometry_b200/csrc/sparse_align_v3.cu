@@ -726,6 +726,8 @@ __global__ void __launch_bounds__(NT, V3Occ<NT>::MINB) k_align_cluster(const V3A
                 set_Rt(ctrl);
             }
             __syncthreads();
+            // (bar.sync does not block at issue: a clock read here shows the barrier's ISSUE time; the wait for the
+            // single-thread solve is charged to the first dependent read of the next evaluation, phase [0])
             if (ctrl->done) break;
         }
 #ifdef SVO_PROFILE

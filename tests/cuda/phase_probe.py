@@ -16,7 +16,7 @@ for mode in (2, 1, 0):
         dd = ctx.debug_cycles()
         d = dd[:4]
         print("mode", mode, "evals", res[0]["evaluations"], "tiers", hex(res[0]["reserved"]))
-        print("per level [wait-solve+warp+sample, sigma, -, sums, reduce, -, n_eval]:")
+        print("per level [wait for the solve + warp + sample, sigma, -, sums, reduce, -, n_eval]:")
         print(d[:, :7])
         tot = d[:, :6].sum(0); n = d[:, 6].sum()
         print("cycles per evaluation:", (tot / n).round(0), "total", (tot.sum() / n).round(0), "=> us/eval %.2f" % (tot.sum() / n / 1965))
