@@ -5,8 +5,9 @@
  * photometric-alignment hot path of amin-abouee/semi-direct-visual-odometry
  * (image pyramid -> grid feature selection -> sparse SE3 image alignment ->
  * per-feature 2D alignment).  Each function cites the reference file:line it
- * follows.  Only tests/, __graft_entry__.smoke() and bench.py's CPU-baseline /
- * `--impl reference` legs may load it.  The product (libsvo_b200.so) never does.
+ * follows.  Only tests/, __graft_entry__.smoke(), bench.py's CPU-baseline /
+ * `--impl reference` legs and bench_configs.py's CPU baselines may load it.  The product
+ * (libsvo_b200.so) never does.
  *
  * PARITY PINNING: the reference's own tests hold no numeric golden vector for
  * this path and the reference cannot be compiled here
@@ -15,8 +16,13 @@
  *   - orc_project2d     the reference's own KAT, tests/test_camera.cpp:83-96
  *   - orc_image_jac     against central differences of the projection (python/symbol.py:50-60)
  *   - orc_se3_exp       against the closed form / scipy Rotation
+ *   - orc_sparse_align  (reference mode, four levels) against a second, independent numpy restatement to 1e-9 per
+ *                       level (tests/test_oracle_numerics.py::test_align_against_independent_numpy)
+ *   - orc_select_ssc, orc_epipolar_match  against direct python / numpy restatements and the golden vectors they
+ *                       produced (tests/golden/next_rows_golden.npz)
  * The alignment numerics (H, g, pose) are therefore "parity unpinned" against a
- * running reference binary; they are pinned only to this line-by-line restatement.
+ * running reference binary; they are pinned to this line-by-line restatement and to the
+ * independent restatements above.
  */
 #ifndef SVO_ORACLE_H
 #define SVO_ORACLE_H
