@@ -421,8 +421,8 @@ __global__ void __launch_bounds__(NT, V3Occ<NT>::MINB) k_align_cluster(const V3A
                     float px[G::FW];
 #pragma unroll
                     for (int c = 0; c < G::FW; c++) {
-                        const uint32_t b = c < 4 ? (lo >> (8 * c)) & 0xffu : (hi >> (8 * (c - 4))) & 0xffu;
-                        px[c]            = (float)b;
+                        // byte -> float without the conversion pipe: 0x4B0000bb is 2^23 + bb exactly
+                        px[c] = __uint_as_float(__byte_perm(c < 4 ? lo : hi, 0x4B000000u, 0x7650u | (uint32_t)(c & 3))) - 8388608.f;
                     }
                     float curRow[P];
 #pragma unroll
@@ -507,7 +507,7 @@ __global__ void __launch_bounds__(NT, V3Occ<NT>::MINB) k_align_cluster(const V3A
                         const float gr = gridS[(size_t)((y + 1) * G::GW + x + 2) * NT + f];
                         const float gu = gridS[(size_t)(y * G::GW + x + 1) * NT + f];
                         const float gd = gridS[(size_t)((y + 2) * G::GW + x + 1) * NT + f];
-                        const float gx = 0.5f * (gr - gl), gy = 0.5f * (gd - gu);
+                        const float gx = gr - gl, gy = gd - gu;  // twice the central differences: rescaled once per feature
                         float w        = 0.f;
                         if (fabsf(rr) <= cF) {
                             const float t = 1.f - rr * rr * ic2;
@@ -522,6 +522,7 @@ __global__ void __launch_bounds__(NT, V3Occ<NT>::MINB) k_align_cluster(const V3A
                         ch += wr * rr;
                     }
                 }
+                sxx *= 0.25f, sxy *= 0.25f, syy *= 0.25f, bx *= 0.5f, by *= 0.5f;
                 float A[6], B[6];
 #pragma unroll
                 for (int i = 0; i < 6; i++) {
