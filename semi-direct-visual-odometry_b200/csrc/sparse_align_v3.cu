@@ -211,7 +211,9 @@ __global__ void __launch_bounds__(NT, V3Occ<NT>::MINB) k_align_cluster(const V3A
     sc.tlast = clock64();
 #endif
     sp += cs_smem_bytes<NT>();
-    sp          = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(sp) + 15) & ~uintptr_t(15));
+    static_assert(((size_t)G::ROWW * NT * 4 + (size_t)3 * NT * 8 + cs_smem_bytes<NT>()) % 16 == 0, "carve-up keeps 16-byte alignment");
+    // (no integer round trip of the pointer: the compiler keeps the shared address space and emits LDS / STS for
+    // every access below instead of generic loads)
     double* red = reinterpret_cast<double*>(sp);  // [NW][32]
     sp += (size_t)NW * 32 * 8;
     double* xE = reinterpret_cast<double*>(sp);   // [2][32]
