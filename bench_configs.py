@@ -10,6 +10,7 @@
   config 2  the whole per-frame front end as one CUDA graph launch (svo_frontend_run)
   config 3  1,024 pairs x 1,000 features (bench.py --features 1000)
   config 5  (the first "next" component) depth-filter epipolar search: 2,000 seeds, 7x7 patches
+  config 7  (SURVEY 8f row f1) Map::reprojectMap: 1,000 candidates -> per-cell choice -> <= 151 feature alignments
   config 6  (SURVEY 8f row f2) FeatureSelection::gradientMagnitudeWithSSC on one frame, 250 / 1,000 candidates
 
 Prints one JSON line per measurement; every line carries `roofline` (algorithmic bytes of SURVEY 8d / device time
@@ -66,7 +67,7 @@ def wall_time(fn, reps):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="0,1,2,3,5,6")
+    ap.add_argument("--configs", default="0,1,2,3,5,6,7")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     want = set(int(x) for x in a.configs.split(","))
@@ -284,6 +285,38 @@ def main():
                   "roofline": roof(bytes_, e2e_us),
                   "cpu_baseline": {"value": cpu_us, "unit": "us", "cores": 1, "kind": "port",
                                    "sample": "first %d of the %d seeds through the oracle port, scaled to the batch" % (nsamp, ns)}})
+        # ---------------- "next" row f1: Map::reprojectMap ----------------
+        if 7 in want:
+            rng = np.random.default_rng(71)
+            f = pair["feats"][pair["feats"]["has_point"] != 0]
+            cands = np.zeros(2 * len(f), capi.REPROJ_CAND_DTYPE)
+            cands["ref_slot"] = 0
+            cands["ref_px"], cands["point"] = np.tile(f["px"], (2, 1)), np.tile(f["point"], (2, 1))
+            cands["type"] = rng.choice([0, 1, 2, 3], size=len(cands), p=[0.4, 0.1, 0.2, 0.3])
+            ncell = -(-w // 30) * -(-h // 30)
+            order = rng.permutation(ncell).astype(np.int32)
+            got, proj = ctx.reproject_map(1, pair["T_cur_true"], cands, 30, order)
+            for _ in range(3):
+                ctx.reproject_map(1, pair["T_cur_true"], cands, 30, order)
+            us = wall_time(lambda: ctx.reproject_map(1, pair["T_cur_true"], cands, 30, order), 30)
+            g0, g1 = ctx.download(0, 0, 1), ctx.download(1, 0, 1)
+            ts = []
+            for _ in range(3):
+                t0 = time.perf_counter()
+                ow, op = orc.reproject_map([g0, g1], g1, K, pair["T_cur_true"], cands, 30, order)
+                ts.append((time.perf_counter() - t0) * 1e6)
+            same = len(ow) == len(got) and np.array_equal(got["candidate"], ow[:, 1].astype(np.int32)) and \
+                np.abs(got["px"] - ow[:, 2:4]).max() < 1e-7
+            emit({"config": {"workload": "next row f1: Map::reprojectMap, %d candidates, cell 30, %d cells, %d matches (one 7x7 feature "
+                                         "alignment each)" % (len(cands), ncell, len(got))},
+                  "metric": "us_per_frame_reproject_map", "unit": "us", "higher_is_better": False, "value": us, "dtype": "f64",
+                  "identical_to_oracle": bool(same),
+                  "e2e": {"value": us, "unit": "us", "h2d_bytes_per_step": int(cands.nbytes + order.nbytes),
+                          "d2h_bytes_per_step": int(151 * 40 + len(cands)),
+                          "what": "svo_reproject_map (candidates + cell order H2D, four kernels, matches D2H), host wall clock, median of 30"},
+                  "roofline": roof(float(48 * len(cands) + 212 * len(got)), us),
+                  "cpu_baseline": {"value": float(np.median(ts)), "unit": "us", "cores": 1, "kind": "port",
+                                   "sample": "the same call through the oracle port, median of 3"}})
         # ---------------- "next" row f2: SSC feature selection ----------------
         if 6 in want:
             grad0 = ctx.download(0, 0, 1)

@@ -244,6 +244,34 @@ svo_status svo_feature_align_d2h(svo_ctx* ctx);
 svo_status svo_feature_align_fetch(svo_ctx* ctx, svo_fa_result* results);
 
 /* ---------------------------------------------------------------------------------------------
+ * Map::reprojectMap(refFrame, curFrame, overlapKeyFrames) (src/map.cpp:260-489), SURVEY 8(f) row f1: reprojectPoint
+ * (:492-504) for every candidate, the per-cell choice of reprojectCell (:506-579) and ONE FeatureAlignment launch.
+ * The caller lists the candidates in the reference's insertion order (features with a point of refFrame, then of its
+ * last keyframe, :462-476) and keeps the Point bookkeeping (m_lastProjectedKFId, m_succeededProjection, types).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t ref_slot;  /* candidate.m_feature->m_frame->m_imagePyramid */
+    int32_t type;      /* Point::PointType: 0 GOOD, 1 DELETED, 2 CANDIDATE, 3 UNKNOWN (include/point.hpp:18-24) */
+    double ref_px[2];  /* candidate.m_feature->m_pixelPosition */
+    double point[3];   /* candidate.m_point->m_position */
+} svo_reproj_candidate;
+typedef struct {
+    int32_t cell;      /* grid cell (row-major over ceil(h/cell) x ceil(w/cell)) */
+    int32_t candidate; /* index into the candidate array: the cell's first candidate after the sort by type, descending */
+    double px[2];      /* pixel position of the new Feature (:564): the projected pixel refined by FeatureAlignment::align */
+    double rmse;       /* align's return value (the reference ignores it: the match test is commented out, :528-549) */
+    int32_t status;
+    int32_t reserved;
+} svo_reproj_match;
+/* cell_order: Map::m_grid.m_cellOrders (a permutation of the cells, shuffled once at start-up, :237-247).  matches:
+ * capacity max_matches + 1 (the walk stops once m_matches exceeds max_matches = 150, :484-487), in cell_order order.
+ * projected (nullable, n bytes): reprojectPoint's return value per candidate (for overlapKeyFrames' counters).
+ * Synchronous. */
+svo_status svo_reproject_map(svo_ctx* ctx, int cur_slot, const double T_cur[7], const svo_reproj_candidate* cands, int n,
+                             int cell_size, const int32_t* cell_order, int n_cells, int max_matches, const svo_fa_params* fa,
+                             svo_reproj_match* matches, int* n_matches, uint8_t* projected);
+
+/* ---------------------------------------------------------------------------------------------
  * algorithm::matchEpipolarConstraint(refFrame, curFrame, refFeature, patchSize, initialDepth, minDepth, maxDepth,
  * estimatedDepth) (src/algorithm.cpp:412-551), batched: one item per depth-filter seed and frame, as
  * DepthEstimator::updateFilters calls it serially (src/depth_estimator.cpp:245).  Runs on IMAGE level 0.

@@ -358,5 +358,30 @@ def epipolar_match(ref_img, cur_img, K, T_rel, ref_px, ref_bearing, depth, min_d
     return dict(found=bool(out.found), depth=out.depth, px=np.array([out.px[0], out.px[1]]), score=out.score, steps=out.steps)
 
 
+REPROJ_CAND_DTYPE = np.dtype([("ref_slot", "<i4"), ("type", "<i4"), ("ref_px", "<f8", 2), ("point", "<f8", 3)])
+
+
+def reproject_map(grads, cur_grad, K, T_cur, cands, cell, cell_order, max_matches=150, patch_size=7, mode=LM_FAITHFUL, max_iter=20):
+    """Map::reprojectMap.  grads: list of gradient images indexed by the candidates' ref_slot.
+    Returns (matches (m, 6): cell, candidate, px x, px y, rmse, status; projected (n,) uint8)."""
+    grads = [_c8(g) for g in grads]
+    cur_grad = _c8(cur_grad)
+    h, w = cur_grad.shape
+    ptrs = (C.c_void_p * len(grads))(*[g.ctypes.data for g in grads])
+    cands = np.ascontiguousarray(cands, dtype=REPROJ_CAND_DTYPE).reshape(-1)
+    order = np.ascontiguousarray(cell_order, dtype=np.int32)
+    Kk, Tc = _f8(K, 4), _f8(T_cur, 7)
+    prm = FaParams(patch_size, mode, max_iter, MEDIAN_EXACT)
+    out = np.zeros((max_matches + 1, 6), np.float64)
+    proj = np.zeros(max(1, cands.size), np.uint8)
+    L = lib()
+    L.orc_reproject_map.restype = C.c_int
+    L.orc_reproject_map.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int,
+                                    C.c_void_p, C.c_int, C.c_int, C.POINTER(FaParams), C.c_void_p, C.c_void_p]
+    m = L.orc_reproject_map(ptrs, _p(cur_grad), w, h, _p(Kk), _p(Tc), _p(cands), cands.size, cell, _p(order), order.size, max_matches,
+                            C.byref(prm), _p(out), _p(proj))
+    return out[:m].copy(), proj[:cands.size].copy()
+
+
 def hardware_threads():
     return lib().orc_hardware_threads()

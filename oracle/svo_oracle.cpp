@@ -1239,6 +1239,52 @@ void orc_epipolar_match(const uint8_t* refImg, const uint8_t* curImg, int w, int
     }
 }
 
+// Map::reprojectMap, src/map.cpp:260-489
+int orc_reproject_map(const uint8_t* const* grads, const uint8_t* curGrad, int w, int h, const double K[4], const double Tcur7[7],
+                      const orc_reproj_candidate* cands, int n, int cell, const int32_t* cellOrder, int nCells, int maxMatches,
+                      const orc_fa_params* fa, double* matches, uint8_t* projected)
+{
+    const SE3 T        = fromParams(Tcur7);
+    const int gridCols = (int)std::ceil((double)w / cell);  // Map::initializeGrid, :226-227
+    std::vector<std::vector<int>> cells(nCells);
+    std::vector<double> px(2 * (size_t)std::max(n, 1));
+    for (int i = 0; i < n; i++) {  // reprojectPoint, :492-504, in insertion order
+        double pc[3];
+        act(T, cands[i].point, pc);
+        const double u = K[0] * (pc[0] / pc[2]) + K[2], v = K[1] * (pc[1] / pc[2]) + K[3];
+        px[2 * i] = u, px[2 * i + 1] = v;
+        const bool in = u >= 3 && v >= 3 && u < w - 3 && v < h - 3;
+        if (projected) projected[i] = in ? 1 : 0;
+        if (in) {
+            const int k = (int)v / cell * gridCols + (int)u / cell;
+            if (k >= 0 && k < nCells) cells[k].push_back(i);
+        }
+    }
+    int m = 0;
+    for (int i = 0; i < nCells; i++) {  // :475-488
+        const int idx = cellOrder[i];
+        if (idx < 0 || idx >= nCells) continue;
+        std::vector<int>& cl = cells[idx];
+        if (cl.empty()) continue;
+        // reprojectCell, :506-579: sort by type, descending (stable here); the first non-DELETED candidate is aligned and kept
+        std::stable_sort(cl.begin(), cl.end(), [&](int a, int b) { return cands[a].type > cands[b].type; });
+        bool matched = false;
+        for (int ci : cl) {
+            if (cands[ci].type == 1) continue;  // Point::PointType::DELETED
+            double p[2] = {px[2 * ci], px[2 * ci + 1]};
+            int32_t st = 0, it = 0;
+            const double err = orc_feature_align(grads[cands[ci].ref_slot], curGrad, w, h, cands[ci].ref_px, nullptr, p, fa, &st, &it);
+            double* o = matches + 6 * (size_t)m;
+            o[0] = idx, o[1] = ci, o[2] = p[0], o[3] = p[1], o[4] = err, o[5] = st;
+            matched = true;
+            break;
+        }
+        if (matched) m++;
+        if (m > maxMatches) break;  // :484-487
+    }
+    return m;
+}
+
 int orc_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }
 
 }  // extern "C"

@@ -180,6 +180,20 @@ void orc_epipolar_match(const uint8_t* ref_img, const uint8_t* cur_img, int w, i
                         const double ref_px[2], const double ref_bearing[3], double depth, double min_depth, double max_depth,
                         const orc_epi_params* params, orc_epi_result* out);
 
+/* ---- Map::reprojectMap (src/map.cpp:260-489): reprojectPoint (:492-504) per candidate, reprojectCell (:506-579) per
+ * cell in cell_order; equal Point types keep their insertion order (the reference's std::sort is unstable).
+ * grads: gradient level 0 of the frame in each slot (w x h, pitch w), indexed by the candidates' ref_slot; cur_grad: the
+ * new frame's.  matches: (cell, candidate, px x, px y, rmse, status) per match as doubles, capacity max_matches + 1.
+ * Returns the number of matches. ---- */
+typedef struct {
+    int32_t ref_slot, type;
+    double ref_px[2];
+    double point[3];
+} orc_reproj_candidate;
+int orc_reproject_map(const uint8_t* const* grads, const uint8_t* cur_grad, int w, int h, const double K[4], const double T_cur[7],
+                      const orc_reproj_candidate* cands, int n, int cell, const int32_t* cell_order, int n_cells, int max_matches,
+                      const orc_fa_params* fa, double* matches, uint8_t* projected);
+
 int orc_hardware_threads(void);
 
 #ifdef __cplusplus

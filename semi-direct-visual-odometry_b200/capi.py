@@ -26,7 +26,7 @@ SYMBOLS = [
     "svo_sparse_align_results_device", "svo_debug_cycles",
     "svo_feature_align", "svo_feature_align_stage", "svo_feature_align_h2d", "svo_feature_align_launch",
     "svo_feature_align_d2h", "svo_feature_align_fetch", "svo_frontend_run", "svo_frontend_image_buffer",
-    "svo_epipolar_match", "svo_select_ssc",
+    "svo_epipolar_match", "svo_select_ssc", "svo_reproject_map",
 ]
 
 
@@ -64,6 +64,9 @@ ALIGN_STATS_DTYPE = np.dtype([("H", "<f8", (6, 6)), ("g", "<f8", 6), ("dx", "<f8
                               ("status", "<i4"), ("iterations", "<i4"), ("evaluations", "<i4")])
 FA_ITEM_DTYPE = np.dtype([("ref_slot", "<i4"), ("cur_slot", "<i4"), ("ref_px", "<f8", 2), ("px", "<f8", 2),
                           ("A", "<f8", 4), ("use_affine", "<i4"), ("reserved", "<i4")])
+REPROJ_CAND_DTYPE = np.dtype([("ref_slot", "<i4"), ("type", "<i4"), ("ref_px", "<f8", 2), ("point", "<f8", 3)])
+REPROJ_MATCH_DTYPE = np.dtype([("cell", "<i4"), ("candidate", "<i4"), ("px", "<f8", 2), ("rmse", "<f8"), ("status", "<i4"),
+                               ("reserved", "<i4")])
 EPI_ITEM_DTYPE = np.dtype([("ref_slot", "<i4"), ("cur_slot", "<i4"), ("T_rel", "<f8", 7), ("px", "<f8", 2), ("bearing", "<f8", 3),
                            ("depth", "<f8"), ("min_depth", "<f8"), ("max_depth", "<f8")])
 EPI_RESULT_DTYPE = np.dtype([("depth", "<f8"), ("px", "<f8", 2), ("score", "<f8"), ("found", "<i4"), ("steps", "<i4")])
@@ -127,6 +130,7 @@ def load():
     L.svo_sparse_align_results_device.argtypes = [vp]
     L.svo_debug_cycles.argtypes = [vp, vp]
     L.svo_sparse_align_results_device.restype = vp
+    L.svo_reproject_map.argtypes = [vp, i, vp, vp, i, i, vp, i, i, C.POINTER(FaParams), vp, C.POINTER(i), vp]
     L.svo_select_ssc.argtypes = [vp, i, C.c_uint32, i, i, vp, i, vp, i, C.POINTER(i), vp]
     L.svo_epipolar_match.argtypes = [vp, vp, i, C.POINTER(EpiParams), vp]
     L.svo_frontend_run.argtypes = [vp, C.POINTER(FrontendParams), vp, i, vp, vp, i, vp, vp, vp, i, vp]
@@ -331,6 +335,19 @@ class Context:
     @property
     def results_device_ptr(self):
         return self.L.svo_sparse_align_results_device(self.h)
+
+    # ---- Map::reprojectMap: projection, per-cell choice, one FeatureAlignment launch ----
+    def reproject_map(self, cur_slot, T_cur, cands, cell, cell_order, max_matches=150, patch_size=7, mode=LM_FAITHFUL, max_iter=20):
+        cands = np.ascontiguousarray(cands, dtype=REPROJ_CAND_DTYPE).reshape(-1)
+        order = np.ascontiguousarray(cell_order, dtype=np.int32)
+        T = np.ascontiguousarray(T_cur, dtype=np.float64)
+        prm = FaParams(patch_size, mode, max_iter, 0)
+        out = np.zeros(max_matches + 1, REPROJ_MATCH_DTYPE)
+        proj = np.zeros(max(1, cands.size), np.uint8)
+        n = C.c_int()
+        self._check(self.L.svo_reproject_map(self.h, cur_slot, _ptr(T), _ptr(cands), cands.size, cell, _ptr(order), order.size,
+                                             max_matches, C.byref(prm), _ptr(out), C.byref(n), _ptr(proj)))
+        return out[:n.value].copy(), proj[:cands.size].copy()
 
     # ---- algorithm::matchEpipolarConstraint, batched over depth-filter seeds ----
     def epipolar_match(self, items, patch_size=7, mean_mode=MEAN_EIGEN_U8):

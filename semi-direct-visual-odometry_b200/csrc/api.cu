@@ -69,6 +69,13 @@ void release(svo_ctx* ctx)
     cudaFree(ctx->d_scratch_jac);
     cudaFree(ctx->d_scratch2);
     cudaFree(ctx->d_dbg);
+    cudaFree(ctx->d_rp_cands);
+    cudaFree(ctx->d_rp_matches);
+    cudaFreeHost(ctx->h_rp_matches);
+    cudaFree(ctx->d_rp_order);
+    cudaFree(ctx->d_rp_px);
+    cudaFree(ctx->d_rp_projected);
+    cudaFreeHost(ctx->h_rp_projected);
     cudaFreeHost(ctx->h_epi_items);
     cudaFreeHost(ctx->h_epi_results);
     cudaFree(ctx->d_epi_items);
@@ -703,6 +710,54 @@ svo_status svo_feature_align(svo_ctx* ctx, const svo_fa_item* items, int n, cons
     if ((st = svo_feature_align_launch(ctx)) != SVO_OK) return st;
     if ((st = svo_feature_align_d2h(ctx)) != SVO_OK) return st;
     return svo_feature_align_fetch(ctx, results);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Map::reprojectMap
+// ------------------------------------------------------------------------------------------------
+svo_status svo_reproject_map(svo_ctx* ctx, int cur_slot, const double T_cur[7], const svo_reproj_candidate* cands, int n, int cell_size,
+                             const int32_t* cell_order, int n_cells, int max_matches, const svo_fa_params* fa,
+                             svo_reproj_match* matches, int* n_matches, uint8_t* projected)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    if (!T_cur || n < 0 || (n > 0 && !cands) || !cell_order || !fa || !matches || !n_matches || cell_size < 4 || max_matches < 0 ||
+        bad_slot(ctx, cur_slot))
+        SVO_FAIL(SVO_ERR_INVALID, "svo_reproject_map: bad arguments");
+    const LevelGeom& g = ctx->arena.geom[0];
+    const int gridCols = (g.w + cell_size - 1) / cell_size, gridRows = (g.h + cell_size - 1) / cell_size;  // Map::initializeGrid, :226-227
+    if (n_cells != gridCols * gridRows) SVO_FAIL(SVO_ERR_INVALID, "svo_reproject_map: cell_order must list ceil(w/cell) * ceil(h/cell) cells");
+    const int maxItems = max_matches + 1;  // the walk stops once m_matches EXCEEDS max_matches (:484-487)
+    if (n > ctx->cfg.max_fa_items || maxItems > ctx->cfg.max_fa_items || n_cells > ctx->sel_cap_cells)
+        SVO_FAIL(SVO_ERR_CAPACITY, "svo_reproject_map: more candidates / matches than max_fa_items, or more cells than the context holds");
+    if (fa->patch_size < 1 || fa->patch_size > 8 || fa->mode < SVO_LM_FAITHFUL || fa->mode > SVO_GN)
+        SVO_FAIL(SVO_ERR_INVALID, "svo_reproject_map: bad FeatureAlignment parameters");
+    for (int i = 0; i < n; i++)
+        if (bad_slot(ctx, cands[i].ref_slot)) SVO_FAIL(SVO_ERR_INVALID, "svo_reproject_map: candidate frame slot out of range");
+    SVO_CUDA(cudaSetDevice(ctx->cfg.device));
+    if (!ctx->d_rp_cands) {
+        const size_t nf = (size_t)std::max(1, ctx->cfg.max_fa_items);
+        SVO_CUDA(cudaMalloc(&ctx->d_rp_cands, sizeof(svo_reproj_candidate) * nf));
+        SVO_CUDA(cudaMalloc(&ctx->d_rp_matches, sizeof(svo_reproj_match) * nf));
+        SVO_CUDA(cudaHostAlloc(&ctx->h_rp_matches, sizeof(svo_reproj_match) * nf, cudaHostAllocDefault));
+        SVO_CUDA(cudaMalloc(&ctx->d_rp_order, sizeof(int32_t) * ctx->sel_cap_cells));
+        SVO_CUDA(cudaMalloc(&ctx->d_rp_px, sizeof(double) * 2 * nf));
+        SVO_CUDA(cudaMalloc(&ctx->d_rp_projected, nf));
+        SVO_CUDA(cudaHostAlloc(&ctx->h_rp_projected, nf, cudaHostAllocDefault));
+    }
+    svo_status st = wait_ingest(ctx);
+    if (st != SVO_OK) return st;
+    SVO_CUDA(cudaStreamSynchronize(ctx->stream));
+    if (n) SVO_CUDA(cudaMemcpyAsync(ctx->d_rp_cands, cands, sizeof(svo_reproj_candidate) * n, cudaMemcpyHostToDevice, ctx->stream));
+    SVO_CUDA(cudaMemcpyAsync(ctx->d_rp_order, cell_order, sizeof(int32_t) * n_cells, cudaMemcpyHostToDevice, ctx->stream));
+    if ((st = launch_reproject_map(ctx, cur_slot, T_cur, n, cell_size, n_cells, gridCols, maxItems, *fa)) != SVO_OK) return st;
+    SVO_CUDA(cudaMemcpyAsync(ctx->h_sel_count, ctx->d_sel_count, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SVO_CUDA(cudaMemcpyAsync(ctx->h_rp_matches, ctx->d_rp_matches, sizeof(svo_reproj_match) * maxItems, cudaMemcpyDeviceToHost, ctx->stream));
+    if (n) SVO_CUDA(cudaMemcpyAsync(ctx->h_rp_projected, ctx->d_rp_projected, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    SVO_CUDA(cudaStreamSynchronize(ctx->stream));
+    *n_matches = *ctx->h_sel_count;
+    std::memcpy(matches, ctx->h_rp_matches, sizeof(svo_reproj_match) * *n_matches);
+    if (projected && n) std::memcpy(projected, ctx->h_rp_projected, (size_t)n);
+    return SVO_OK;
 }
 
 // ------------------------------------------------------------------------------------------------

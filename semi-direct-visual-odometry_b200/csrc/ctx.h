@@ -113,6 +113,15 @@ struct svo_ctx {
     svo_align_result* h_fe_align;  // pinned
     svo_fa_result* h_fe_fa;        // pinned, max_features records
 
+    // Map::reprojectMap batch (svo_reproject_map), capacity max_fa_items candidates / sel_cap_cells cells
+    svo_reproj_candidate* d_rp_cands;
+    svo_reproj_match* d_rp_matches;
+    svo_reproj_match* h_rp_matches;  // pinned
+    int32_t* d_rp_order;
+    double* d_rp_px;
+    uint8_t* d_rp_projected;
+    uint8_t* h_rp_projected;         // pinned
+
     // epipolar search batch (depth-filter seeds), capacity max_fa_items
     svo_epi_item* h_epi_items;      // pinned
     svo_epi_result* h_epi_results;  // pinned
@@ -166,6 +175,8 @@ svo_status launch_select_ssc(svo_ctx* ctx, int slot, uint32_t thr, int numCandid
                              bool useBucketing, int maxOut);
 svo_status launch_sparse_align(svo_ctx* ctx);
 svo_status launch_feature_align(svo_ctx* ctx);
+svo_status launch_reproject_map(svo_ctx* ctx, int curSlot, const double T[7], int n, int cell, int nCells, int gridCols, int maxItems,
+                                const svo_fa_params& fa);
 svo_status launch_epipolar_match(svo_ctx* ctx, int n, const svo_epi_params& prm);
 void frontend_release(svo_ctx* ctx);
 size_t sparse_align_smem_bytes(int nthreads, int max_features, int patch_area);

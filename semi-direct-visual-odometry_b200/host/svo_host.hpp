@@ -638,4 +638,51 @@ inline bool matchEpipolarConstraint(const std::shared_ptr<Frame>& refFrame, cons
 }
 }  // namespace algorithm
 
+// ------------------------------------------------------------------------------------------------------------
+// Map::reprojectMap (src/map.cpp:260-489) as one batched pass: reprojectPoint for every candidate, reprojectCell's choice
+// per grid cell, one FeatureAlignment launch.  The caller (the reference's Map) keeps its Point bookkeeping: it lists
+// the candidates in insertion order (features with a point of refFrame, then of its last keyframe, :462-476) and applies
+// the matches (:551-576: new Feature at `pixelPosition`, m_succeededProjection, type promotion).
+struct ReprojectionCandidate {
+    std::shared_ptr<Feature> feature;  // candidate.m_feature (its m_point is candidate.m_point)
+    uint32_t pointType;                // Point::PointType: 0 GOOD, 1 DELETED, 2 CANDIDATE, 3 UNKNOWN
+};
+struct ReprojectionMatch {
+    int32_t cell;
+    size_t candidate;     // index into the candidate list
+    Vec2 pixelPosition;   // where the new Feature goes (:564)
+    double error;         // FeatureAlignment::align's return value (ignored by the reference)
+};
+inline std::vector<ReprojectionMatch> reprojectMap(const std::shared_ptr<Frame>& curFrame, const std::vector<ReprojectionCandidate>& candidates,
+                                                   uint32_t cellSize, const std::vector<int32_t>& cellOrders, uint32_t maxMatches = 150,
+                                                   std::vector<bool>* projected = nullptr)
+{
+    const auto& dev = curFrame->m_imagePyramid.device();
+    std::vector<svo_reproj_candidate> in(candidates.size());
+    for (size_t i = 0; i < candidates.size(); i++) {
+        const auto& f = candidates[i].feature;
+        if (!f->m_point) throw std::invalid_argument("reprojectMap: candidate feature without a 3D point");
+        svo_reproj_candidate c{};
+        c.ref_slot  = f->m_frame->m_imagePyramid.slot();
+        c.type      = (int32_t)candidates[i].pointType;
+        c.ref_px[0] = f->m_pixelPosition.x();
+        c.ref_px[1] = f->m_pixelPosition.y();
+        for (int k = 0; k < 3; k++) c.point[k] = f->m_point->m_position[k];
+        in[i] = c;
+    }
+    double T[7];
+    curFrame->m_absPose.params(T);
+    svo_fa_params fa{7, SVO_LM_FAITHFUL, 20, 0};  // Map::m_alignment = FeatureAlignment(7, 0, 3), src/map.cpp:18
+    std::vector<svo_reproj_match> out(maxMatches + 1);
+    std::vector<uint8_t> proj(candidates.size() ? candidates.size() : 1);
+    int n = 0;
+    dev->check(svo_reproject_map(dev->ctx(), curFrame->m_imagePyramid.slot(), T, in.data(), (int)in.size(), (int)cellSize,
+                                 cellOrders.data(), (int)cellOrders.size(), (int)maxMatches, &fa, out.data(), &n, proj.data()),
+               "svo_reproject_map");
+    if (projected) projected->assign(proj.begin(), proj.begin() + candidates.size());
+    std::vector<ReprojectionMatch> res;
+    for (int i = 0; i < n; i++) res.push_back({out[i].cell, (size_t)out[i].candidate, Vec2(out[i].px[0], out[i].px[1]), out[i].rmse});
+    return res;
+}
+
 }  // namespace svo

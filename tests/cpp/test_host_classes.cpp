@@ -300,6 +300,47 @@ int main(int argc, char** argv)
         CHECK(ok == found[0] && (!ok || est == depth[0]));
         std::printf("matchEpipolarConstraint: %zu of %zu seeds matched\n", nFound, seeds.size());
     }
+    // ---- Map::reprojectMap (one batched pass) vs the oracle: same cells, same candidates, same refined positions ----
+    {
+        std::vector<ReprojectionCandidate> cands;
+        std::vector<orc_reproj_candidate> oc;
+        for (size_t i = 0; i < ref->m_features.size(); i++) {
+            const auto& f = ref->m_features[i];
+            if (!f->m_point) continue;
+            const uint32_t type = (uint32_t)((i * 7) % 4);  // GOOD / DELETED / CANDIDATE / UNKNOWN mixed
+            cands.push_back({f, type});
+            orc_reproj_candidate c{};
+            c.ref_slot = 0;
+            c.type     = (int32_t)type;
+            c.ref_px[0] = f->m_pixelPosition.x(), c.ref_px[1] = f->m_pixelPosition.y();
+            for (int k = 0; k < 3; k++) c.point[k] = f->m_point->m_position[k];
+            oc.push_back(c);
+        }
+        const int cell = 30, cols = (w + cell - 1) / cell, rows = (h + cell - 1) / cell;
+        std::vector<int32_t> order(cols * rows);
+        for (size_t i = 0; i < order.size(); i++) order[i] = (int32_t)((i * 37) % order.size());  // 37 is coprime to the cell count below
+        CHECK(order.size() % 37 != 0);
+        std::vector<bool> projected;
+        const auto matches = reprojectMap(cur, cands, cell, order, 150, &projected);
+        const Mat8& gr = ref->m_imagePyramid.getGradientAtLevel(0);
+        const Mat8& gc = cur->m_imagePyramid.getGradientAtLevel(0);
+        const uint8_t* grads[1] = {gr.ptr()};
+        double T[7];
+        cur->m_absPose.params(T);
+        orc_fa_params fa{7, ORC_LM_FAITHFUL, 20, ORC_MEDIAN_EXACT};
+        std::vector<double> om(151 * 6);
+        std::vector<uint8_t> op(oc.size());
+        const int m = orc_reproject_map(grads, gc.ptr(), w, h, K, T, oc.data(), (int)oc.size(), cell, order.data(), (int)order.size(), 150, &fa,
+                                        om.data(), op.data());
+        CHECK((size_t)m == matches.size() && m > 10);
+        for (size_t i = 0; i < oc.size(); i++) CHECK(projected[i] == (op[i] != 0));
+        for (int i = 0; i < m && (size_t)i < matches.size(); i++) {
+            CHECK(matches[i].cell == (int32_t)om[i * 6] && matches[i].candidate == (size_t)om[i * 6 + 1]);
+            CHECK(std::fabs(matches[i].pixelPosition.x() - om[i * 6 + 2]) < 1e-7 && std::fabs(matches[i].pixelPosition.y() - om[i * 6 + 3]) < 1e-7);
+            CHECK(cands[matches[i].candidate].pointType != 1);
+        }
+        std::printf("reprojectMap: %zu candidates -> %zu matches\n", cands.size(), matches.size());
+    }
     Device::current().reset();
     std::printf(g_fail ? "FAILED (%d checks)\n" : "ALL HOST-CLASS CHECKS PASSED\n", g_fail);
     return g_fail ? 1 : 0;

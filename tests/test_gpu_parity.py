@@ -660,3 +660,44 @@ def test_sparse_align_level_ranges(pkg, orc, synth, pair_cache, align_path, min_
     _check_levels(stats[0], lv, synth, True)
     assert synth.rotation_angle(res[0]["T_cur"], T) < ROT_TOL and np.abs(res[0]["T_cur"][4:] - T[4:]).max() < TRANS_TOL
     assert res[0]["evaluations"] == max_level - min_level + 1
+
+
+# ------------------------------------------------------------------------------------------------
+# Map::reprojectMap: projection, per-cell choice, one FeatureAlignment launch
+# ------------------------------------------------------------------------------------------------
+def _reproj_cands(pkg, pair, rng, dup=2):
+    """candidates in the reference's insertion order: refFrame's features, then its last keyframe's (the same plane
+    points again, seen from the keyframe image in slot 2), with mixed Point types incl. DELETED"""
+    f = pair["feats"][pair["feats"]["has_point"] != 0]
+    c = np.zeros(len(f) * dup, pkg.capi.REPROJ_CAND_DTYPE)
+    for d in range(dup):
+        s = slice(d * len(f), (d + 1) * len(f))
+        c["ref_slot"][s] = 0 if d == 0 else 2
+        c["ref_px"][s], c["point"][s] = f["px"], f["point"]
+    c["type"] = rng.choice([0, 1, 2, 3], size=len(c), p=[0.4, 0.1, 0.2, 0.3])
+    return c
+
+
+@pytest.mark.parametrize("cell,max_matches", [(30, 150), (30, 40), (64, 150), (16, 150)])
+def test_reproject_map_parity(pkg, orc, synth, pair_cache, cell, max_matches):
+    pair = pair_cache(10, 400)
+    rng = np.random.default_rng(cell + max_matches)
+    cands = _reproj_cands(pkg, pair, rng)
+    h, w = pair["h"], pair["w"]
+    n_cells = -(-w // cell) * -(-h // cell)
+    order = rng.permutation(n_cells).astype(np.int32)          # Map::m_grid.m_cellOrders: shuffled once
+    T = pair["T_cur_true"]
+    with _ctx(pkg, pair) as ctx:
+        ctx.upload(0, np.stack([pair["ref"], pair["cur"], pair["ref"]]))   # slot 2: the "last keyframe" image
+        got, gproj = ctx.reproject_map(1, T, cands, cell, order, max_matches=max_matches)
+        gref, gcur = ctx.download(0, 0, 1), ctx.download(1, 0, 1)
+    want, wproj = orc.reproject_map([gref, gcur, gref], gcur, pair["K"], T, cands, cell, order, max_matches=max_matches)
+    assert np.array_equal(gproj, wproj)
+    assert len(got) == len(want) and len(got) <= max_matches + 1
+    assert np.array_equal(got["cell"], want[:, 0].astype(np.int32)) and np.array_equal(got["candidate"], want[:, 1].astype(np.int32))
+    assert np.abs(got["px"] - want[:, 2:4]).max() < 1e-7
+    assert np.allclose(got["rmse"], want[:, 4], rtol=1e-7, equal_nan=True) and np.array_equal(got["status"], want[:, 5].astype(np.int32))
+    # one match per cell, never a DELETED point, and the highest type of the cell
+    assert len(set(got["cell"])) == len(got) and (cands["type"][got["candidate"]] != 1).all()
+    if max_matches == 40:
+        assert len(got) == 41                                   # the walk stops once m_matches exceeds max_matches

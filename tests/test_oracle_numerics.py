@@ -553,3 +553,59 @@ def test_align_against_independent_numpy(orc, pkg, n_features):
         Ro = Rotation.from_quat(o["pose_after"][:4]).as_matrix()
         assert np.abs(Ro - w_["pose"][:3, :3]).max() < 1e-9 and np.abs(o["pose_after"][4:] - w_["pose"][:3, 3]).max() < 1e-9, s
     assert abs(rmse - want[-1]["rmse"]) <= 1e-9 * rmse
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# Row f1: an independent Python restatement of Map::reprojectMap's walk (src/map.cpp:462-489 fill the cells through
+# reprojectPoint :491-503; :474-488 visit the cells in m_cellOrders; reprojectCell :505-576 sorts each cell by point type,
+# skips DELETED points and accepts the first other candidate after FeatureAlignment::align, whatever it returned).
+def _py_reproject_map(orc, grads, cur_grad, K, T_cur, cands, cell, order, max_matches):
+    h, w = cur_grad.shape
+    cols = -(-w // cell)
+    cells = {}
+    projected = np.zeros(len(cands), np.uint8)
+    pix = []
+    for i, c in enumerate(cands):
+        px = orc.project2d(K, orc.se3_act(T_cur, c["point"]))                      # Frame::world2image, src/frame.cpp:83-101
+        pix.append(px)
+        if px[0] >= 3 and px[1] >= 3 and px[0] < w - 3 and px[1] < h - 3:          # PinholeCamera::isInFrame(px, 3), :163-169
+            cells.setdefault(int(px[1]) // cell * cols + int(px[0]) // cell, []).append(i)
+            projected[i] = 1
+    out = []
+    for k in order:
+        got = False
+        for i in sorted(cells.get(int(k), []), key=lambda i: -int(cands["type"][i])):   # sorted() is stable, like the oracle's choice
+            if cands["type"][i] == 1:                                              # Point::PointType::DELETED
+                continue
+            rmse, px, st, _ = orc.feature_align(grads[cands["ref_slot"][i]], cur_grad, cands["ref_px"][i], pix[i])
+            out.append((int(k), i, px[0], px[1], rmse, st))
+            got = True
+            break
+        if got and len(out) > max_matches:                                         # `if ( m_matches > 150 ) break;`
+            break
+    return out, projected
+
+
+@pytest.mark.parametrize("cell,max_matches", [(30, 150), (48, 25)])
+def test_reproject_map_against_python(orc, pkg, pair_cache, cell, max_matches):
+    pair = pair_cache(10, 300)
+    rng = np.random.default_rng(5 + cell)
+    f = pair["feats"][pair["feats"]["has_point"] != 0]
+    cands = np.zeros(2 * len(f), pkg.capi.REPROJ_CAND_DTYPE)
+    cands["ref_slot"] = np.repeat([0, 1], len(f))
+    cands["ref_px"], cands["point"] = np.tile(f["px"], (2, 1)), np.tile(f["point"], (2, 1))
+    cands["point"][::7] += 40.0                                                    # some points leave the frame
+    cands["type"] = rng.choice([0, 1, 2, 3], size=len(cands), p=[0.4, 0.1, 0.2, 0.3])
+    h, w = pair["h"], pair["w"]
+    gref, gcur = orc.abs_gradient(pair["ref"]), orc.abs_gradient(pair["cur"])
+    order = rng.permutation(-(-w // cell) * -(-h // cell)).astype(np.int32)
+    T = pair["T_cur_true"]
+    want, wproj = _py_reproject_map(orc, [gref, gref], gcur, pair["K"], T, cands, cell, order, max_matches)
+    got, gproj = orc.reproject_map([gref, gref], gcur, pair["K"], T, cands, cell, order, max_matches=max_matches)
+    assert np.array_equal(gproj, wproj) and 0 < wproj.sum() < len(cands)
+    assert len(got) == len(want) and len(got) > 10
+    want = np.array(want, np.float64)
+    assert np.array_equal(got[:, :2], want[:, :2]) and np.array_equal(got[:, 5], want[:, 5])
+    assert np.array_equal(got[:, 2:5], want[:, 2:5], equal_nan=True)
+    if max_matches == 25:
+        assert len(got) == 26
