@@ -10,6 +10,7 @@
   config 2  the whole per-frame front end as one CUDA graph launch (svo_frontend_run)
   config 3  1,024 pairs x 1,000 features (bench.py --features 1000)
   config 5  (the first "next" component) depth-filter epipolar search: 2,000 seeds, 7x7 patches
+  config 8  (SURVEY 8f row f4) computeOpticalFlowSparse's tracker: cv::calcOpticalFlowPyrLK, 500 / 2,000 points, 11x11, 4 levels
   config 7  (SURVEY 8f row f1) Map::reprojectMap: 1,000 candidates -> per-cell choice -> <= 151 feature alignments
   config 6  (SURVEY 8f row f2) FeatureSelection::gradientMagnitudeWithSSC on one frame, 250 / 1,000 candidates
 
@@ -67,7 +68,7 @@ def wall_time(fn, reps):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="0,1,2,3,5,6,7")
+    ap.add_argument("--configs", default="0,1,2,3,5,6,7,8")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     want = set(int(x) for x in a.configs.split(","))
@@ -285,6 +286,57 @@ def main():
                   "roofline": roof(bytes_, e2e_us),
                   "cpu_baseline": {"value": cpu_us, "unit": "us", "cores": 1, "kind": "port",
                                    "sample": "first %d of the %d seeds through the oracle port, scaled to the batch" % (nsamp, ns)}})
+        # ---------------- "next" row f4: pyramidal Lucas-Kanade (initialisation) ----------------
+        if 8 in want:
+            try:
+                import cv2
+            except ImportError:
+                cv2 = None
+            rng = np.random.default_rng(81)
+            for npts in (500, 2000):
+                base = pair["feats"]["px"][: pair["n_ref"]].astype(np.float32)
+                pts = base if npts <= len(base) else np.concatenate(
+                    [base, rng.uniform([8, 8], [w - 9, h - 9], size=(npts - len(base), 2)).astype(np.float32)])
+                pts = np.ascontiguousarray(pts[:npts])
+                got, gst, gerr = ctx.klt_track(0, 1, pts, pts, win=11)
+                for _ in range(3):
+                    ctx.klt_track(0, 1, pts, pts, win=11)
+                us = wall_time(lambda: ctx.klt_track(0, 1, pts, pts, win=11), 30)
+                ts = []
+                for _ in range(3):
+                    t0 = time.perf_counter()
+                    ow, ost, oerr, _ = orc.klt_track(pair["ref"], pair["cur"], pts, pts, win=11)
+                    ts.append((time.perf_counter() - t0) * 1e6)
+                both = (gst == 1) & (ost == 1)
+                d = np.abs(got[both] - ow[both]).max(axis=1)
+                cpu = {"value": float(np.median(ts)), "unit": "us", "cores": 1, "kind": "port",
+                       "sample": "the same call through the oracle port (pyramids + derivative images rebuilt per call, as OpenCV does), median of 3"}
+                if cv2 is not None:
+                    crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, 30, 1e-4)
+                    tc = []
+                    for _ in range(7):
+                        t0 = time.perf_counter()
+                        cw, cst, _ = cv2.calcOpticalFlowPyrLK(pair["ref"], pair["cur"], pts.copy(), pts.copy(), winSize=(11, 11), maxLevel=3,
+                                                              criteria=crit, flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+                        tc.append((time.perf_counter() - t0) * 1e6)
+                    cpu = {"value": float(np.median(tc)), "unit": "us", "cores": cv2.getNumThreads(), "kind": "reference",
+                           "sample": "cv2.calcOpticalFlowPyrLK %s of this image (the library call the reference makes), median of 7; "
+                                     "the oracle port takes %.0f us on one thread" % (cv2.__version__, float(np.median(ts)))}
+                    cb = (gst == 1) & (cst.reshape(-1) == 1)
+                    cd = np.abs(got[cb] - cw[cb]).max(axis=1)
+                # algorithmic bytes: per point and level the (win+3)^2 reference neighbourhood once + (win+1)^2 current-image bytes
+                # per iteration (~8 iterations per level on this data); all of it L1/L2 resident
+                emit({"config": {"workload": "next row f4: calcOpticalFlowPyrLK, %d points, 11x11 window, 4 levels, <= 30 iterations, eps 1e-4"
+                                             % npts},
+                      "metric": "us_per_frame_klt", "unit": "us", "higher_is_better": False, "value": us, "dtype": "i32/f32",
+                      "parity": {"status_mismatches_vs_oracle": int((gst != ost).sum()), "tracked": int(both.sum()),
+                                 "px_diff_q99_vs_oracle": float(np.quantile(d, 0.99)), "px_diff_max_vs_oracle": float(d.max()),
+                                 "px_diff_q99_vs_cv2": float(np.quantile(cd, 0.99)) if cv2 is not None else None},
+                      "e2e": {"value": us, "unit": "us", "h2d_bytes_per_step": int(2 * pts.nbytes), "d2h_bytes_per_step": int(pts.nbytes + 5 * npts),
+                              "what": "svo_klt_track (points H2D, one kernel for all levels, positions/status/error D2H), host wall clock, "
+                                      "median of 30; the pyramids are the frame slots' own"},
+                      "roofline": roof(float(npts * 4 * (14 * 14 + 8 * 12 * 12)), us),
+                      "cpu_baseline": cpu})
         # ---------------- "next" row f1: Map::reprojectMap ----------------
         if 7 in want:
             rng = np.random.default_rng(71)

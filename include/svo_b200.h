@@ -305,6 +305,28 @@ svo_status svo_epipolar_match(svo_ctx* ctx, const svo_epi_item* items, int n, co
                               svo_epi_result* results);
 
 /* ---------------------------------------------------------------------------------------------
+ * Next row f4: the tracker of algorithm::computeOpticalFlowSparse (src/algorithm.cpp:29-107, System's initialisation,
+ * src/system.cpp:129; the same call at src/map.cpp:322,403), i.e.
+ *   cv::calcOpticalFlowPyrLK(refImg, curImg, refPoints, curPoints, status, errors, cv::Size(win, win), 3,
+ *                            cv::TermCriteria(COUNT + EPS, 30, 1e-4), cv::OPTFLOW_USE_INITIAL_FLOW)
+ * on the image pyramids of two frame slots (OpenCV rebuilds the same cv::pyrDown pyramids on every call).
+ * prev_pts / next_pts: n (x, y) float pairs (cv::Point2f); next_pts is the initial guess on entry when use_initial_flow
+ * and the tracked position on return (also for points whose status is 0, as OpenCV leaves them).  status: 1 = tracked.
+ * err (may be NULL): mean absolute window difference at level 0.  The top level is min(max_level, the last level
+ * larger than the window) and must exist in the context (levels > top).  Capacity: n <= max_fa_items.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    int32_t win;              /* window side, 3..21 (m_patchSizeOpticalFlow; 11 in src/map.cpp) */
+    int32_t max_level;        /* 3 */
+    int32_t max_count;        /* 30 */
+    int32_t use_initial_flow; /* 1 */
+    double epsilon;           /* 1e-4 */
+    double min_eig_threshold; /* 1e-4, OpenCV's default */
+} svo_klt_params;
+svo_status svo_klt_track(svo_ctx* ctx, int ref_slot, int cur_slot, const float* prev_pts, float* next_pts, int n,
+                         const svo_klt_params* params, uint8_t* status, float* err);
+
+/* ---------------------------------------------------------------------------------------------
  * The per-frame front end as ONE CUDA graph launch: what System::processNewFrame runs for a new camera image between
  * Frame::Frame (src/system.cpp:36, src/frame.cpp:26) and the candidate matching of Map::reprojectMap /
  * addCandidateToFrame (src/system.cpp:313-330, src/map.cpp:595-627):

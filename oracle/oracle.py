@@ -383,5 +383,28 @@ def reproject_map(grads, cur_grad, K, T_cur, cands, cell, cell_order, max_matche
     return out[:m].copy(), proj[:cands.size].copy()
 
 
+class KltParams(C.Structure):
+    _fields_ = [("win", C.c_int32), ("max_level", C.c_int32), ("max_count", C.c_int32), ("use_initial_flow", C.c_int32),
+                ("epsilon", C.c_double), ("min_eig_threshold", C.c_double)]
+
+
+def klt_track(ref_img, cur_img, prev_pts, next_pts=None, win=11, max_level=3, max_count=30, epsilon=1e-4, min_eig_threshold=1e-4):
+    """cv::calcOpticalFlowPyrLK as algorithm::computeOpticalFlowSparse calls it.  Returns (next_pts (n, 2) float32, status (n,) uint8,
+    err (n,) float32, top level used).  next_pts given = OPTFLOW_USE_INITIAL_FLOW."""
+    ref_img, cur_img = _c8(ref_img), _c8(cur_img)
+    h, w = ref_img.shape
+    prev = np.ascontiguousarray(prev_pts, dtype=np.float32).reshape(-1, 2)
+    nxt = np.ascontiguousarray(next_pts if next_pts is not None else prev, dtype=np.float32).reshape(-1, 2).copy()
+    n = prev.shape[0]
+    prm = KltParams(win, max_level, max_count, 1 if next_pts is not None else 0, epsilon, min_eig_threshold)
+    status, err = np.zeros(max(1, n), np.uint8), np.zeros(max(1, n), np.float32)
+    L = lib()
+    L.orc_klt_track.restype = C.c_int
+    L.orc_klt_track.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.POINTER(KltParams),
+                                C.c_void_p, C.c_void_p]
+    top = L.orc_klt_track(_p(ref_img), _p(cur_img), w, h, _p(prev), _p(nxt), n, C.byref(prm), _p(status), _p(err))
+    return nxt, status[:n].copy(), err[:n].copy(), top
+
+
 def hardware_threads():
     return lib().orc_hardware_threads()

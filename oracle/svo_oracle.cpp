@@ -1285,6 +1285,189 @@ int orc_reproject_map(const uint8_t* const* grads, const uint8_t* curGrad, int w
     return m;
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// cv::calcOpticalFlowPyrLK as the reference calls it (src/algorithm.cpp:60-62), restated from OpenCV 4.x lkpyramid.cpp.
+namespace {
+struct KltLevel {
+    int w, h, pad;
+    std::vector<uint8_t> img;    // (h + 2 pad) x (w + 2 pad), BORDER_REFLECT_101
+    std::vector<int16_t> deriv;  // same extent, 2 channels (dI/dx, dI/dy), zero outside the image
+    int pitch() const { return w + 2 * pad; }
+    const uint8_t* I(int x, int y) const { return &img[(size_t)(y + pad) * pitch() + x + pad]; }
+    const int16_t* D(int x, int y) const { return &deriv[((size_t)(y + pad) * pitch() + x + pad) * 2]; }
+};
+void kltPad(const std::vector<uint8_t>& src, int w, int h, int pad, KltLevel& L, bool withDeriv)
+{
+    L.w = w, L.h = h, L.pad = pad;
+    const int P = L.pitch();
+    L.img.assign((size_t)(h + 2 * pad) * P, 0);
+    for (int y = -pad; y < h + pad; y++)
+        for (int x = -pad; x < w + pad; x++) L.img[(size_t)(y + pad) * P + x + pad] = src[(size_t)reflect101(y, h) * w + reflect101(x, w)];
+    if (!withDeriv) return;
+    // calcSharrDeriv: t0 = 3 (row-1 + row+1) + 10 row, t1 = row+1 - row-1; dx = t0[x+1] - t0[x-1], dy = 3 (t1[x-1] + t1[x+1]) + 10 t1[x];
+    // rows and columns beyond the image are reflected (101)
+    L.deriv.assign((size_t)(h + 2 * pad) * P * 2, 0);
+    std::vector<int> t0(w + 2), t1(w + 2);
+    for (int y = 0; y < h; y++) {
+        const uint8_t* r0 = &src[(size_t)reflect101(y - 1, h) * w];
+        const uint8_t* r1 = &src[(size_t)y * w];
+        const uint8_t* r2 = &src[(size_t)reflect101(y + 1, h) * w];
+        for (int x = -1; x <= w; x++) {
+            const int xx = reflect101(x, w);
+            t0[x + 1]    = (r0[xx] + r2[xx]) * 3 + r1[xx] * 10;
+            t1[x + 1]    = r2[xx] - r0[xx];
+        }
+        for (int x = 0; x < w; x++) {
+            int16_t* d = &L.deriv[((size_t)(y + pad) * P + x + pad) * 2];
+            d[0]       = (int16_t)(t0[x + 2] - t0[x]);
+            d[1]       = (int16_t)((t1[x + 2] + t1[x]) * 3 + t1[x + 1] * 10);
+        }
+    }
+}
+inline int kltDescale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+inline int kltRound(float v) { return (int)lrintf(v); }  // cvRound: nearest, ties to even
+}  // namespace
+
+int orc_klt_track(const uint8_t* refImg, const uint8_t* curImg, int w, int h, const float* prevPts, float* nextPts, int n,
+                  const orc_klt_params* prm, uint8_t* status, float* err)
+{
+    const int win = prm->win;
+    // TermCriteria clamps of calcOpticalFlowPyrLK; epsilon is compared against |delta|^2
+    const int maxCount = std::min(std::max(prm->max_count, 0), 100);
+    double eps         = std::min(std::max(prm->epsilon, 0.0), 10.0);
+    eps *= eps;
+    // buildOpticalFlowPyramid: stop before a level that is not larger than the window
+    std::vector<std::vector<uint8_t>> pr(1), pc(1);
+    std::vector<int> lw{w}, lh{h};
+    pr[0].assign((size_t)w * h, 0), pc[0].assign((size_t)w * h, 0);
+    std::memcpy(pr[0].data(), refImg, (size_t)w * h), std::memcpy(pc[0].data(), curImg, (size_t)w * h);
+    int maxLevel = 0;
+    for (int l = 1; l <= prm->max_level; l++) {
+        const int sw = lw[l - 1], sh = lh[l - 1], dw = (sw + 1) / 2, dh = (sh + 1) / 2;
+        if (dw <= win || dh <= win) break;
+        pr.emplace_back((size_t)dw * dh), pc.emplace_back((size_t)dw * dh);
+        orc_pyrdown(pr[l - 1].data(), sw, sh, sw, pr[l].data(), dw);
+        orc_pyrdown(pc[l - 1].data(), sw, sh, sw, pc[l].data(), dw);
+        lw.push_back(dw), lh.push_back(dh);
+        maxLevel = l;
+    }
+    for (int i = 0; i < n; i++) {
+        status[i] = 1;
+        if (err) err[i] = 0.f;
+    }
+    const float halfWin  = (win - 1) * 0.5f;
+    const float FLT_SCALE = 1.f / (1 << 20);
+    std::vector<int16_t> Iw((size_t)win * win), dIw((size_t)win * win * 2);
+    for (int level = maxLevel; level >= 0; level--) {
+        KltLevel I, J;
+        kltPad(pr[level], lw[level], lh[level], win, I, true);
+        kltPad(pc[level], lw[level], lh[level], win, J, false);
+        const int cols = lw[level], rows = lh[level];
+        for (int pt = 0; pt < n; pt++) {
+            const float sc = (float)(1. / (1 << level));
+            float px = prevPts[2 * pt] * sc, py = prevPts[2 * pt + 1] * sc;
+            float nx, ny;
+            if (level == maxLevel) {
+                if (prm->use_initial_flow)
+                    nx = nextPts[2 * pt] * sc, ny = nextPts[2 * pt + 1] * sc;
+                else
+                    nx = px, ny = py;
+            } else
+                nx = nextPts[2 * pt] * 2.f, ny = nextPts[2 * pt + 1] * 2.f;
+            nextPts[2 * pt] = nx, nextPts[2 * pt + 1] = ny;
+            px -= halfWin, py -= halfWin;
+            const int ipx = (int)std::floor(px), ipy = (int)std::floor(py);
+            if (ipx < -win || ipx >= cols || ipy < -win || ipy >= rows) {
+                if (level == 0) {
+                    status[pt] = 0;
+                    if (err) err[pt] = 0.f;
+                }
+                continue;
+            }
+            float a = px - ipx, b = py - ipy;
+            int iw00 = kltRound((1.f - a) * (1.f - b) * (1 << 14)), iw01 = kltRound(a * (1.f - b) * (1 << 14));
+            int iw10 = kltRound((1.f - a) * b * (1 << 14)), iw11 = (1 << 14) - iw00 - iw01 - iw10;
+            float A11 = 0, A12 = 0, A22 = 0;
+            for (int y = 0; y < win; y++)
+                for (int x = 0; x < win; x++) {
+                    const uint8_t* s0 = I.I(ipx + x, ipy + y);
+                    const uint8_t* s1 = I.I(ipx + x, ipy + y + 1);
+                    const int16_t* d0 = I.D(ipx + x, ipy + y);
+                    const int16_t* d1 = I.D(ipx + x, ipy + y + 1);
+                    const int ival  = kltDescale(s0[0] * iw00 + s0[1] * iw01 + s1[0] * iw10 + s1[1] * iw11, 14 - 5);
+                    const int ixval = kltDescale(d0[0] * iw00 + d0[2] * iw01 + d1[0] * iw10 + d1[2] * iw11, 14);
+                    const int iyval = kltDescale(d0[1] * iw00 + d0[3] * iw01 + d1[1] * iw10 + d1[3] * iw11, 14);
+                    Iw[y * win + x]            = (int16_t)ival;
+                    dIw[(y * win + x) * 2]     = (int16_t)ixval;
+                    dIw[(y * win + x) * 2 + 1] = (int16_t)iyval;
+                    A11 += (float)(ixval * ixval);
+                    A12 += (float)(ixval * iyval);
+                    A22 += (float)(iyval * iyval);
+                }
+            A11 *= FLT_SCALE, A12 *= FLT_SCALE, A22 *= FLT_SCALE;
+            float D            = A11 * A22 - A12 * A12;
+            const float minEig = (A22 + A11 - std::sqrt((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (2 * win * win);
+            if (minEig < prm->min_eig_threshold || D < FLT_EPSILON) {
+                if (level == 0) status[pt] = 0;
+                continue;
+            }
+            D = 1.f / D;
+            nx -= halfWin, ny -= halfWin;
+            float pdx = 0.f, pdy = 0.f;
+            for (int j = 0; j < maxCount; j++) {
+                const int inx = (int)std::floor(nx), iny = (int)std::floor(ny);
+                if (inx < -win || inx >= cols || iny < -win || iny >= rows) {
+                    if (level == 0) status[pt] = 0;
+                    break;
+                }
+                a = nx - inx, b = ny - iny;
+                iw00 = kltRound((1.f - a) * (1.f - b) * (1 << 14)), iw01 = kltRound(a * (1.f - b) * (1 << 14));
+                iw10 = kltRound((1.f - a) * b * (1 << 14)), iw11 = (1 << 14) - iw00 - iw01 - iw10;
+                float b1 = 0, b2 = 0;
+                for (int y = 0; y < win; y++)
+                    for (int x = 0; x < win; x++) {
+                        const uint8_t* s0 = J.I(inx + x, iny + y);
+                        const uint8_t* s1 = J.I(inx + x, iny + y + 1);
+                        const int diff = kltDescale(s0[0] * iw00 + s0[1] * iw01 + s1[0] * iw10 + s1[1] * iw11, 14 - 5) - Iw[y * win + x];
+                        b1 += (float)(diff * dIw[(y * win + x) * 2]);
+                        b2 += (float)(diff * dIw[(y * win + x) * 2 + 1]);
+                    }
+                b1 *= FLT_SCALE, b2 *= FLT_SCALE;
+                const float dx = (float)((A12 * b2 - A22 * b1) * D), dy = (float)((A12 * b1 - A11 * b2) * D);
+                nx += dx, ny += dy;
+                nextPts[2 * pt] = nx + halfWin, nextPts[2 * pt + 1] = ny + halfWin;
+                if ((double)dx * dx + (double)dy * dy <= eps) break;
+                if (j > 0 && std::abs(dx + pdx) < 0.01 && std::abs(dy + pdy) < 0.01) {
+                    nextPts[2 * pt] -= dx * 0.5f, nextPts[2 * pt + 1] -= dy * 0.5f;
+                    break;
+                }
+                pdx = dx, pdy = dy;
+            }
+            if (status[pt] && err && level == 0) {
+                const float ex = nextPts[2 * pt] - halfWin, ey = nextPts[2 * pt + 1] - halfWin;
+                const int iex = (int)std::floor(ex), iey = (int)std::floor(ey);
+                if (iex < -win || iex >= cols || iey < -win || iey >= rows) {
+                    status[pt] = 0;
+                    continue;
+                }
+                const float aa = ex - iex, bb = ey - iey;
+                iw00 = kltRound((1.f - aa) * (1.f - bb) * (1 << 14)), iw01 = kltRound(aa * (1.f - bb) * (1 << 14));
+                iw10 = kltRound((1.f - aa) * bb * (1 << 14)), iw11 = (1 << 14) - iw00 - iw01 - iw10;
+                float errval = 0.f;
+                for (int y = 0; y < win; y++)
+                    for (int x = 0; x < win; x++) {
+                        const uint8_t* s0 = J.I(iex + x, iey + y);
+                        const uint8_t* s1 = J.I(iex + x, iey + y + 1);
+                        const int diff = kltDescale(s0[0] * iw00 + s0[1] * iw01 + s1[0] * iw10 + s1[1] * iw11, 14 - 5) - Iw[y * win + x];
+                        errval += std::abs((float)diff);
+                    }
+                err[pt] = errval * 1.f / (32 * win * win);
+            }
+        }
+    }
+    return maxLevel;
+}
+
 int orc_hardware_threads(void) { return (int)std::thread::hardware_concurrency(); }
 
 }  // extern "C"

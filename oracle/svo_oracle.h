@@ -194,6 +194,26 @@ int orc_reproject_map(const uint8_t* const* grads, const uint8_t* cur_grad, int 
                       const orc_reproj_candidate* cands, int n, int cell, const int32_t* cell_order, int n_cells, int max_matches,
                       const orc_fa_params* fa, double* matches, uint8_t* projected);
 
+/* ---- algorithm::computeOpticalFlowSparse's tracker (src/algorithm.cpp:29-107, the initialisation; the same call sits at
+ * src/map.cpp:322,403): cv::calcOpticalFlowPyrLK(refImg, curImg, refPoints, curPoints, status, errors, Size(win, win), 3,
+ * TermCriteria(COUNT + EPS, 30, 1e-4), OPTFLOW_USE_INITIAL_FLOW).  OpenCV is a dependency of the reference that is not
+ * vendored (CMake find_package(OpenCV)); this restates the published algorithm of OpenCV 4.x modules/video/src/lkpyramid.cpp
+ * (buildOpticalFlowPyramid: pyrDown levels padded BORDER_REFLECT_101; calcSharrDeriv: int16 Scharr 3-10-3 with reflected
+ * borders, zero outside the image; LKTrackerInvoker: 14-bit fixed-point bilinear weights, window values scaled by 32, float
+ * sums, the eps / oscillation exits) and is pinned against the cv2 4.13 binary of this image (tests/test_oracle_klt.py).
+ * prev_pts / next_pts: n (x, y) float pairs; next_pts holds the initial guess when use_initial_flow.  status: 1 tracked.
+ * err: mean absolute window difference at level 0 (OpenCV's default error measure).  Returns the top level used. ---- */
+typedef struct {
+    int32_t win;              /* window side (cv::Size(win, win)) */
+    int32_t max_level;        /* 3 in the reference */
+    int32_t max_count;        /* 30 */
+    int32_t use_initial_flow; /* 1 */
+    double epsilon;           /* 1e-4 (squared internally, as OpenCV does) */
+    double min_eig_threshold; /* 1e-4, OpenCV's default */
+} orc_klt_params;
+int orc_klt_track(const uint8_t* ref_img, const uint8_t* cur_img, int w, int h, const float* prev_pts, float* next_pts, int n,
+                  const orc_klt_params* params, uint8_t* status, float* err);
+
 int orc_hardware_threads(void);
 
 #ifdef __cplusplus

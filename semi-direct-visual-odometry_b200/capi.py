@@ -26,7 +26,7 @@ SYMBOLS = [
     "svo_sparse_align_results_device", "svo_debug_cycles",
     "svo_feature_align", "svo_feature_align_stage", "svo_feature_align_h2d", "svo_feature_align_launch",
     "svo_feature_align_d2h", "svo_feature_align_fetch", "svo_frontend_run", "svo_frontend_image_buffer",
-    "svo_epipolar_match", "svo_select_ssc", "svo_reproject_map",
+    "svo_epipolar_match", "svo_select_ssc", "svo_reproject_map", "svo_klt_track",
 ]
 
 
@@ -43,6 +43,11 @@ class AlignParams(C.Structure):
 
 class FaParams(C.Structure):
     _fields_ = [("patch_size", C.c_int32), ("mode", C.c_int32), ("max_iter", C.c_int32), ("reserved", C.c_int32)]
+
+
+class KltParams(C.Structure):
+    _fields_ = [("win", C.c_int32), ("max_level", C.c_int32), ("max_count", C.c_int32), ("use_initial_flow", C.c_int32),
+                ("epsilon", C.c_double), ("min_eig_threshold", C.c_double)]
 
 
 class FrontendParams(C.Structure):
@@ -131,6 +136,7 @@ def load():
     L.svo_debug_cycles.argtypes = [vp, vp]
     L.svo_sparse_align_results_device.restype = vp
     L.svo_reproject_map.argtypes = [vp, i, vp, vp, i, i, vp, i, i, C.POINTER(FaParams), vp, C.POINTER(i), vp]
+    L.svo_klt_track.argtypes = [vp, i, i, vp, vp, i, C.POINTER(KltParams), vp, vp]
     L.svo_select_ssc.argtypes = [vp, i, C.c_uint32, i, i, vp, i, vp, i, C.POINTER(i), vp]
     L.svo_epipolar_match.argtypes = [vp, vp, i, C.POINTER(EpiParams), vp]
     L.svo_frontend_run.argtypes = [vp, C.POINTER(FrontendParams), vp, i, vp, vp, i, vp, vp, vp, i, vp]
@@ -348,6 +354,19 @@ class Context:
         self._check(self.L.svo_reproject_map(self.h, cur_slot, _ptr(T), _ptr(cands), cands.size, cell, _ptr(order), order.size,
                                              max_matches, C.byref(prm), _ptr(out), C.byref(n), _ptr(proj)))
         return out[:n.value].copy(), proj[:cands.size].copy()
+
+    # ---- cv::calcOpticalFlowPyrLK as algorithm::computeOpticalFlowSparse calls it ----
+    def klt_track(self, ref_slot, cur_slot, prev_pts, next_pts=None, win=11, max_level=3, max_count=30, epsilon=1e-4,
+                  min_eig_threshold=1e-4):
+        """returns (next_pts (n, 2) float32, status (n,) uint8, err (n,) float32); next_pts given = OPTFLOW_USE_INITIAL_FLOW"""
+        prev = np.ascontiguousarray(prev_pts, dtype=np.float32).reshape(-1, 2)
+        nxt = np.ascontiguousarray(next_pts if next_pts is not None else prev, dtype=np.float32).reshape(-1, 2).copy()
+        n = prev.shape[0]
+        assert nxt.shape[0] == n
+        prm = KltParams(win, max_level, max_count, 1 if next_pts is not None else 0, epsilon, min_eig_threshold)
+        status, err = np.zeros(max(1, n), np.uint8), np.zeros(max(1, n), np.float32)
+        self._check(self.L.svo_klt_track(self.h, ref_slot, cur_slot, _ptr(prev), _ptr(nxt), n, C.byref(prm), _ptr(status), _ptr(err)))
+        return nxt, status[:n].copy(), err[:n].copy()
 
     # ---- algorithm::matchEpipolarConstraint, batched over depth-filter seeds ----
     def epipolar_match(self, items, patch_size=7, mean_mode=MEAN_EIGEN_U8):

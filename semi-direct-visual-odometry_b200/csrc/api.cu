@@ -76,6 +76,11 @@ void release(svo_ctx* ctx)
     cudaFree(ctx->d_rp_px);
     cudaFree(ctx->d_rp_projected);
     cudaFreeHost(ctx->h_rp_projected);
+    cudaFree(ctx->d_klt_prev);
+    cudaFree(ctx->d_klt_next);
+    cudaFree(ctx->d_klt_status);
+    cudaFree(ctx->d_klt_err);
+    cudaFreeHost(ctx->h_klt);
     cudaFreeHost(ctx->h_epi_items);
     cudaFreeHost(ctx->h_epi_results);
     cudaFree(ctx->d_epi_items);
@@ -785,6 +790,58 @@ svo_status svo_epipolar_match(svo_ctx* ctx, const svo_epi_item* items, int n, co
     SVO_CUDA(cudaMemcpyAsync(ctx->h_epi_results, ctx->d_epi_results, sizeof(svo_epi_result) * n, cudaMemcpyDeviceToHost, ctx->stream));
     SVO_CUDA(cudaStreamSynchronize(ctx->stream));
     std::memcpy(results, ctx->h_epi_results, sizeof(svo_epi_result) * n);
+    return SVO_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+// pyramidal Lucas-Kanade (initialisation)
+// ------------------------------------------------------------------------------------------------
+svo_status svo_klt_track(svo_ctx* ctx, int ref_slot, int cur_slot, const float* prev_pts, float* next_pts, int n,
+                         const svo_klt_params* prm, uint8_t* status, float* err)
+{
+    if (!ctx) return SVO_ERR_INVALID;
+    if (n < 0 || !prm || (n > 0 && (!prev_pts || !next_pts || !status))) SVO_FAIL(SVO_ERR_INVALID, "svo_klt_track: null argument");
+    if (bad_slot(ctx, ref_slot) || bad_slot(ctx, cur_slot)) SVO_FAIL(SVO_ERR_INVALID, "svo_klt_track: frame slot out of range");
+    if (prm->win < 3 || prm->win > 21 || prm->max_level < 0) SVO_FAIL(SVO_ERR_INVALID, "svo_klt_track: win must be 3..21, max_level >= 0");
+    if (n > ctx->cfg.max_fa_items) SVO_FAIL(SVO_ERR_CAPACITY, "svo_klt_track: more points than max_fa_items");
+    // buildOpticalFlowPyramid stops before the first level that is not larger than the window
+    int top = 0;
+    {
+        int w = ctx->arena.geom[0].w, h = ctx->arena.geom[0].h;
+        if (w <= prm->win || h <= prm->win) SVO_FAIL(SVO_ERR_INVALID, "svo_klt_track: the image must be larger than the window");
+        for (int l = 1; l <= prm->max_level; l++) {
+            w = (w + 1) / 2, h = (h + 1) / 2;
+            if (w <= prm->win || h <= prm->win) break;
+            top = l;
+        }
+    }
+    if (top >= ctx->cfg.levels) SVO_FAIL(SVO_ERR_UNSUPPORTED, "svo_klt_track: the context holds fewer pyramid levels than max_level needs");
+    if (n == 0) return SVO_OK;
+    SVO_CUDA(cudaSetDevice(ctx->cfg.device));
+    const size_t nf = (size_t)std::max(1, ctx->cfg.max_fa_items);
+    if (!ctx->d_klt_prev) {
+        SVO_CUDA(cudaMalloc(&ctx->d_klt_prev, sizeof(float2) * nf));
+        SVO_CUDA(cudaMalloc(&ctx->d_klt_next, sizeof(float2) * nf));
+        SVO_CUDA(cudaMalloc(&ctx->d_klt_status, nf));
+        SVO_CUDA(cudaMalloc(&ctx->d_klt_err, sizeof(float) * nf));
+        SVO_CUDA(cudaHostAlloc(&ctx->h_klt, nf * 13, cudaHostAllocDefault));
+    }
+    svo_status st = wait_ingest(ctx);
+    if (st != SVO_OK) return st;
+    SVO_CUDA(cudaStreamSynchronize(ctx->stream));
+    float* hNext     = reinterpret_cast<float*>(ctx->h_klt);
+    float* hErr      = hNext + 2 * nf;
+    uint8_t* hStatus = reinterpret_cast<uint8_t*>(hErr + nf);
+    SVO_CUDA(cudaMemcpyAsync(ctx->d_klt_prev, prev_pts, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream));
+    SVO_CUDA(cudaMemcpyAsync(ctx->d_klt_next, next_pts, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream));
+    if ((st = launch_klt_track(ctx, ref_slot, cur_slot, n, *prm, top)) != SVO_OK) return st;
+    SVO_CUDA(cudaMemcpyAsync(hNext, ctx->d_klt_next, sizeof(float2) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    SVO_CUDA(cudaMemcpyAsync(hErr, ctx->d_klt_err, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
+    SVO_CUDA(cudaMemcpyAsync(hStatus, ctx->d_klt_status, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
+    SVO_CUDA(cudaStreamSynchronize(ctx->stream));
+    std::memcpy(next_pts, hNext, sizeof(float2) * n);
+    std::memcpy(status, hStatus, (size_t)n);
+    if (err) std::memcpy(err, hErr, sizeof(float) * n);
     return SVO_OK;
 }
 

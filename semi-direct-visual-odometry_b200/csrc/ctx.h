@@ -123,6 +123,12 @@ struct svo_ctx {
     uint8_t* h_rp_projected;         // pinned
 
     // epipolar search batch (depth-filter seeds), capacity max_fa_items
+    // svo_klt_track
+    float2* d_klt_prev;
+    float2* d_klt_next;
+    uint8_t* d_klt_status;
+    float* d_klt_err;
+    unsigned char* h_klt;  // pinned: next, err, status
     svo_epi_item* h_epi_items;      // pinned
     svo_epi_result* h_epi_results;  // pinned
     svo_epi_item* d_epi_items;
@@ -178,6 +184,8 @@ svo_status launch_feature_align(svo_ctx* ctx);
 svo_status launch_reproject_map(svo_ctx* ctx, int curSlot, const double T[7], int n, int cell, int nCells, int gridCols, int maxItems,
                                 const svo_fa_params& fa);
 svo_status launch_epipolar_match(svo_ctx* ctx, int n, const svo_epi_params& prm);
+svo_status launch_klt_track(svo_ctx* ctx, int refSlot, int curSlot, int n, const svo_klt_params& prm, int topLevel);
+size_t klt_smem_bytes(int win);
 void frontend_release(svo_ctx* ctx);
 size_t sparse_align_smem_bytes(int nthreads, int max_features, int patch_area);
 bool sparse_align_v3_supported(const svo_ctx* ctx, int maxF);

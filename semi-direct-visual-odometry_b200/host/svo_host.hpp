@@ -12,6 +12,7 @@
 //   FeatureAlignment  include/feature_alignment.hpp:15-44, src/feature_alignment.cpp:25-62
 // All arithmetic of the hot path runs on the GPU; these classes only marshal.  No CPU fallback exists.
 #pragma once
+#include <algorithm>
 #include <cmath>
 #include <cstdint>
 #include <limits>
@@ -635,6 +636,51 @@ inline bool matchEpipolarConstraint(const std::shared_ptr<Frame>& refFrame, cons
     matchEpipolarConstraintBatch(curFrame, {EpipolarSeed{refFeature, initialDepth, minDepth, maxDepth}}, patchSize, found, depth);
     if (found[0]) estimatedDepth = depth[0];  // the reference leaves it untouched on failure
     return found[0];
+}
+// algorithm::computeMedian (src/algorithm.cpp:813-832); the mean of the two middle elements for an even count is taken
+// from true order statistics (the reference reads vec[mid - 1] after one nth_element: SURVEY 9.3)
+inline double computeMedian(std::vector<double> vec)
+{
+    if (vec.empty()) return std::numeric_limits<double>::quiet_NaN();
+    const size_t mid = vec.size() / 2;
+    std::nth_element(vec.begin(), vec.begin() + mid, vec.end());
+    if (vec.size() % 2) return vec[mid];
+    return (*std::max_element(vec.begin(), vec.begin() + mid) + vec[mid]) / 2.0;
+}
+
+// algorithm::computeOpticalFlowSparse (src/algorithm.cpp:29-107), System's initialisation step (src/system.cpp:129): every
+// feature of refFrame is tracked into curFrame with cv::calcOpticalFlowPyrLK(..., Size(patchSize, patchSize), 3,
+// TermCriteria(COUNT + EPS, 30, 1e-4), OPTFLOW_USE_INITIAL_FLOW) -- here svo_klt_track on the two frames' pyramids -- the
+// tracked positions become features of curFrame (:66-76, before the disparity test, as in the reference), the median
+// disparity gates the result (:78-84) and the features that were not tracked leave refFrame (:86-102).
+inline bool computeOpticalFlowSparse(std::shared_ptr<Frame>& refFrame, std::shared_ptr<Frame>& curFrame, const uint32_t patchSize,
+                                     const double disparityThreshold)
+{
+    const auto& dev = curFrame->m_imagePyramid.device();
+    const size_t n  = refFrame->numberObservation();
+    std::vector<float> refPoints(2 * n), curPoints(2 * n);
+    for (size_t i = 0; i < n; i++) {
+        refPoints[2 * i] = curPoints[2 * i] = (float)refFrame->m_features[i]->m_pixelPosition.x();
+        refPoints[2 * i + 1] = curPoints[2 * i + 1] = (float)refFrame->m_features[i]->m_pixelPosition.y();
+    }
+    std::vector<uint8_t> status(n ? n : 1);
+    svo_klt_params prm{(int32_t)patchSize, 3, 30, 1, 1e-4, 1e-4};
+    dev->check(svo_klt_track(dev->ctx(), refFrame->m_imagePyramid.slot(), curFrame->m_imagePyramid.slot(), refPoints.data(),
+                             curPoints.data(), (int)n, &prm, status.data(), nullptr),
+               "svo_klt_track");
+    std::vector<double> disparity;
+    for (size_t i = 0; i < n; i++) {
+        if (!status[i]) continue;
+        auto f = std::make_shared<Feature>(curFrame, Vec2(curPoints[2 * i], curPoints[2 * i + 1]), 0.0, 0.0, 0);
+        curFrame->addFeature(f);
+        disparity.push_back(std::hypot((double)refPoints[2 * i] - curPoints[2 * i], (double)refPoints[2 * i + 1] - curPoints[2 * i + 1]));
+    }
+    const double medianDisparity = computeMedian(disparity);
+    if (medianDisparity < disparityThreshold) return false;
+    size_t cnt = 0;
+    auto& fs   = refFrame->m_features;
+    fs.erase(std::remove_if(fs.begin(), fs.end(), [&](const auto& f) { return !(f != nullptr && status[cnt++] == 1); }), fs.end());
+    return true;
 }
 }  // namespace algorithm
 

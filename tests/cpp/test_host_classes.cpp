@@ -341,6 +341,36 @@ int main(int argc, char** argv)
         }
         std::printf("reprojectMap: %zu candidates -> %zu matches\n", cands.size(), matches.size());
     }
+    // ---- algorithm::computeOpticalFlowSparse (System's initialisation) vs the oracle's calcOpticalFlowPyrLK ----
+    {
+        const size_t n0 = ref->numberObservation(), c0 = cur->numberObservation();
+        std::vector<float> prev(2 * n0), next(2 * n0), oerr(n0);
+        for (size_t i = 0; i < n0; i++) {
+            prev[2 * i] = next[2 * i] = (float)ref->m_features[i]->m_pixelPosition.x();
+            prev[2 * i + 1] = next[2 * i + 1] = (float)ref->m_features[i]->m_pixelPosition.y();
+        }
+        std::vector<uint8_t> ost(n0);
+        orc_klt_params kp{11, 3, 30, 1, 1e-4, 1e-4};
+        CHECK(orc_klt_track(refImg.ptr(), curImg.ptr(), w, h, prev.data(), next.data(), (int)n0, &kp, ost.data(), oerr.data()) == 3);
+        size_t tracked = 0;
+        for (size_t i = 0; i < n0; i++) tracked += ost[i];
+        auto r2 = ref, c2 = cur;
+        CHECK(!algorithm::computeOpticalFlowSparse(r2, c2, 11, 1e9));  // median disparity below the threshold: refFrame untouched
+        CHECK(ref->numberObservation() == n0);
+        const size_t added = cur->numberObservation() - c0;            // ... but the tracked features were added already (:66-76)
+        CHECK(added + 2 >= tracked && added <= tracked + 2);
+        size_t k = 0, close = 0;
+        for (size_t i = 0; i < n0 && c0 + k < cur->numberObservation(); i++) {
+            if (!ost[i]) continue;
+            const auto& f = cur->m_features[c0 + k++];
+            close += std::fabs(f->m_pixelPosition.x() - next[2 * i]) < 2e-3 && std::fabs(f->m_pixelPosition.y() - next[2 * i + 1]) < 2e-3;
+        }
+        CHECK(close + 4 >= tracked);
+        CHECK(algorithm::computeOpticalFlowSparse(r2, c2, 11, 0.0));
+        CHECK(ref->numberObservation() + 2 >= tracked && ref->numberObservation() <= tracked + 2);  // untracked features erased (:86-102)
+        CHECK(algorithm::computeMedian({3.0, 1.0, 2.0}) == 2.0 && algorithm::computeMedian({4.0, 1.0, 3.0, 2.0}) == 2.5);
+        std::printf("computeOpticalFlowSparse: %zu of %zu features tracked\n", tracked, n0);
+    }
     Device::current().reset();
     std::printf(g_fail ? "FAILED (%d checks)\n" : "ALL HOST-CLASS CHECKS PASSED\n", g_fail);
     return g_fail ? 1 : 0;

@@ -37,7 +37,8 @@ def test_struct_layouts_match_header(pkg, tmp_path):
                     'sizeof(svo_align_level_stats), sizeof(svo_fa_item), sizeof(svo_fa_params), sizeof(svo_fa_result),'
                     'offsetof(svo_align_level_stats, pose_after), sizeof(svo_frontend_params), sizeof(svo_frontend_result),'
                     'sizeof(svo_epi_item), sizeof(svo_epi_params), sizeof(svo_epi_result), offsetof(svo_epi_item, depth));'
-                    'printf("%zu %zu\\n", sizeof(svo_reproj_candidate), sizeof(svo_reproj_match)); return 0; }\n')
+                    'printf("%zu %zu\\n", sizeof(svo_reproj_candidate), sizeof(svo_reproj_match));'
+                    'printf("%zu %zu\\n", sizeof(svo_klt_params), offsetof(svo_klt_params, epsilon)); return 0; }\n')
     exe = tmp_path / "layout"
     subprocess.check_call(["gcc", "-std=c99", "-I", os.path.join(ROOT, "include"), str(prog), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
@@ -47,7 +48,7 @@ def test_struct_layouts_match_header(pkg, tmp_path):
             C.sizeof(c.FaParams), c.FA_RESULT_DTYPE.itemsize, c.ALIGN_STATS_DTYPE.fields["pose_after"][1],
             C.sizeof(c.FrontendParams), c.FRONTEND_RESULT_DTYPE.itemsize, c.EPI_ITEM_DTYPE.itemsize, C.sizeof(c.EpiParams),
             c.EPI_RESULT_DTYPE.itemsize, c.EPI_ITEM_DTYPE.fields["depth"][1], c.REPROJ_CAND_DTYPE.itemsize,
-            c.REPROJ_MATCH_DTYPE.itemsize]
+            c.REPROJ_MATCH_DTYPE.itemsize, C.sizeof(c.KltParams), c.KltParams.epsilon.offset]
     assert got == want
 
 
