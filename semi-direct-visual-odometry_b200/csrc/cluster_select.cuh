@@ -159,6 +159,9 @@ struct SelCtx {  // uniform over the cluster
     uint32_t tBelow, tAux, tMax;  // cluster totals of the last finished round
     uint32_t auxTotal;            // aux total of the round that fixed a rank (kFromAux)
 #ifdef SVO_PROFILE
+    long long stat[20];           // hot attempts by shift [0..7], hits by shift [8..15], [16] hits with <= 128 keys inside,
+                                  // [17] <= 256, [18] <= 512, [19] sum of keys inside over the hits
+    uint32_t lastInside;
     long long prof[12], tlast;    // cycles: 0 push 1 pop A 2 finish A 3 locate A 4 pop B 5 finish B 6 locate B 7 private count
                                   //         8 private reduce 9 private finish + scan 10 other
 #endif
@@ -440,6 +443,9 @@ __device__ __forceinline__ int cs_sweep_a(const uint32_t (&key)[AREA], bool live
     if (kin < 0) return -1;
     *out = cs_locate<NT>(hist, (uint32_t)kin, -1, sc);
     CS_T(3);
+#ifdef SVO_PROFILE
+    sc.lastInside = out->total;
+#endif
     return out->found ? 0 : 1;
 }
 
@@ -642,6 +648,18 @@ __device__ __forceinline__ bool cs_tiered_select(const uint32_t (&key)[AREA], bo
             shift = 7;  // 512 bins of 2^7 keys = the coarse bin
         }
         const int rc = cs_bracket_select<AREA, NT>(key, live, lo, shift, k, kFromAux, !(nTotal & 1), sc, &kOut, &pred);
+#ifdef SVO_PROFILE
+        if (have) {
+            sc.stat[shift]++;
+            if (rc == 0) {
+                sc.stat[8 + shift]++;
+                sc.stat[16] += sc.lastInside <= 128;
+                sc.stat[17] += sc.lastInside <= 256;
+                sc.stat[18] += sc.lastInside <= 512;
+                sc.stat[19] += sc.lastInside;
+            }
+        }
+#endif
         if (kFromAux && sc.auxTotal == 0) return false;
         kFromAux = false;
         if (rc == 0) break;

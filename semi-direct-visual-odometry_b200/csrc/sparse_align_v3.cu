@@ -208,6 +208,7 @@ __global__ void __launch_bounds__(NT, V3Occ<NT>::MINB) k_align_cluster(const V3A
     sc.init(sp, C);
 #ifdef SVO_PROFILE
     for (int i = 0; i < 12; i++) sc.prof[i] = 0;
+    for (int i = 0; i < 20; i++) sc.stat[i] = 0;
     sc.tlast = clock64();
 #endif
     sp += cs_smem_bytes<NT>();
@@ -737,6 +738,7 @@ __global__ void __launch_bounds__(NT, V3Occ<NT>::MINB) k_align_cluster(const V3A
         if (a.dbg && job == 0 && crank == 0 && tid == 33) {
             for (int i = 0; i < 8; i++) a.dbg[si * 8 + i] = tph[i];
             for (int i = 0; i < 12; i++) a.dbg[32 + i] = sc.prof[i];  // selection phases, summed over the levels so far
+            for (int i = 0; i < 20; i++) a.dbg[44 + i] = sc.stat[i];  // bracket statistics
         }
 #endif
         if (tid == 0) {
