@@ -774,3 +774,44 @@ def test_klt_track_golden_and_errors(pkg):
             ctx.klt_track(0, 1, np.ones((4, 2), np.float32), None, max_level=3)        # needs 4 pyramid levels
         ctx.upload(0, np.stack([g["ref0"], g["cur0"]]))
         ctx.klt_track(0, 1, g["pts0"][:8], None, max_level=1)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE.json config 1 at full size (1,024 pairs x 500 features, GN <= 30 iterations per level): the oracle on a sample,
+# and size-independent properties on everything -- ground truth, bitwise independence of a pair from its batch (what the
+# multi-GPU sharding relies on), bitwise invariance under a permutation of the jobs.
+def test_full_size_batch_properties(pkg, orc, synth):
+    n = 1024
+    batch = synth.make_batch(n, 500)
+    ident = np.array([0, 0, 0, 1, 0, 0, 0], dtype=np.float64)
+    jobs = pkg.capi.make_jobs(n)
+    jobs["ref_slot"], jobs["kf_slot"], jobs["cur_slot"] = np.arange(n), np.arange(n), np.arange(n) + n
+    jobs["n_ref"], jobs["n_kf"], jobs["feat_offset"] = batch["n_feat"], 0, batch["feat_offset"]
+    jobs["T_ref"], jobs["T_kf"], jobs["T_cur"] = ident, ident, ident
+    F = int(batch["n_feat"].max())
+    with pkg.Context(batch["w"], batch["h"], batch["K"], levels=4, max_frames=2 * n, max_jobs=n, max_features=F, max_fa_items=16) as ctx:
+        for s in range(0, n, 128):
+            ctx.upload(s, batch["ref"][s:s + 128])
+            ctx.upload(n + s, batch["cur"][s:s + 128])
+        res, _ = ctx.sparse_align(jobs, batch["feats"], mode=pkg.capi.GN, max_iter=30)
+        perm = np.random.default_rng(3).permutation(n)
+        res_p, _ = ctx.sparse_align(jobs[perm], batch["feats"], mode=pkg.capi.GN, max_iter=30)
+        half, _ = ctx.sparse_align(jobs[n // 2:], batch["feats"], mode=pkg.capi.GN, max_iter=30)
+        one, _ = ctx.sparse_align(jobs[777:778], batch["feats"], mode=pkg.capi.GN, max_iter=30)
+    # ground truth: every pair converges to the pose the frames were rendered from
+    rot = np.array([synth.rotation_angle(res[i]["T_cur"], batch["T_true"][i]) for i in range(n)])
+    tr = np.linalg.norm(res["T_cur"][:, 4:] - batch["T_true"][:, 4:], axis=1)
+    assert (rot < 1e-3).all() and (tr < 1e-2).all(), (rot.max(), tr.max())
+    assert np.isfinite(res["rmse"]).all() and (res["evaluations"] >= 8).all() and (res["evaluations"] <= 4 * 31).all()
+    # independence and permutation invariance, bit for bit
+    assert res_p.tobytes() == res[perm].tobytes()
+    assert half.tobytes() == res[n // 2:].tobytes()
+    assert one.tobytes() == res[777:778].tobytes()
+    # the oracle on a sample
+    for i in np.random.default_rng(4).choice(n, 12, replace=False):
+        f = batch["feats"][batch["feat_offset"][i]: batch["feat_offset"][i] + batch["n_feat"][i]]
+        rp, cp = orc.build_pyramid(batch["ref"][i], 4), orc.build_pyramid(batch["cur"][i], 4)
+        _, T, _, _ = orc.sparse_align(rp[0], rp[0], cp[0], batch["w"], batch["h"], f, len(f), 0, ident, ident, batch["K"], ident,
+                                      patch_size=5, mode=orc.GN, max_iter=30)
+        assert synth.rotation_angle(res[i]["T_cur"], T) < ROT_TOL
+        assert np.abs(res[i]["T_cur"][4:] - np.asarray(T)[4:]).max() < TRANS_TOL
