@@ -12,15 +12,23 @@
 //     "cells within Chebyshev distance 2", priorities = (gradient desc, raster asc).  It is computed by rounds: a champion
 //     is kept once every higher-priority champion in its 5x5 neighbourhood has been refused, refused once one of them
 //     has been kept; decisions only ever move from undecided to final, so rounds need no double buffering.
-// One CTA runs the whole binary search (count, per-width arg-max by atomicMax, rounds, decision) without host round
-// trips, sorts the <= 4,096 keepers by priority (the order the reference emits them in) and applies the first-come
-// bucketing of :62-78.
+// One CTA runs the whole binary search (count, per-width champions, rounds, decision) without host round trips, sorts
+// the <= 4,096 keepers by priority (the order the reference emits them in) and applies the first-come bucketing of
+// :62-78.  Per width: one thread per cell scans the cell's pixel rectangle (no atomics), the champion key and the state of
+// every cell live in SHARED memory whenever the cell grid fits (36,864 cells: every width >= 7 on a 1241x376 frame; finer
+// grids use the global arrays), and a round loads a cell's whole 5x5 neighbourhood before looking at it.  Phase counters
+// (cycles per width, 1241x376, ~1,500 cells): champions 215 K with an atomicMax per keypoint into global memory -> 140 K
+// with shared-memory atomics and a branch-free two-segment word path -> 80-100 K per-cell scan; rounds 240 K with dependent
+// global loads -> 45 K; count pass 47 K -> 14 K with 16 loads in flight; final sort 80 K -> 16 K over the power of two that
+// holds the keepers.  What remains is one SM's instruction issue (~15 instructions per pixel and width).
 #include "ctx.h"
 
 namespace {
 
 constexpr int SSC_NT  = 1024;
 constexpr int SSC_CAP = 4096;  // keepers (Kmax = 1.1 K: numberCandidate up to ~3,700)
+constexpr int SSC_SMEM_CELLS = 36864;  // cells held in shared memory: 4-byte key + 1-byte state each = 180 KB
+constexpr size_t SSC_DYN_SMEM = (size_t)SSC_SMEM_CELLS * 5;
 
 struct SscArgs {
     const uint8_t* grad;
@@ -32,7 +40,7 @@ struct SscArgs {
     const uint8_t* occ;  // nullable
     int useBucketing;
     uint32_t* cellKey;    // champion of each SSC cell: gradient << 24 | (0xFFFFFF - raster index); 0 = no keypoint
-    uint32_t* cellState;  // 0 undecided, 1 kept, 2 refused
+    uint8_t* cellState;   // 0 undecided, 1 kept, 2 refused
     long long cellCap;
     uint32_t* bucket;     // per occupancy-grid cell: position of its first keeper
     svo_feature_px* out;
@@ -42,6 +50,140 @@ struct SscArgs {
 };
 
 __device__ __forceinline__ uint32_t ldcg(const uint32_t* p) { return __ldcg(p); }
+
+// One width of the binary search: clear, per-cell champions, rounds of the lexicographically-first maximal independent
+// set, number of keepers.  SM: the cell arrays are the CTA's shared memory (the compiler sees the address space).
+template <bool SM>
+__device__ __forceinline__ int ssc_width_pass(const SscArgs& a, uint32_t* __restrict__ key, uint8_t* state, int width, int ncc, int ncr,
+                                              int* s_undecided, int* s_kept)
+{
+    const int tid = threadIdx.x;
+    const int w = a.w, h = a.h;
+    const double c  = width / 2.0;
+    const int cells = (ncr + 1) * (ncc + 1);
+    // champion of every cell: largest gradient above the threshold, earliest raster position among equals.  The cell of a
+    // keypoint is static_cast<int>(kp.pt.x / c) with pt a Point2f and c = width / 2.0 (:199-205): for integer coordinates
+    // that is the integer quotient (2 x) / width exactly (a correctly rounded quotient of two integers below 2^53 that is
+    // not an integer lies at least 1 / width away from one).  So cell (r, cc) owns the pixel rectangle
+    //   x in [ceil(cc width / 2), ceil((cc + 1) width / 2)),  y in [ceil(r width / 2), ceil((r + 1) width / 2))
+    // and ONE THREAD PER CELL scans its rectangle in raster order, word-wise: no division, no atomics, no clearing pass;
+    // neighbouring lanes read neighbouring segments of the same image rows.  (A pass over the pixels with an atomicMax per
+    // cell was 8x slower: ~100 instructions per 4-pixel word on one SM, phase counters in profiles/README.md.)
+    {
+        const int pw4       = a.pitch >> 2;
+        const uint32_t* g4  = reinterpret_cast<const uint32_t*>(a.grad);
+        const uint32_t thr4 = a.thr * 0x01010101u;
+        for (int i = tid; i < cells; i += SSC_NT) {
+            const int r = i / (ncc + 1), cc = i - r * (ncc + 1);
+            const int ys = (int)(((long long)r * width + 1) >> 1), ye = (int)min((long long)h, ((long long)(r + 1) * width + 1) >> 1);
+            const int xs = (int)(((long long)cc * width + 1) >> 1), xe = (int)min((long long)w, ((long long)(cc + 1) * width + 1) >> 1);
+            uint32_t bestM = 0, bestPos = 0;
+            if (xs < xe) {
+                const int w0 = xs >> 2, w1 = (xe - 1) >> 2;  // words of a row that hold the segment
+                const uint32_t mFirst = 0xffffffffu << (8 * (xs & 3));
+                const uint32_t mLast  = 0xffffffffu >> (8 * (3 - ((xe - 1) & 3)));
+                for (int y = ys; y < ye; y++) {
+                    const uint32_t* grow = g4 + (long long)y * pw4;
+                    // eight words of the row in flight before the first is looked at: the scan is bound by load latency
+                    for (int xb = w0; xb <= w1; xb += 8) {
+                        uint32_t q8[8];
+#pragma unroll
+                        for (int u = 0; u < 8; u++) q8[u] = xb + u <= w1 ? __ldg(grow + xb + u) : 0u;
+#pragma unroll
+                        for (int u = 0; u < 8; u++) {
+                            const int xw = xb + u;
+                            uint32_t q   = q8[u];
+                            uint32_t msk = __vcmpgtu4(q, thr4);  // 0xff in every byte above the threshold (thr <= 255)
+                            if (xw == w0) msk &= mFirst;
+                            if (xw == w1) msk &= mLast;
+                            q &= msk;  // words beyond w1 were loaded as zeros
+                            const uint32_t t2 = __vmaxu4(q, q >> 8);  // byte 0 = max(b0, b1), byte 2 = max(b2, b3)
+                            const uint32_t m  = max(t2 & 0xffu, (t2 >> 16) & 0xffu);
+                            if (m > bestM) {  // strictly: the first maximal pixel in raster order
+                                bestM   = m;
+                                bestPos = (uint32_t)(y * w + 4 * xw + ((__ffs(__vcmpeq4(q, m * 0x01010101u)) - 1) >> 3));
+                            }
+                        }
+                    }
+                }
+            }
+            key[i]   = bestM ? (bestM << 24) | (0xFFFFFFu - bestPos) : 0u;
+            state[i] = 0;
+        }
+    }
+    __syncthreads();
+    // rounds of the lexicographically-first maximal independent set
+    const int reach = (int)(width / c);  // 2
+    while (true) {
+        if (tid == 0) *s_undecided = 0;
+        __syncthreads();
+        int pending = 0;
+        for (int i = tid; i < cells; i += SSC_NT) {
+            if ((SM ? state[i] : __ldcg(state + i)) != 0) continue;
+            const uint32_t mine = key[i];
+            if (mine == 0) {
+                state[i] = 2;
+                continue;
+            }
+            const int row = i / (ncc + 1), col = i - row * (ncc + 1);
+            // the whole 5 x 5 neighbourhood is loaded before any of it is looked at (reach = width / c = 2 always):
+            // independent loads instead of 25 dependent load -> branch steps
+            uint32_t nk[25], ns[25];
+#pragma unroll
+            for (int dr = -2; dr <= 2; dr++)
+#pragma unroll
+                for (int dc = -2; dc <= 2; dc++) {
+                    const int r = row + dr, cc = col + dc, q = (dr + 2) * 5 + dc + 2;
+                    const bool in = r >= 0 && r <= ncr && cc >= 0 && cc <= ncc && reach == 2;
+                    const int j   = in ? r * (ncc + 1) + cc : i;  // outside the grid: the cell itself (never larger than itself)
+                    nk[q]         = key[j];
+                    ns[q]         = SM ? *(volatile uint8_t*)(state + j) : __ldcg(state + j);
+                }
+            bool refused = false, blocked = false;
+#pragma unroll
+            for (int q = 0; q < 25; q++) {
+                const bool higher = nk[q] > mine;
+                refused |= higher && ns[q] == 1;
+                blocked |= higher && ns[q] == 0;
+            }
+            if (reach != 2) {  // cannot happen for c = width / 2.0; kept as the general (slow) form
+                refused = blocked = false;
+                const int r0 = max(row - reach, 0), r1 = min(row + reach, ncr);
+                const int c0 = max(col - reach, 0), c1 = min(col + reach, ncc);
+                for (int r = r0; r <= r1; r++)
+                    for (int cc = c0; cc <= c1; cc++) {
+                        const int j = r * (ncc + 1) + cc;
+                        if (key[j] > mine) {
+                            const uint32_t st = SM ? *(volatile uint8_t*)(state + j) : __ldcg(state + j);
+                            refused |= st == 1;
+                            blocked |= st == 0;
+                        }
+                    }
+            }
+            if (refused)
+                state[i] = 2;
+            else if (!blocked)
+                state[i] = 1;
+            else
+                pending++;
+        }
+        if (pending) atomicAdd(s_undecided, pending);
+        __syncthreads();
+        if (*s_undecided == 0) break;
+        __syncthreads();
+    }
+    // result.size()
+    if (tid == 0) *s_kept = 0;
+    __syncthreads();
+    {
+        int k = 0;
+        for (int i = tid; i < cells; i += SSC_NT) k += (SM ? state[i] : __ldcg(state + i)) == 1;
+        k = __reduce_add_sync(0xffffffffu, k);
+        if ((tid & 31) == 0 && k) atomicAdd(s_kept, k);
+    }
+    __syncthreads();
+    return *s_kept;
+}
 
 __global__ void __launch_bounds__(SSC_NT) k_select_ssc(const SscArgs a)
 {
@@ -59,13 +201,16 @@ __global__ void __launch_bounds__(SSC_NT) k_select_ssc(const SscArgs a)
         int n = 0;
         const int pw4 = a.pitch >> 2;  // rows are padded to 16 bytes with zeros: four pixels per load
         const uint32_t* g4 = reinterpret_cast<const uint32_t*>(a.grad);
-        const int words    = h * pw4;   // the image as one flat array of words: every thread busy, loads in flight
-#pragma unroll 4
-        for (int i = tid; i < words; i += SSC_NT) {
-            const uint32_t q = g4[i];
-            const int xw     = i % pw4;
+        const int words    = h * pw4;   // the image as one flat array of words (row padding is zeros: never above thr >= 0)
+        for (int i0 = 0; i0 < words; i0 += SSC_NT * 16) {  // sixteen loads per thread in flight
+            uint32_t q16[16];
 #pragma unroll
-            for (int k = 0; k < 4; k++) n += (4 * xw + k < w) && ((q >> (8 * k)) & 0xffu) > a.thr;
+            for (int u = 0; u < 16; u++) {
+                const int i = i0 + u * SSC_NT + tid;
+                q16[u]      = i < words ? __ldg(g4 + i) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < 16; u++) n += __popc(__vcmpgtu4(q16[u], a.thr * 0x01010101u)) >> 3;
         }
         n = __reduce_add_sync(0xffffffffu, n);
         if ((tid & 31) == 0 && n) atomicAdd(&s_n, n);
@@ -87,6 +232,10 @@ __global__ void __launch_bounds__(SSC_NT) k_select_ssc(const SscArgs a)
         s_kmax = (uint32_t)roundf(Kf + (Kf * tol));
     }
     __syncthreads();
+    extern __shared__ __align__(16) unsigned char ssc_dyn[];
+    uint32_t* sKey  = reinterpret_cast<uint32_t*>(ssc_dyn);
+    uint8_t* sState = ssc_dyn + (size_t)SSC_SMEM_CELLS * 4;
+    bool inSmem     = false;
     int ncc = 0, ncr = 0;
     while (true) {
         if (tid == 0) {
@@ -111,95 +260,11 @@ __global__ void __launch_bounds__(SSC_NT) k_select_ssc(const SscArgs a)
             __syncthreads();
             break;
         }
-        for (long long i = tid; i < cells; i += SSC_NT) {
-            a.cellKey[i]   = 0;
-            a.cellState[i] = 0;
-        }
-        __syncthreads();
-        // champion of every cell: largest gradient, earliest raster position among equals
-        {
-            const int pw4      = a.pitch >> 2;
-            const uint32_t* g4 = reinterpret_cast<const uint32_t*>(a.grad);
-            const int words    = h * pw4;
-#pragma unroll 2
-            for (int i = tid; i < words; i += SSC_NT) {
-                const uint32_t q = g4[i];
-                if (__vcmpgtu4(q, a.thr * 0x01010101u) == 0) continue;  // no byte above the threshold (thr <= 255)
-                const int y = i / pw4, xw = i - y * pw4;
-                const int row  = (int)((double)(float)y / c);  // static_cast<int32_t>(kp.pt.y / c), pt is Point2f
-                uint32_t* krow = a.cellKey + (long long)row * (ncc + 1);
-                int curCol      = -1;
-                uint32_t curKey = 0;  // four consecutive pixels span at most a few cells: one atomic per cell
-#pragma unroll
-                for (int k = 0; k < 4; k++) {
-                    const int x      = 4 * xw + k;
-                    const uint32_t v = (q >> (8 * k)) & 0xffu;
-                    if (x < w && v > a.thr) {
-                        const int col      = (int)((double)(float)x / c);
-                        const uint32_t key = (v << 24) | (0xFFFFFFu - (uint32_t)(y * w + x));
-                        if (col != curCol) {
-                            if (curKey) atomicMax(&krow[curCol], curKey);
-                            curCol = col;
-                            curKey = key;
-                        } else
-                            curKey = max(curKey, key);
-                    }
-                }
-                if (curKey) atomicMax(&krow[curCol], curKey);
-            }
-        }
-        __syncthreads();
-        // rounds of the lexicographically-first maximal independent set
-        const int reach = (int)(width / c);  // 2
-        while (true) {
-            if (tid == 0) s_undecided = 0;
-            __syncthreads();
-            int pending = 0;
-            for (long long i = tid; i < cells; i += SSC_NT) {
-                if (ldcg(&a.cellState[i]) != 0) continue;
-                const uint32_t key = a.cellKey[i];
-                if (key == 0) {
-                    a.cellState[i] = 2;
-                    continue;
-                }
-                const int row = (int)(i / (ncc + 1)), col = (int)(i - (long long)row * (ncc + 1));
-                const int r0 = max(row - reach, 0), r1 = min(row + reach, ncr);
-                const int c0 = max(col - reach, 0), c1 = min(col + reach, ncc);
-                bool refused = false, blocked = false;
-                for (int r = r0; r <= r1 && !refused; r++)
-                    for (int cc = c0; cc <= c1; cc++) {
-                        const long long j = (long long)r * (ncc + 1) + cc;
-                        if (a.cellKey[j] > key) {
-                            const uint32_t st = ldcg(&a.cellState[j]);
-                            if (st == 1) {
-                                refused = true;
-                                break;
-                            }
-                            blocked |= st == 0;
-                        }
-                    }
-                if (refused)
-                    a.cellState[i] = 2;
-                else if (!blocked)
-                    a.cellState[i] = 1;
-                else
-                    pending++;
-            }
-            if (pending) atomicAdd(&s_undecided, pending);
-            __syncthreads();
-            if (s_undecided == 0) break;
-            __syncthreads();
-        }
-        // result.size() and the binary-search step, :233-245
-        if (tid == 0) s_kept = 0;
-        __syncthreads();
-        {
-            int k = 0;
-            for (long long i = tid; i < cells; i += SSC_NT) k += ldcg(&a.cellState[i]) == 1;
-            k = __reduce_add_sync(0xffffffffu, k);
-            if ((tid & 31) == 0 && k) atomicAdd(&s_kept, k);
-        }
-        __syncthreads();
+        inSmem = cells <= SSC_SMEM_CELLS;
+        if (inSmem)
+            ssc_width_pass<true>(a, sKey, sState, width, ncc, ncr, &s_undecided, &s_kept);
+        else
+            ssc_width_pass<false>(a, a.cellKey, a.cellState, width, ncc, ncr, &s_undecided, &s_kept);
         if (tid == 0) {
             const uint32_t sz = (uint32_t)s_kept;
             if (sz >= s_kmin && sz <= s_kmax)
@@ -219,9 +284,9 @@ __global__ void __launch_bounds__(SSC_NT) k_select_ssc(const SscArgs a)
     if (s_iters > 0 && !s_err) {
         const long long cells = (long long)(ncr + 1) * (ncc + 1);
         for (long long i = tid; i < cells; i += SSC_NT)
-            if (ldcg(&a.cellState[i]) == 1) {
+            if ((inSmem ? sState[i] : __ldcg(a.cellState + i)) == 1) {
                 const int pos = atomicAdd(&s_nsel, 1);
-                if (pos < SSC_CAP) list[pos] = a.cellKey[i];
+                if (pos < SSC_CAP) list[pos] = inSmem ? sKey[i] : a.cellKey[i];
             }
     }
     __syncthreads();
@@ -230,10 +295,13 @@ __global__ void __launch_bounds__(SSC_NT) k_select_ssc(const SscArgs a)
         __syncthreads();
     }
     const int nsel = min(s_nsel, SSC_CAP);
-    // bitonic sort, descending (larger key = earlier in the reference's sorted keypoint list)
-    for (int k = 2; k <= SSC_CAP; k <<= 1)
+    // bitonic sort, descending (larger key = earlier in the reference's sorted keypoint list), over the power of two that
+    // holds the keepers (the zeros behind them sort last)
+    int sortN = 32;
+    while (sortN < nsel) sortN <<= 1;
+    for (int k = 2; k <= sortN; k <<= 1)
         for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = tid; i < SSC_CAP; i += SSC_NT) {
+            for (int i = tid; i < sortN; i += SSC_NT) {
                 const int ixj = i ^ j;
                 if (ixj > i) {
                     const uint32_t x = list[i], y = list[ixj];
@@ -332,10 +400,11 @@ svo_status launch_select_ssc(svo_ctx* ctx, int slot, uint32_t thr, int numCandid
     a.thr = thr, a.K = numCandidates, a.cell = cell, a.gridRows = rows, a.gridCols = cols;
     a.occ          = useOcc ? ctx->d_occupancy : nullptr;
     a.useBucketing = useBucketing ? 1 : 0;
-    a.cellKey = ctx->d_ssc_key, a.cellState = ctx->d_ssc_state, a.cellCap = cap;
+    a.cellKey = ctx->d_ssc_key, a.cellState = reinterpret_cast<uint8_t*>(ctx->d_ssc_state), a.cellCap = cap;
     a.bucket = ctx->d_cell_best;
     a.out = ctx->d_sel_out, a.maxOut = maxOut, a.count = ctx->d_sel_count, a.info = ctx->d_ssc_info;
-    k_select_ssc<<<1, SSC_NT, 0, ctx->stream>>>(a);
+    SVO_CUDA(cudaFuncSetAttribute(k_select_ssc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SSC_DYN_SMEM));
+    k_select_ssc<<<1, SSC_NT, SSC_DYN_SMEM, ctx->stream>>>(a);
     ctx->launches++;
     SVO_CUDA(cudaGetLastError());
     return SVO_OK;
