@@ -51,19 +51,33 @@ __device__ __forceinline__ void klt_weights(float a, float b, int& w00, int& w01
     w11 = 16384 - w00 - w01 - w10;
 }
 
-__device__ __forceinline__ long long warp_sum_ll(long long v)
+// exact warp total of 32-bit lane values (the total may need up to 37 bits): two hardware reductions, of the low
+// 16 bits and of the (signed) rest, instead of five 64-bit shuffle steps on the serial path of every iteration
+__device__ __forceinline__ long long warp_sum_i32(int v)
 {
-#pragma unroll
-    for (int s = 16; s >= 1; s >>= 1) v += __shfl_xor_sync(0xffffffffu, v, s);
-    return v;
+    const int lo = __reduce_add_sync(0xffffffffu, v & 0xffff);
+    const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
+    return (long long)hi * 65536 + (long long)lo;
 }
 
-// window value of image J at integer origin (ox, oy) + (x, y), x32
+// window value of image J at integer origin (ox, oy) + (x, y), x32.  INTERIOR (uniform over the warp): the whole
+// (win+1)^2 footprint lies inside the image, no reflection
+template <bool INTERIOR>
 __device__ __forceinline__ int klt_sample(const KltImg& J, int ox, int oy, int x, int y, int w00, int w01, int w10, int w11)
 {
     const int X = ox + x, Y = oy + y;
-    const int v = J.at(X, Y) * w00 + J.at(X + 1, Y) * w01 + J.at(X, Y + 1) * w10 + J.at(X + 1, Y + 1) * w11;
+    int v;
+    if (INTERIOR) {
+        const uint8_t* p = J.p + Y * J.pitch + X;
+        v = (int)__ldg(p) * w00 + (int)__ldg(p + 1) * w01 + (int)__ldg(p + J.pitch) * w10 + (int)__ldg(p + J.pitch + 1) * w11;
+    } else {
+        v = J.at(X, Y) * w00 + J.at(X + 1, Y) * w01 + J.at(X, Y + 1) * w10 + J.at(X + 1, Y + 1) * w11;
+    }
     return klt_descale(v, 14 - 5);
+}
+__device__ __forceinline__ bool klt_interior(const KltImg& J, int ox, int oy, int win)
+{
+    return ox >= 0 && oy >= 0 && ox + win < J.w && oy + win < J.h;
 }
 
 __global__ void __launch_bounds__(128) k_klt_track(const KltArgs a)
@@ -73,6 +87,7 @@ __global__ void __launch_bounds__(128) k_klt_track(const KltArgs a)
     const int pt = blockIdx.x * 4 + warp;
     if (pt >= a.n) return;
     const int win = a.win, W1 = win + 1, area = win * win;
+    const int rcpWin = (65536 + win - 1) / win;  // i / win = (i rcpWin) >> 16 exactly for i < 441, win <= 21
     // per warp: derivative pairs of the (win+1)^2 neighbourhood, then the template (value, dx, dy)
     const size_t perWarp = ((size_t)W1 * W1 * 4 + (size_t)area * 6 + 31) & ~size_t(15);
     short2* dS  = reinterpret_cast<short2*>(klt_smem + perWarp * warp);
@@ -140,9 +155,10 @@ __global__ void __launch_bounds__(128) k_klt_track(const KltArgs a)
         int w00, w01, w10, w11;
         klt_weights(__fsub_rn(px, (float)ipx), __fsub_rn(py, (float)ipy), w00, w01, w10, w11);
         long long s11 = 0, s12 = 0, s22 = 0;
+        const bool inI = klt_interior(I, ipx, ipy, win);
         for (int i = lane; i < area; i += 32) {
-            const int y = i / win, x = i - y * win;
-            const int ival = klt_sample(I, ipx, ipy, x, y, w00, w01, w10, w11);
+            const int y = (i * rcpWin) >> 16, x = i - y * win;
+            const int ival = inI ? klt_sample<true>(I, ipx, ipy, x, y, w00, w01, w10, w11) : klt_sample<false>(I, ipx, ipy, x, y, w00, w01, w10, w11);
             const short2 d00 = dS[y * W1 + x], d01 = dS[y * W1 + x + 1], d10 = dS[(y + 1) * W1 + x], d11 = dS[(y + 1) * W1 + x + 1];
             const int ix = klt_descale(d00.x * w00 + d01.x * w01 + d10.x * w10 + d11.x * w11, 14);
             const int iy = klt_descale(d00.y * w00 + d01.y * w01 + d10.y * w10 + d11.y * w11, 14);
@@ -152,7 +168,8 @@ __global__ void __launch_bounds__(128) k_klt_track(const KltArgs a)
             s12 += (long long)(ix * iy);
             s22 += (long long)(iy * iy);
         }
-        s11 = warp_sum_ll(s11), s12 = warp_sum_ll(s12), s22 = warp_sum_ll(s22);
+        // per lane <= ceil(441 / 32) = 14 products of <= 4,080^2: 2.3e8, inside 32 bits
+        s11 = warp_sum_i32((int)s11), s12 = warp_sum_i32((int)s12), s22 = warp_sum_i32((int)s22);
         __syncwarp();
         const float A11 = __fmul_rn((float)s11, FLT_SCALE), A12 = __fmul_rn((float)s12, FLT_SCALE), A22 = __fmul_rn((float)s22, FLT_SCALE);
         float D         = __fsub_rn(__fmul_rn(A11, A22), __fmul_rn(A12, A12));
@@ -174,15 +191,34 @@ __global__ void __launch_bounds__(128) k_klt_track(const KltArgs a)
                 break;
             }
             klt_weights(__fsub_rn(nx, (float)inx), __fsub_rn(ny, (float)iny), w00, w01, w10, w11);
-            long long sb1 = 0, sb2 = 0;
-            for (int i = lane; i < area; i += 32) {
-                const int y = i / win, x = i - y * win;
-                const int diff = klt_sample(J, inx, iny, x, y, w00, w01, w10, w11) - (int)Iw[i];
-                const short2 d = dIw[i];
-                sb1 += (long long)(diff * (int)d.x);
-                sb2 += (long long)(diff * (int)d.y);
+            // per lane <= 14 products of <= 8,160 x 4,080 = 3.3e7: 4.7e8, inside 32 bits
+            int pb1 = 0, pb2 = 0;
+            if (klt_interior(J, inx, iny, win)) {
+                // four window pixels per lane in flight, branch-free (a lane past the end repeats the last pixel with
+                // weight 0): the iteration is a chain of dependent latencies, not of instructions
+                for (int i0 = lane; i0 < area; i0 += 128) {
+#pragma unroll
+                    for (int u = 0; u < 4; u++) {
+                        const int i  = i0 + 32 * u;
+                        const int ii = min(i, area - 1);
+                        const int y = (ii * rcpWin) >> 16, x = ii - y * win;
+                        int diff = klt_sample<true>(J, inx, iny, x, y, w00, w01, w10, w11) - (int)Iw[ii];
+                        diff     = i < area ? diff : 0;
+                        const short2 d = dIw[ii];
+                        pb1 += diff * (int)d.x;
+                        pb2 += diff * (int)d.y;
+                    }
+                }
+            } else {
+                for (int i = lane; i < area; i += 32) {
+                    const int y = (i * rcpWin) >> 16, x = i - y * win;
+                    const int diff = klt_sample<false>(J, inx, iny, x, y, w00, w01, w10, w11) - (int)Iw[i];
+                    const short2 d = dIw[i];
+                    pb1 += diff * (int)d.x;
+                    pb2 += diff * (int)d.y;
+                }
             }
-            sb1 = warp_sum_ll(sb1), sb2 = warp_sum_ll(sb2);
+            const long long sb1 = warp_sum_i32(pb1), sb2 = warp_sum_i32(pb2);
             const float b1 = __fmul_rn((float)sb1, FLT_SCALE), b2 = __fmul_rn((float)sb2, FLT_SCALE);
             const float dx = __fmul_rn(__fsub_rn(__fmul_rn(A12, b2), __fmul_rn(A22, b1)), D);
             const float dy = __fmul_rn(__fsub_rn(__fmul_rn(A12, b1), __fmul_rn(A11, b2)), D);
@@ -205,12 +241,12 @@ __global__ void __launch_bounds__(128) k_klt_track(const KltArgs a)
                 continue;
             }
             klt_weights(__fsub_rn(ex, (float)iex), __fsub_rn(ey, (float)iey), w00, w01, w10, w11);
-            long long se = 0;
+            int pe = 0;
             for (int i = lane; i < area; i += 32) {
-                const int y = i / win, x = i - y * win;
-                se += (long long)abs(klt_sample(J, iex, iey, x, y, w00, w01, w10, w11) - (int)Iw[i]);
+                const int y = (i * rcpWin) >> 16, x = i - y * win;
+                pe += abs(klt_sample<false>(J, iex, iey, x, y, w00, w01, w10, w11) - (int)Iw[i]);
             }
-            se  = warp_sum_ll(se);
+            const long long se = warp_sum_i32(pe);
             err = __fdiv_rn((float)se, (float)(32 * win * win));
         }
     }
