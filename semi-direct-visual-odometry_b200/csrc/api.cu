@@ -50,6 +50,7 @@ void release(svo_ctx* ctx)
     cudaFree(ctx->d_ssc_key);
     cudaFree(ctx->d_ssc_state);
     cudaFree(ctx->d_ssc_info);
+    cudaFreeHost(ctx->h_ssc_info);
     cudaFree(ctx->d_cell_best);
     cudaFree(ctx->d_occupancy);
     cudaFree(ctx->d_sel_out);
@@ -510,11 +511,11 @@ svo_status svo_select_ssc(svo_ctx* ctx, int slot, uint32_t thr, int num_candidat
     const int cap = std::min(ctx->sel_cap_cells, 4096);  // d_sel_out holds sel_cap_cells records
     const svo_status st = launch_select_ssc(ctx, slot, thr, num_candidates, cell, rows, cols, occupancy != nullptr, use_bucketing != 0, cap);
     if (st != SVO_OK) return st;
-    int32_t hinfo[8];
     SVO_CUDA(cudaMemcpyAsync(ctx->h_sel_count, ctx->d_sel_count, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
+    SVO_CUDA(cudaMemcpyAsync(ctx->h_ssc_info, ctx->d_ssc_info, sizeof(int32_t) * 5, cudaMemcpyDeviceToHost, ctx->stream));
     SVO_CUDA(cudaMemcpyAsync(ctx->h_sel_out, ctx->d_sel_out, sizeof(svo_feature_px) * cap, cudaMemcpyDeviceToHost, ctx->stream));
     SVO_CUDA(cudaStreamSynchronize(ctx->stream));
-    SVO_CUDA(cudaMemcpy(hinfo, ctx->d_ssc_info, sizeof(int32_t) * 5, cudaMemcpyDeviceToHost));
+    const int32_t* hinfo = ctx->h_ssc_info;
     if (info)
         for (int i = 0; i < 4; i++) info[i] = hinfo[i];
     if (hinfo[4] == 1) SVO_FAIL(SVO_ERR_CAPACITY, "svo_select_ssc: more SSC cells than the scratch holds");

@@ -82,6 +82,8 @@ struct svo_ctx {
     uint32_t* d_ssc_key;         // svo_select_ssc: champion key / state per SSC cell (allocated on first use)
     uint32_t* d_ssc_state;
     int32_t* d_ssc_info;
+    int32_t* h_ssc_info;         // pinned
+    int ssc_cluster;             // CTAs per cluster of k_select_ssc (decided on first use)
     bool sel_use_occupancy;
 
     // sparse alignment batch

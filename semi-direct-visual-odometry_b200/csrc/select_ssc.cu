@@ -12,15 +12,19 @@
 //     "cells within Chebyshev distance 2", priorities = (gradient desc, raster asc).  It is computed by rounds: a champion
 //     is kept once every higher-priority champion in its 5x5 neighbourhood has been refused, refused once one of them
 //     has been kept; decisions only ever move from undecided to final, so rounds need no double buffering.
-// One CTA runs the whole binary search (count, per-width champions, rounds, decision) without host round trips, sorts
+// One launch runs the whole binary search (count, per-width champions, rounds, decision) without host round trips, sorts
 // the <= 4,096 keepers by priority (the order the reference emits them in) and applies the first-come bucketing of
-// :62-78.  Per width: one thread per cell scans the cell's pixel rectangle (no atomics), the champion key and the state of
-// every cell live in SHARED memory whenever the cell grid fits (36,864 cells: every width >= 7 on a 1241x376 frame; finer
-// grids use the global arrays), and a round loads a cell's whole 5x5 neighbourhood before looking at it.  Phase counters
-// (cycles per width, 1241x376, ~1,500 cells): champions 215 K with an atomicMax per keypoint into global memory -> 140 K
-// with shared-memory atomics and a branch-free two-segment word path -> 80-100 K per-cell scan; rounds 240 K with dependent
-// global loads -> 45 K; count pass 47 K -> 14 K with 16 loads in flight; final sort 80 K -> 16 K over the power of two that
-// holds the keepers.  What remains is one SM's instruction issue (~15 instructions per pixel and width).
+// :62-78.  The launch is ONE CLUSTER of 8 CTAs: all of them scan pixels (one thread per cell scans the cell's pixel
+// rectangle, no atomics) and write the champions straight into CTA 0's shared memory (distributed shared memory); CTA 0
+// owns the cell arrays (36,864 cells fit: every width >= 7 on a 1241x376 frame; finer grids use global arrays), runs the
+// rounds -- a cell's whole 5x5 neighbourhood is loaded before it is looked at, one barrier per round -- and everything
+// after the search.  Every CTA keeps an identical copy of the search state, so the only exchange per width is the keeper
+// count.  Phase counters (cycles per width, 1241x376, ~1,500 cells): champions 215 K with an atomicMax per keypoint into
+// global memory -> 140 K shared-memory atomics, branch-free two-segment words -> 80-100 K per-cell scan -> ~12 K over the
+// cluster; rounds 240 K with dependent global loads -> 45 K; count pass 47 K -> 14 K (16 loads in flight) -> 2 K; final sort
+// 80 K -> 16 K over the power of two that holds the keepers.  What remains is CTA 0's rounds.
+#include <cstdlib>
+
 #include "ctx.h"
 
 namespace {
@@ -51,16 +55,56 @@ struct SscArgs {
 
 __device__ __forceinline__ uint32_t ldcg(const uint32_t* p) { return __ldcg(p); }
 
+// ---- thread-block cluster plumbing: CTA 0 owns the cell arrays and the search state, the other CTAs of the cluster only
+// scan pixels and write their champions into CTA 0's shared memory (distributed shared memory) ----
+__device__ __forceinline__ uint32_t ssc_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ uint32_t ssc_cta0(uint32_t addr)  // the same shared-memory address in CTA 0 of the cluster
+{
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(0u));
+    return r;
+}
+__device__ __forceinline__ void ssc_st_cluster_u32(uint32_t addr, uint32_t v) { asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ void ssc_st_cluster_u8(uint32_t addr, uint32_t v) { asm volatile("st.shared::cluster.u8 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ int ssc_ld_cluster_s32(uint32_t addr)
+{
+    int v;
+    asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void ssc_red_cluster_add(uint32_t addr, int v) { asm volatile("red.shared::cluster.add.s32 [%0], %1;" ::"r"(addr), "r"(v) : "memory"); }
+__device__ __forceinline__ uint32_t ssc_cluster_rank()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ uint32_t ssc_cluster_size()
+{
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+    return r;
+}
+// all threads of all CTAs; orders shared-memory (local and distributed) and global accesses across the cluster
+__device__ __forceinline__ void ssc_sync(int C)
+{
+    if (C == 1)
+        __syncthreads();
+    else
+        asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // One width of the binary search: clear, per-cell champions, rounds of the lexicographically-first maximal independent
 // set, number of keepers.  SM: the cell arrays are the CTA's shared memory (the compiler sees the address space).
 template <bool SM>
-__device__ __forceinline__ int ssc_width_pass(const SscArgs& a, uint32_t* __restrict__ key, uint8_t* state, int width, int ncc, int ncr,
-                                              int* s_undecided, int* s_kept)
+__device__ __forceinline__ void ssc_champions(const SscArgs& a, uint32_t* __restrict__ key, uint8_t* state, int width, int ncc, int ncr,
+                                              int C, int crank)
 {
     const int tid = threadIdx.x;
     const int w = a.w, h = a.h;
-    const double c  = width / 2.0;
     const int cells = (ncr + 1) * (ncc + 1);
+    // SM: the arrays are CTA 0's shared memory -- written through the cluster window (a plain store when C == 1)
+    const uint32_t keyA = SM && C > 1 ? ssc_cta0(ssc_smem_u32(key)) : 0u, stateA = SM && C > 1 ? ssc_cta0(ssc_smem_u32(state)) : 0u;
     // champion of every cell: largest gradient above the threshold, earliest raster position among equals.  The cell of a
     // keypoint is static_cast<int>(kp.pt.x / c) with pt a Point2f and c = width / 2.0 (:199-205): for integer coordinates
     // that is the integer quotient (2 x) / width exactly (a correctly rounded quotient of two integers below 2^53 that is
@@ -73,7 +117,7 @@ __device__ __forceinline__ int ssc_width_pass(const SscArgs& a, uint32_t* __rest
         const int pw4       = a.pitch >> 2;
         const uint32_t* g4  = reinterpret_cast<const uint32_t*>(a.grad);
         const uint32_t thr4 = a.thr * 0x01010101u;
-        for (int i = tid; i < cells; i += SSC_NT) {
+        for (int i = crank * SSC_NT + tid; i < cells; i += C * SSC_NT) {
             const int r = i / (ncc + 1), cc = i - r * (ncc + 1);
             const int ys = (int)(((long long)r * width + 1) >> 1), ye = (int)min((long long)h, ((long long)(r + 1) * width + 1) >> 1);
             const int xs = (int)(((long long)cc * width + 1) >> 1), xe = (int)min((long long)w, ((long long)(cc + 1) * width + 1) >> 1);
@@ -107,16 +151,27 @@ __device__ __forceinline__ int ssc_width_pass(const SscArgs& a, uint32_t* __rest
                     }
                 }
             }
-            key[i]   = bestM ? (bestM << 24) | (0xFFFFFFu - bestPos) : 0u;
-            state[i] = 0;
+            const uint32_t kv = bestM ? (bestM << 24) | (0xFFFFFFu - bestPos) : 0u;
+            if (SM && C > 1) {
+                ssc_st_cluster_u32(keyA + 4u * (uint32_t)i, kv);
+                ssc_st_cluster_u8(stateA + (uint32_t)i, 0u);
+            } else {
+                key[i]   = kv;
+                state[i] = 0;
+            }
         }
     }
-    __syncthreads();
-    // rounds of the lexicographically-first maximal independent set
+}
+
+// rounds of the lexicographically-first maximal independent set over the champions, and the number of keepers (one CTA)
+template <bool SM>
+__device__ __forceinline__ int ssc_rounds(uint32_t* __restrict__ key, uint8_t* state, int width, int ncc, int ncr, int* s_undecided, int* s_kept)
+{
+    const int tid   = threadIdx.x;
+    const double c  = width / 2.0;
+    const int cells = (ncr + 1) * (ncc + 1);
     const int reach = (int)(width / c);  // 2
     while (true) {
-        if (tid == 0) *s_undecided = 0;
-        __syncthreads();
         int pending = 0;
         for (int i = tid; i < cells; i += SSC_NT) {
             if ((SM ? state[i] : __ldcg(state + i)) != 0) continue;
@@ -167,10 +222,7 @@ __device__ __forceinline__ int ssc_width_pass(const SscArgs& a, uint32_t* __rest
             else
                 pending++;
         }
-        if (pending) atomicAdd(s_undecided, pending);
-        __syncthreads();
-        if (*s_undecided == 0) break;
-        __syncthreads();
+        if (!__syncthreads_or(pending)) break;  // one barrier per round: it also carries "anything left?"
     }
     // result.size()
     if (tid == 0) *s_kept = 0;
@@ -194,15 +246,16 @@ __global__ void __launch_bounds__(SSC_NT) k_select_ssc(const SscArgs a)
     __shared__ int s_scan[SSC_NT / 32];
     const int tid = threadIdx.x;
     const int w = a.w, h = a.h;
-    if (tid == 0) s_n = 0, s_iters = 0, s_err = 0, s_done = 0, s_prev = -1, s_width = -1, s_nsel = 0;
-    __syncthreads();
+    const int C = (int)ssc_cluster_size(), crank = (int)ssc_cluster_rank();
+    if (tid == 0) s_n = 0, s_iters = 0, s_err = 0, s_done = 0, s_prev = -1, s_width = -1, s_nsel = 0, s_kept = 0;
+    ssc_sync(C);  // CTA 0's counters are zero before any CTA adds to them
     // ---- keypoints above the threshold, :41-51 ----
     {
         int n = 0;
         const int pw4 = a.pitch >> 2;  // rows are padded to 16 bytes with zeros: four pixels per load
         const uint32_t* g4 = reinterpret_cast<const uint32_t*>(a.grad);
         const int words    = h * pw4;   // the image as one flat array of words (row padding is zeros: never above thr >= 0)
-        for (int i0 = 0; i0 < words; i0 += SSC_NT * 16) {  // sixteen loads per thread in flight
+        for (int i0 = crank * SSC_NT * 16; i0 < words; i0 += C * SSC_NT * 16) {  // sixteen loads per thread in flight
             uint32_t q16[16];
 #pragma unroll
             for (int u = 0; u < 16; u++) {
@@ -213,10 +266,17 @@ __global__ void __launch_bounds__(SSC_NT) k_select_ssc(const SscArgs a)
             for (int u = 0; u < 16; u++) n += __popc(__vcmpgtu4(q16[u], a.thr * 0x01010101u)) >> 3;
         }
         n = __reduce_add_sync(0xffffffffu, n);
-        if ((tid & 31) == 0 && n) atomicAdd(&s_n, n);
+        if ((tid & 31) == 0 && n) {
+            if (C == 1)
+                atomicAdd(&s_n, n);
+            else
+                ssc_red_cluster_add(ssc_cta0(ssc_smem_u32(&s_n)), n);
+        }
     }
-    __syncthreads();
-    if (tid == 0) {  // SSC :172-192
+    ssc_sync(C);
+    if (C > 1 && crank != 0 && tid == 0) s_n = ssc_ld_cluster_s32(ssc_cta0(ssc_smem_u32(&s_n)));
+    // (CTA 0's s_n is not written again: the read needs no further barrier)
+    if (tid == 0) {  // SSC :172-192 -- every CTA keeps its own copy of the search state; the copies stay identical
         const int rows = h, cols = w, K = a.K;
         const int exp1       = rows + cols + 2 * K;
         const long long exp2 = ((long long)4 * cols + (long long)4 * K + (long long)4 * rows * K + (long long)rows * rows +
@@ -262,9 +322,23 @@ __global__ void __launch_bounds__(SSC_NT) k_select_ssc(const SscArgs a)
         }
         inSmem = cells <= SSC_SMEM_CELLS;
         if (inSmem)
-            ssc_width_pass<true>(a, sKey, sState, width, ncc, ncr, &s_undecided, &s_kept);
+            ssc_champions<true>(a, sKey, sState, width, ncc, ncr, C, crank);
         else
-            ssc_width_pass<false>(a, a.cellKey, a.cellState, width, ncc, ncr, &s_undecided, &s_kept);
+            ssc_champions<false>(a, a.cellKey, a.cellState, width, ncc, ncr, C, crank);
+        ssc_sync(C);  // the champions of every CTA are in CTA 0's shared memory (or in global memory)
+        if (crank == 0) {
+            if (inSmem)
+                ssc_rounds<true>(sKey, sState, width, ncc, ncr, &s_undecided, &s_kept);
+            else
+                ssc_rounds<false>(a.cellKey, a.cellState, width, ncc, ncr, &s_undecided, &s_kept);
+        }
+        if (C > 1) {
+            ssc_sync(C);  // CTA 0's keeper count is final
+            if (crank != 0 && tid == 0) s_kept = ssc_ld_cluster_s32(ssc_cta0(ssc_smem_u32(&s_kept)));
+            // (CTA 0 resets it inside the rounds of the next width, i.e. behind the next cluster barrier, which every
+            // CTA reaches only after this read)
+        }
+        __syncthreads();
         if (tid == 0) {
             const uint32_t sz = (uint32_t)s_kept;
             if (sz >= s_kmin && sz <= s_kmax)
@@ -278,6 +352,7 @@ __global__ void __launch_bounds__(SSC_NT) k_select_ssc(const SscArgs a)
         __syncthreads();
         if (s_done) break;
     }
+    if (crank != 0) return;  // no cluster barrier and no access to another CTA's shared memory follows
     // ---- the keepers of the last width walked, in the order the reference emits them (sorted-keypoint order) ----
     for (int i = tid; i < SSC_CAP; i += SSC_NT) list[i] = 0;
     __syncthreads();
@@ -393,6 +468,26 @@ svo_status launch_select_ssc(svo_ctx* ctx, int slot, uint32_t thr, int numCandid
         SVO_CUDA(cudaMalloc(&ctx->d_ssc_key, sizeof(uint32_t) * cap));
         SVO_CUDA(cudaMalloc(&ctx->d_ssc_state, sizeof(uint32_t) * cap));
         SVO_CUDA(cudaMalloc(&ctx->d_ssc_info, sizeof(int32_t) * 8));
+        SVO_CUDA(cudaHostAlloc(&ctx->h_ssc_info, sizeof(int32_t) * 8, cudaHostAllocDefault));
+        SVO_CUDA(cudaFuncSetAttribute(k_select_ssc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SSC_DYN_SMEM));
+        // a cluster of 8 CTAs scans the pixels (SVO_SSC_CLUSTER=1|2|4|8 overrides); CTA 0 owns the cell arrays
+        int C = 8;
+        if (const char* e = getenv("SVO_SSC_CLUSTER")) C = atoi(e);
+        if (C != 1 && C != 2 && C != 4 && C != 8) C = 8;
+        if (C > 1) {
+            cudaLaunchConfig_t q = {};
+            q.gridDim = dim3(C, 1, 1), q.blockDim = dim3(SSC_NT, 1, 1), q.dynamicSmemBytes = SSC_DYN_SMEM;
+            cudaLaunchAttribute qa[1];
+            qa[0].id               = cudaLaunchAttributeClusterDimension;
+            qa[0].val.clusterDim.x = C, qa[0].val.clusterDim.y = 1, qa[0].val.clusterDim.z = 1;
+            q.attrs = qa, q.numAttrs = 1;
+            int maxClusters = 0;
+            if (cudaOccupancyMaxActiveClusters(&maxClusters, k_select_ssc, &q) != cudaSuccess || maxClusters < 1) {
+                cudaGetLastError();  // the device cannot co-schedule the cluster: one CTA does everything
+                C = 1;
+            }
+        }
+        ctx->ssc_cluster = C;
     }
     SscArgs a;
     a.grad = ctx->arena.grad[0] + (int64_t)slot * g.plane_stride;
@@ -403,8 +498,20 @@ svo_status launch_select_ssc(svo_ctx* ctx, int slot, uint32_t thr, int numCandid
     a.cellKey = ctx->d_ssc_key, a.cellState = reinterpret_cast<uint8_t*>(ctx->d_ssc_state), a.cellCap = cap;
     a.bucket = ctx->d_cell_best;
     a.out = ctx->d_sel_out, a.maxOut = maxOut, a.count = ctx->d_sel_count, a.info = ctx->d_ssc_info;
-    SVO_CUDA(cudaFuncSetAttribute(k_select_ssc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SSC_DYN_SMEM));
-    k_select_ssc<<<1, SSC_NT, SSC_DYN_SMEM, ctx->stream>>>(a);
+    const int C            = ctx->ssc_cluster;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim            = dim3(C, 1, 1);
+    cfg.blockDim           = dim3(SSC_NT, 1, 1);
+    cfg.dynamicSmemBytes   = SSC_DYN_SMEM;
+    cfg.stream             = ctx->stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id               = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs                = attr;
+    cfg.numAttrs             = C > 1 ? 1 : 0;
+    SVO_CUDA(cudaLaunchKernelEx(&cfg, k_select_ssc, a));
     ctx->launches++;
     SVO_CUDA(cudaGetLastError());
     return SVO_OK;
