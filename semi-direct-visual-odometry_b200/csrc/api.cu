@@ -77,11 +77,7 @@ void release(svo_ctx* ctx)
     cudaFree(ctx->d_rp_px);
     cudaFree(ctx->d_rp_projected);
     cudaFreeHost(ctx->h_rp_projected);
-    cudaFree(ctx->d_klt_prev);
-    cudaFree(ctx->d_klt_next);
-    cudaFree(ctx->d_klt_status);
-    cudaFree(ctx->d_klt_err);
-    cudaFreeHost(ctx->h_klt);
+    cudaFreeHost(ctx->h_klt);  // d_klt_* are device views of this mapped allocation
     cudaFreeHost(ctx->h_epi_items);
     cudaFreeHost(ctx->h_epi_results);
     cudaFree(ctx->d_epi_items);
@@ -820,25 +816,28 @@ svo_status svo_klt_track(svo_ctx* ctx, int ref_slot, int cur_slot, const float* 
     if (n == 0) return SVO_OK;
     SVO_CUDA(cudaSetDevice(ctx->cfg.device));
     const size_t nf = (size_t)std::max(1, ctx->cfg.max_fa_items);
-    if (!ctx->d_klt_prev) {
-        SVO_CUDA(cudaMalloc(&ctx->d_klt_prev, sizeof(float2) * nf));
-        SVO_CUDA(cudaMalloc(&ctx->d_klt_next, sizeof(float2) * nf));
-        SVO_CUDA(cudaMalloc(&ctx->d_klt_status, nf));
-        SVO_CUDA(cudaMalloc(&ctx->d_klt_err, sizeof(float) * nf));
-        SVO_CUDA(cudaHostAlloc(&ctx->h_klt, nf * 13, cudaHostAllocDefault));
+    if (!ctx->h_klt) {
+        // Zero-copy: a few KB in, a few KB out.  The kernel reads the points from and writes the results to mapped
+        // page-locked host memory directly (one PCIe transaction per warp each way), which saves the two DMA round trips
+        // (~10 us each) that cudaMemcpyAsync would put in front of and behind a ~40 us kernel.
+        SVO_CUDA(cudaHostAlloc(&ctx->h_klt, nf * 21, cudaHostAllocMapped));
+        unsigned char* d = nullptr;
+        SVO_CUDA(cudaHostGetDevicePointer(&d, ctx->h_klt, 0));
+        ctx->d_klt_prev   = reinterpret_cast<float2*>(d);
+        ctx->d_klt_next   = reinterpret_cast<float2*>(d + 8 * nf);
+        ctx->d_klt_err    = reinterpret_cast<float*>(d + 16 * nf);
+        ctx->d_klt_status = d + 20 * nf;
     }
     svo_status st = wait_ingest(ctx);
     if (st != SVO_OK) return st;
     SVO_CUDA(cudaStreamSynchronize(ctx->stream));
-    float* hNext     = reinterpret_cast<float*>(ctx->h_klt);
+    float* hPrev     = reinterpret_cast<float*>(ctx->h_klt);
+    float* hNext     = hPrev + 2 * nf;
     float* hErr      = hNext + 2 * nf;
     uint8_t* hStatus = reinterpret_cast<uint8_t*>(hErr + nf);
-    SVO_CUDA(cudaMemcpyAsync(ctx->d_klt_prev, prev_pts, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream));
-    SVO_CUDA(cudaMemcpyAsync(ctx->d_klt_next, next_pts, sizeof(float2) * n, cudaMemcpyHostToDevice, ctx->stream));
+    std::memcpy(hPrev, prev_pts, sizeof(float2) * n);
+    std::memcpy(hNext, next_pts, sizeof(float2) * n);
     if ((st = launch_klt_track(ctx, ref_slot, cur_slot, n, *prm, top)) != SVO_OK) return st;
-    SVO_CUDA(cudaMemcpyAsync(hNext, ctx->d_klt_next, sizeof(float2) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    SVO_CUDA(cudaMemcpyAsync(hErr, ctx->d_klt_err, sizeof(float) * n, cudaMemcpyDeviceToHost, ctx->stream));
-    SVO_CUDA(cudaMemcpyAsync(hStatus, ctx->d_klt_status, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     SVO_CUDA(cudaStreamSynchronize(ctx->stream));
     std::memcpy(next_pts, hNext, sizeof(float2) * n);
     std::memcpy(status, hStatus, (size_t)n);
