@@ -46,6 +46,7 @@ struct SscArgs {
     uint32_t* cellKey;    // champion of each SSC cell: gradient << 24 | (0xFFFFFF - raster index); 0 = no keypoint
     uint8_t* cellState;   // 0 undecided, 1 kept, 2 refused
     long long cellCap;
+    int smemCells;        // cell grids up to this size live in CTA 0's shared memory (SSC_SMEM_CELLS; 0 forces the global arrays)
     uint32_t* bucket;     // per occupancy-grid cell: position of its first keeper
     svo_feature_px* out;
     int maxOut;
@@ -320,7 +321,7 @@ __global__ void __launch_bounds__(SSC_NT) k_select_ssc(const SscArgs a)
             __syncthreads();
             break;
         }
-        inSmem = cells <= SSC_SMEM_CELLS;
+        inSmem = cells <= a.smemCells;
         if (inSmem)
             ssc_champions<true>(a, sKey, sState, width, ncc, ncr, C, crank);
         else
@@ -496,6 +497,8 @@ svo_status launch_select_ssc(svo_ctx* ctx, int slot, uint32_t thr, int numCandid
     a.occ          = useOcc ? ctx->d_occupancy : nullptr;
     a.useBucketing = useBucketing ? 1 : 0;
     a.cellKey = ctx->d_ssc_key, a.cellState = reinterpret_cast<uint8_t*>(ctx->d_ssc_state), a.cellCap = cap;
+    a.smemCells = SSC_SMEM_CELLS;
+    if (const char* e = getenv("SVO_SSC_SMEM_CELLS")) a.smemCells = std::min(std::max(atoi(e), 0), SSC_SMEM_CELLS);  // tests: global-array path
     a.bucket = ctx->d_cell_best;
     a.out = ctx->d_sel_out, a.maxOut = maxOut, a.count = ctx->d_sel_count, a.info = ctx->d_ssc_info;
     const int C            = ctx->ssc_cluster;

@@ -617,6 +617,24 @@ def test_select_ssc_ties_occupancy_and_sparse(pkg, orc):
                     assert np.array_equal(np.stack([got["x"], got["y"], got["magnitude"]], 1), want), (slot, k)
 
 
+def test_select_ssc_global_array_path(pkg, orc, pair_cache, monkeypatch):
+    """Cell grids that do not fit CTA 0's shared memory use the global arrays, written by every CTA of the cluster and read
+    by CTA 0 behind the cluster barrier: forced here for ordinary widths (SVO_SSC_SMEM_CELLS=0), several calls in a row."""
+    pair = pair_cache(6, 300)
+    with _ctx(pkg, pair) as ctx:
+        ctx.upload(0, np.stack([pair["ref"], pair["cur"]]))
+        grad = ctx.download(0, 0, 1)
+        for smem in ("0", None):
+            if smem is None:
+                monkeypatch.delenv("SVO_SSC_SMEM_CELLS", raising=False)
+            else:
+                monkeypatch.setenv("SVO_SSC_SMEM_CELLS", smem)
+            for thr, k in ((40, 120), (15, 900), (90, 60), (40, 120)):
+                got, info = ctx.select_ssc(0, thr, k)
+                want, winfo = orc.select_ssc(grad, thr, k)
+                assert np.array_equal(np.stack([got["x"], got["y"], got["magnitude"]], 1), want), (smem, thr, k)
+
+
 def test_next_rows_golden_gpu(pkg, synth):
     """The CUDA path against golden vectors that neither it nor the oracle produced (tests/golden/make_golden_next.py)."""
     from test_oracle_numerics import _check_next_rows_golden
