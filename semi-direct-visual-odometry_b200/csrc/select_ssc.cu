@@ -166,7 +166,7 @@ __device__ __forceinline__ void ssc_champions(const SscArgs& a, uint32_t* __rest
 
 // rounds of the lexicographically-first maximal independent set over the champions, and the number of keepers (one CTA)
 template <bool SM>
-__device__ __forceinline__ int ssc_rounds(uint32_t* __restrict__ key, uint8_t* state, int width, int ncc, int ncr, int* s_undecided, int* s_kept)
+__device__ __forceinline__ int ssc_rounds(uint32_t* __restrict__ key, uint8_t* state, int width, int ncc, int ncr, int* s_kept)
 {
     const int tid   = threadIdx.x;
     const double c  = width / 2.0;
@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(SSC_NT) k_select_ssc(const SscArgs a)
 {
     __shared__ uint32_t list[SSC_CAP];
     __shared__ uint32_t keep[SSC_CAP];
-    __shared__ int s_n, s_undecided, s_kept, s_low, s_high, s_prev, s_done, s_width, s_iters, s_err, s_nsel;
+    __shared__ int s_n, s_kept, s_low, s_high, s_prev, s_done, s_width, s_iters, s_err, s_nsel;
     __shared__ uint32_t s_kmin, s_kmax;
     __shared__ int s_scan[SSC_NT / 32];
     const int tid = threadIdx.x;
@@ -329,9 +329,9 @@ __global__ void __launch_bounds__(SSC_NT) k_select_ssc(const SscArgs a)
         ssc_sync(C);  // the champions of every CTA are in CTA 0's shared memory (or in global memory)
         if (crank == 0) {
             if (inSmem)
-                ssc_rounds<true>(sKey, sState, width, ncc, ncr, &s_undecided, &s_kept);
+                ssc_rounds<true>(sKey, sState, width, ncc, ncr, &s_kept);
             else
-                ssc_rounds<false>(a.cellKey, a.cellState, width, ncc, ncr, &s_undecided, &s_kept);
+                ssc_rounds<false>(a.cellKey, a.cellState, width, ncc, ncr, &s_kept);
         }
         if (C > 1) {
             ssc_sync(C);  // CTA 0's keeper count is final
