@@ -636,7 +636,8 @@ __device__ __forceinline__ bool cs_tiered_select(const uint32_t (&key)[AREA], bo
             const uint32_t b = cs_private_coarse<AREA, NT>(key, live, coarseBase, k, kFromAux, sc, &below);
             if (kFromAux && sc.auxTotal == 0) return false;
             kFromAux = false;
-            if (b == 0 || b == 63) {  // clamped outer bins
+            // clamped outer bins (bin 0 clamps nothing when the coarse range starts at key 0, as for the MAD keys)
+            if ((b == 0 && coarseBase > 0) || b == 63) {
                 *tier = 4;
                 uint32_t rank;
                 kOut = cs_generic_select27<AREA, NT>(key, live, (uint32_t)k, sc, &rank);
