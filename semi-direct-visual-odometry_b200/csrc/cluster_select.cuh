@@ -159,8 +159,8 @@ struct SelCtx {  // uniform over the cluster
     uint32_t tBelow, tAux, tMax;  // cluster totals of the last finished round
     uint32_t auxTotal;            // aux total of the round that fixed a rank (kFromAux)
 #ifdef SVO_PROFILE
-    long long stat[20];           // hot attempts by shift [0..7], hits by shift [8..15], [16] hits with <= 128 keys inside,
-                                  // [17] <= 256, [18] <= 512, [19] sum of keys inside over the hits
+    long long stat[20];           // hot attempts by shift [0..7], hits by shift [8..15]; first evaluation of a level with a
+                                  // carried bracket: [16] median attempts [17] hits [18] MAD attempts [19] hits
     uint32_t lastInside;
     long long prof[12], tlast;    // cycles: 0 push 1 pop A 2 finish A 3 locate A 4 pop B 5 finish B 6 locate B 7 private count
                                   //         8 private reduce 9 private finish + scan 10 other
@@ -654,10 +654,6 @@ __device__ __forceinline__ bool cs_tiered_select(const uint32_t (&key)[AREA], bo
             sc.stat[shift]++;
             if (rc == 0) {
                 sc.stat[8 + shift]++;
-                sc.stat[16] += sc.lastInside <= 128;
-                sc.stat[17] += sc.lastInside <= 256;
-                sc.stat[18] += sc.lastInside <= 512;
-                sc.stat[19] += sc.lastInside;
             }
         }
 #endif

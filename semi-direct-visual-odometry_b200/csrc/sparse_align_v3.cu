@@ -339,14 +339,17 @@ __global__ void __launch_bounds__(NT, V3Occ<NT>::MINB) k_align_cluster(const V3A
         uint32_t winLo[G::FW], winHi[G::FW];
         int wx = 0, wy = 0;
         bool winValid = false;
-        // selection brackets carried between evaluations; a new level starts from the previous level's last result
-        // with the widest bracket (the residual distribution of the finer level is a refinement of the coarser one)
+        // selection brackets carried between evaluations.  Across a level change only the MEDIAN's is worth trying, and
+        // only when the level above was iterated: measured on 12 pairs (tests/cuda/bracket_probe.py), the widest bracket
+        // around the previous level's median holds the new one in 36 of 36 cases with GN, in 14 of 36 with the reference's
+        // one step per level, and the MAD's in 2 of 36 / 0 of 36 (the residual scale changes with the level) -- a miss
+        // costs a whole sweep before the cold tier starts.
         if (si == 0) {
             brMed = Bracket{0u, 7, false, false};
             brMad = Bracket{0u, 7, false, false};
         } else {
-            brMed.valid = brMed.have;
-            brMad.valid = brMad.have;
+            brMed.valid = brMed.have && a.prm.mode != SVO_LM_FAITHFUL;
+            brMad.valid = false;
             brMed.shift = brMad.shift = 7;
             brMed.have = brMad.have = false;
         }
@@ -461,6 +464,9 @@ __global__ void __launch_bounds__(NT, V3Occ<NT>::MINB) k_align_cluster(const V3A
 #pragma unroll 1
             for (int s = 0; s < 2; s++) {
                 Bracket b = s ? brMad : brMed;
+#ifdef SVO_PROFILE
+                const bool brMadTried = brMad.valid, brMedTried = brMed.valid;
+#endif
                 uint32_t kHi, kLo;
                 int tier;
                 // mean of elements mid-1 and mid when N is even: the selection returns both
@@ -469,6 +475,12 @@ __global__ void __launch_bounds__(NT, V3Occ<NT>::MINB) k_align_cluster(const V3A
                     brMad = b;
                 else
                     brMed = b;
+#ifdef SVO_PROFILE
+                if (si > 0 && ctrl->evals_level == 0 && (s ? brMadTried : brMedTried)) {  // first evaluation of a level: carried bracket
+                    sc.stat[16 + 2 * s]++;
+                    sc.stat[17 + 2 * s] += tier == 1;
+                }
+#endif
                 if (!ok) break;  // no visible pixel (s == 0 only)
                 tierCount += tier == 1 ? 1 : (tier == 2 ? 0x100 : 0x10000);
                 if (s == 0) {
