@@ -70,13 +70,9 @@ void release(svo_ctx* ctx)
     cudaFree(ctx->d_scratch_jac);
     cudaFree(ctx->d_scratch2);
     cudaFree(ctx->d_dbg);
-    cudaFree(ctx->d_rp_cands);
+    cudaFreeHost(ctx->h_rp);  // d_rp_cands, d_rp_order, d_rp_out, d_rp_projected, d_rp_count are views of it
     cudaFree(ctx->d_rp_matches);
-    cudaFreeHost(ctx->h_rp_matches);
-    cudaFree(ctx->d_rp_order);
     cudaFree(ctx->d_rp_px);
-    cudaFree(ctx->d_rp_projected);
-    cudaFreeHost(ctx->h_rp_projected);
     cudaFreeHost(ctx->h_klt);  // d_klt_* are device views of this mapped allocation
     cudaFreeHost(ctx->h_epi_items);
     cudaFreeHost(ctx->h_epi_results);
@@ -736,29 +732,35 @@ svo_status svo_reproject_map(svo_ctx* ctx, int cur_slot, const double T_cur[7], 
     for (int i = 0; i < n; i++)
         if (bad_slot(ctx, cands[i].ref_slot)) SVO_FAIL(SVO_ERR_INVALID, "svo_reproject_map: candidate frame slot out of range");
     SVO_CUDA(cudaSetDevice(ctx->cfg.device));
-    if (!ctx->d_rp_cands) {
-        const size_t nf = (size_t)std::max(1, ctx->cfg.max_fa_items);
-        SVO_CUDA(cudaMalloc(&ctx->d_rp_cands, sizeof(svo_reproj_candidate) * nf));
+    const size_t nf = (size_t)std::max(1, ctx->cfg.max_fa_items), nc = (size_t)std::max(1, ctx->sel_cap_cells);
+    auto up16 = [](size_t v) { return (v + 15) & ~size_t(15); };
+    const size_t offOrder = up16(sizeof(svo_reproj_candidate) * nf), offOut = up16(offOrder + sizeof(int32_t) * nc);
+    const size_t offProj = up16(offOut + sizeof(svo_reproj_match) * nf), offCount = up16(offProj + nf);
+    if (!ctx->h_rp) {
+        // Zero-copy: ~50 KB in, ~8 KB out.  The kernels read the candidates and the cell order from, and write the
+        // matches, flags and count to, mapped page-locked host memory; no DMA round trip on either side of four tiny
+        // launches (every input word is read once, coalesced).
+        SVO_CUDA(cudaHostAlloc(&ctx->h_rp, offCount + 16, cudaHostAllocMapped));
+        unsigned char* d = nullptr;
+        SVO_CUDA(cudaHostGetDevicePointer(&d, ctx->h_rp, 0));
+        ctx->d_rp_cands     = reinterpret_cast<svo_reproj_candidate*>(d);
+        ctx->d_rp_order     = reinterpret_cast<int32_t*>(d + offOrder);
+        ctx->d_rp_out       = reinterpret_cast<svo_reproj_match*>(d + offOut);
+        ctx->d_rp_projected = d + offProj;
+        ctx->d_rp_count     = reinterpret_cast<int32_t*>(d + offCount);
         SVO_CUDA(cudaMalloc(&ctx->d_rp_matches, sizeof(svo_reproj_match) * nf));
-        SVO_CUDA(cudaHostAlloc(&ctx->h_rp_matches, sizeof(svo_reproj_match) * nf, cudaHostAllocDefault));
-        SVO_CUDA(cudaMalloc(&ctx->d_rp_order, sizeof(int32_t) * ctx->sel_cap_cells));
         SVO_CUDA(cudaMalloc(&ctx->d_rp_px, sizeof(double) * 2 * nf));
-        SVO_CUDA(cudaMalloc(&ctx->d_rp_projected, nf));
-        SVO_CUDA(cudaHostAlloc(&ctx->h_rp_projected, nf, cudaHostAllocDefault));
     }
     svo_status st = wait_ingest(ctx);
     if (st != SVO_OK) return st;
     SVO_CUDA(cudaStreamSynchronize(ctx->stream));
-    if (n) SVO_CUDA(cudaMemcpyAsync(ctx->d_rp_cands, cands, sizeof(svo_reproj_candidate) * n, cudaMemcpyHostToDevice, ctx->stream));
-    SVO_CUDA(cudaMemcpyAsync(ctx->d_rp_order, cell_order, sizeof(int32_t) * n_cells, cudaMemcpyHostToDevice, ctx->stream));
+    if (n) std::memcpy(ctx->h_rp, cands, sizeof(svo_reproj_candidate) * n);
+    std::memcpy(ctx->h_rp + offOrder, cell_order, sizeof(int32_t) * n_cells);
     if ((st = launch_reproject_map(ctx, cur_slot, T_cur, n, cell_size, n_cells, gridCols, maxItems, *fa)) != SVO_OK) return st;
-    SVO_CUDA(cudaMemcpyAsync(ctx->h_sel_count, ctx->d_sel_count, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    SVO_CUDA(cudaMemcpyAsync(ctx->h_rp_matches, ctx->d_rp_matches, sizeof(svo_reproj_match) * maxItems, cudaMemcpyDeviceToHost, ctx->stream));
-    if (n) SVO_CUDA(cudaMemcpyAsync(ctx->h_rp_projected, ctx->d_rp_projected, (size_t)n, cudaMemcpyDeviceToHost, ctx->stream));
     SVO_CUDA(cudaStreamSynchronize(ctx->stream));
-    *n_matches = *ctx->h_sel_count;
-    std::memcpy(matches, ctx->h_rp_matches, sizeof(svo_reproj_match) * *n_matches);
-    if (projected && n) std::memcpy(projected, ctx->h_rp_projected, (size_t)n);
+    *n_matches = *reinterpret_cast<const int32_t*>(ctx->h_rp + offCount);
+    std::memcpy(matches, ctx->h_rp + offOut, sizeof(svo_reproj_match) * *n_matches);
+    if (projected && n) std::memcpy(projected, ctx->h_rp + offProj, (size_t)n);
     return SVO_OK;
 }
 

@@ -116,13 +116,14 @@ struct svo_ctx {
     svo_fa_result* h_fe_fa;        // pinned, max_features records
 
     // Map::reprojectMap batch (svo_reproject_map), capacity max_fa_items candidates / sel_cap_cells cells
+    unsigned char* h_rp;  // mapped page-locked block: candidates | cell order | finished matches | projected flags | count
+    svo_reproj_match* d_rp_out;   // device views of its parts (d_rp_cands, d_rp_order, d_rp_projected are views too)
+    int32_t* d_rp_count;
     svo_reproj_candidate* d_rp_cands;
     svo_reproj_match* d_rp_matches;
-    svo_reproj_match* h_rp_matches;  // pinned
     int32_t* d_rp_order;
     double* d_rp_px;
     uint8_t* d_rp_projected;
-    uint8_t* h_rp_projected;         // pinned
 
     // epipolar search batch (depth-filter seeds), capacity max_fa_items
     // svo_klt_track

@@ -114,14 +114,19 @@ __global__ void __launch_bounds__(1024) k_reproject_emit(const ReprojEmitArgs a)
     if (threadIdx.x == 0) *a.count = min(base, a.maxItems);
 }
 
-__global__ void k_reproject_finish(const svo_fa_result* fa, svo_reproj_match* matches, const int32_t* count)
+// the records go straight to the caller-visible mapped host buffer (out, outCount): no copy behind the last kernel
+__global__ void k_reproject_finish(const svo_fa_result* fa, const svo_reproj_match* matches, const int32_t* count, svo_reproj_match* out,
+                                   int32_t* outCount)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *outCount = *count;
     if (i >= *count) return;
-    matches[i].px[0]  = fa[i].px[0];
-    matches[i].px[1]  = fa[i].px[1];
-    matches[i].rmse   = fa[i].rmse;
-    matches[i].status = fa[i].status;
+    svo_reproj_match m = matches[i];
+    m.px[0]  = fa[i].px[0];
+    m.px[1]  = fa[i].px[1];
+    m.rmse   = fa[i].rmse;
+    m.status = fa[i].status;
+    out[i]   = m;
 }
 
 }  // namespace
@@ -147,7 +152,8 @@ svo_status launch_reproject_map(svo_ctx* ctx, int curSlot, const double T[7], in
     ctx->staged_fa_params = fa;
     const svo_status st   = launch_feature_align(ctx);
     if (st != SVO_OK) return st;
-    k_reproject_finish<<<(maxItems + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_fa_results, ctx->d_rp_matches, ctx->d_sel_count);
+    k_reproject_finish<<<(maxItems + 127) / 128, 128, 0, ctx->stream>>>(ctx->d_fa_results, ctx->d_rp_matches, ctx->d_sel_count, ctx->d_rp_out,
+                                                                       ctx->d_rp_count);
     ctx->launches += 3;
     SVO_CUDA(cudaGetLastError());
     return SVO_OK;
