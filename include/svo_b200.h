@@ -17,7 +17,10 @@
  *   - there is NO CPU fallback: without a CUDA device svo_create fails with SVO_ERR_NO_DEVICE.
  *   - compute is enqueued on one CUDA stream (svo_config.stream, or a private one); host->device copies and the
  *     kernels of svo_frames_prefetch run on private copy / ingest streams of the context, ordered with the main
- *     stream by events.  Calls on one context must be serialised by the caller.
+ *     stream by events.  Every entry point holds the context's lock for the duration of the call: calls from
+ *     several threads (the reference's depth-filter thread next to the tracker) are serialised, never
+ *     interleaved.  The phase-split forms (..._stage / _h2d / _launch / _d2h / _fetch) keep state in the context
+ *     between calls: one thread drives such a sequence at a time.
  */
 #ifndef SVO_B200_H
 #define SVO_B200_H

@@ -249,6 +249,7 @@ const char* svo_last_error(const svo_ctx* ctx) { return ctx ? ctx->err.c_str() :
 svo_status svo_sync(svo_ctx* ctx)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     SVO_CUDA(cudaStreamSynchronize(ctx->ingest_stream));
     SVO_CUDA(cudaStreamSynchronize(ctx->stream));
     return SVO_OK;
@@ -260,7 +261,7 @@ void* svo_stream(const svo_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr
 
 svo_status svo_level_dims(const svo_ctx* ctx, int level, int* w, int* h, int* pitch)
 {
-    if (!ctx || level < 0 || level >= ctx->arena.levels) return SVO_ERR_INVALID;
+    if (!ctx || level < 0 || level >= ctx->arena.levels) return SVO_ERR_INVALID;  // immutable after svo_create: no lock
     if (w) *w = ctx->arena.geom[level].w;
     if (h) *h = ctx->arena.geom[level].h;
     if (pitch) *pitch = ctx->arena.geom[level].pitch;
@@ -270,6 +271,7 @@ svo_status svo_level_dims(const svo_ctx* ctx, int level, int* w, int* h, int* pi
 svo_status svo_host_alloc(svo_ctx* ctx, int64_t bytes, void** out)
 {
     if (!ctx || !out || bytes <= 0) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     SVO_CUDA(cudaSetDevice(ctx->cfg.device));
     SVO_CUDA(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocDefault));
     return SVO_OK;
@@ -278,6 +280,7 @@ svo_status svo_host_alloc(svo_ctx* ctx, int64_t bytes, void** out)
 svo_status svo_host_free(svo_ctx* ctx, void* p)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     if (p) SVO_CUDA(cudaFreeHost(p));
     return SVO_OK;
 }
@@ -289,6 +292,7 @@ static svo_status frames_upload_impl(svo_ctx* ctx, int first_slot, int n, const 
                                      bool overlap)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     if (n == 0) return SVO_OK;
     const LevelGeom& g = ctx->arena.geom[0];
     if (!imgs || n < 0 || bad_slot(ctx, first_slot) || bad_slot(ctx, first_slot + n - 1) || pitch < g.w ||
@@ -401,6 +405,7 @@ svo_status svo_frames_prefetch(svo_ctx* ctx, int first_slot, int n, const uint8_
 svo_status svo_frames_upload_device(svo_ctx* ctx, int first_slot, int n, const void* dptr, int pitch, int64_t frame_stride)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     if (n == 0) return SVO_OK;
     const LevelGeom& g = ctx->arena.geom[0];
     if (!dptr || n < 0 || bad_slot(ctx, first_slot) || bad_slot(ctx, first_slot + n - 1) || pitch < g.w)
@@ -418,6 +423,7 @@ svo_status svo_frames_upload_device(svo_ctx* ctx, int first_slot, int n, const v
 svo_status svo_frames_rebuild(svo_ctx* ctx, int first_slot, int n)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     if (n == 0) return SVO_OK;
     if (n < 0 || bad_slot(ctx, first_slot) || bad_slot(ctx, first_slot + n - 1))
         SVO_FAIL(SVO_ERR_INVALID, "svo_frames_rebuild: bad slot range");
@@ -432,6 +438,7 @@ svo_status svo_frames_rebuild(svo_ctx* ctx, int first_slot, int n)
 svo_status svo_frame_download(svo_ctx* ctx, int slot, int level, int which, uint8_t* dst, int dst_pitch)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     if (!dst || bad_slot(ctx, slot) || level < 0 || level >= ctx->arena.levels || (which != 0 && which != 1))
         SVO_FAIL(SVO_ERR_INVALID, "svo_frame_download: bad slot / level / which");
     const LevelGeom& g = ctx->arena.geom[level];
@@ -454,6 +461,7 @@ svo_status svo_select_grid(svo_ctx* ctx, int slot, int cell, uint32_t thr, const
                            int max_out, int* n_out)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     if (!out || !n_out || max_out < 0 || bad_slot(ctx, slot) || cell < 4)
         SVO_FAIL(SVO_ERR_INVALID, "svo_select_grid: bad arguments (cell must be >= 4)");
     const LevelGeom& g = ctx->arena.geom[0];
@@ -486,6 +494,7 @@ svo_status svo_select_ssc(svo_ctx* ctx, int slot, uint32_t thr, int num_candidat
                           int use_bucketing, svo_feature_px* out, int max_out, int* n_out, int32_t* info)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     if (!out || !n_out || max_out < 0 || bad_slot(ctx, slot) || cell < 4 || num_candidates < 2)
         SVO_FAIL(SVO_ERR_INVALID, "svo_select_ssc: bad arguments (cell >= 4, num_candidates >= 2)");
     const LevelGeom& g = ctx->arena.geom[0];
@@ -525,6 +534,7 @@ svo_status svo_sparse_align_stage(svo_ctx* ctx, const svo_align_job* jobs, int n
                                   int n_feats, const svo_align_params* prm, int want_stats)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     if (!jobs || !prm || n_jobs < 0 || n_feats < 0 || (n_feats > 0 && !feats))
         SVO_FAIL(SVO_ERR_INVALID, "svo_sparse_align: null argument");
     if (n_jobs > ctx->cfg.max_jobs || n_feats > ctx->feats_cap)
@@ -577,6 +587,7 @@ svo_status svo_sparse_align_stage(svo_ctx* ctx, const svo_align_job* jobs, int n
 svo_status svo_sparse_align_h2d(svo_ctx* ctx)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     if (ctx->staged_jobs == 0) return SVO_OK;
     // On the COPY stream, i.e. in call order with the frame DMA: the copy engine drains one stream's queued transfers
     // before it turns to another, so a small copy on the main stream would sit behind every frame batch that a
@@ -594,6 +605,7 @@ svo_status svo_sparse_align_h2d(svo_ctx* ctx)
 svo_status svo_sparse_align_launch(svo_ctx* ctx)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     const svo_status ws = wait_ingest(ctx);
     if (ws != SVO_OK) return ws;
     return launch_sparse_align(ctx);
@@ -602,6 +614,7 @@ svo_status svo_sparse_align_launch(svo_ctx* ctx)
 svo_status svo_sparse_align_d2h(svo_ctx* ctx)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     if (ctx->staged_jobs == 0) return SVO_OK;
     SVO_CUDA(cudaMemcpyAsync(ctx->h_results, ctx->d_results, sizeof(svo_align_result) * ctx->staged_jobs,
                              cudaMemcpyDeviceToHost, ctx->stream));
@@ -615,6 +628,7 @@ svo_status svo_sparse_align_d2h(svo_ctx* ctx)
 svo_status svo_sparse_align_fetch(svo_ctx* ctx, svo_align_result* results, svo_align_level_stats* stats)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     SVO_CUDA(cudaStreamSynchronize(ctx->stream));
     if (results) std::memcpy(results, ctx->h_results, sizeof(svo_align_result) * ctx->staged_jobs);
     if (stats) {
@@ -627,6 +641,7 @@ svo_status svo_sparse_align_fetch(svo_ctx* ctx, svo_align_result* results, svo_a
 svo_status svo_debug_cycles(svo_ctx* ctx, int64_t* out64)
 {
     if (!ctx || !out64) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     SVO_CUDA(cudaStreamSynchronize(ctx->stream));
     SVO_CUDA(cudaMemcpy(out64, ctx->d_dbg, 64 * sizeof(long long), cudaMemcpyDeviceToHost));
     return SVO_OK;
@@ -651,6 +666,7 @@ svo_status svo_sparse_align(svo_ctx* ctx, const svo_align_job* jobs, int n_jobs,
 svo_status svo_feature_align_stage(svo_ctx* ctx, const svo_fa_item* items, int n, const svo_fa_params* prm)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     if (n < 0 || !prm || (n > 0 && !items)) SVO_FAIL(SVO_ERR_INVALID, "svo_feature_align: null argument");
     if (n > ctx->cfg.max_fa_items) SVO_FAIL(SVO_ERR_CAPACITY, "svo_feature_align: more items than max_fa_items");
     if (prm->patch_size < 1 || prm->patch_size > 8 || prm->mode < SVO_LM_FAITHFUL || prm->mode > SVO_GN)
@@ -669,6 +685,7 @@ svo_status svo_feature_align_stage(svo_ctx* ctx, const svo_fa_item* items, int n
 svo_status svo_feature_align_h2d(svo_ctx* ctx)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     if (ctx->staged_fa)
         SVO_CUDA(cudaMemcpyAsync(ctx->d_fa_items, ctx->h_fa_items, sizeof(svo_fa_item) * ctx->staged_fa,
                                  cudaMemcpyHostToDevice, ctx->stream));
@@ -678,6 +695,7 @@ svo_status svo_feature_align_h2d(svo_ctx* ctx)
 svo_status svo_feature_align_launch(svo_ctx* ctx)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     const svo_status ws = wait_ingest(ctx);
     if (ws != SVO_OK) return ws;
     return launch_feature_align(ctx);
@@ -686,6 +704,7 @@ svo_status svo_feature_align_launch(svo_ctx* ctx)
 svo_status svo_feature_align_d2h(svo_ctx* ctx)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     if (ctx->staged_fa)
         SVO_CUDA(cudaMemcpyAsync(ctx->h_fa_results, ctx->d_fa_results, sizeof(svo_fa_result) * ctx->staged_fa,
                                  cudaMemcpyDeviceToHost, ctx->stream));
@@ -695,6 +714,7 @@ svo_status svo_feature_align_d2h(svo_ctx* ctx)
 svo_status svo_feature_align_fetch(svo_ctx* ctx, svo_fa_result* results)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     SVO_CUDA(cudaStreamSynchronize(ctx->stream));
     if (results && ctx->staged_fa) std::memcpy(results, ctx->h_fa_results, sizeof(svo_fa_result) * ctx->staged_fa);
     return SVO_OK;
@@ -718,6 +738,7 @@ svo_status svo_reproject_map(svo_ctx* ctx, int cur_slot, const double T_cur[7], 
                              svo_reproj_match* matches, int* n_matches, uint8_t* projected)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     if (!T_cur || n < 0 || (n > 0 && !cands) || !cell_order || !fa || !matches || !n_matches || cell_size < 4 || max_matches < 0 ||
         bad_slot(ctx, cur_slot))
         SVO_FAIL(SVO_ERR_INVALID, "svo_reproject_map: bad arguments");
@@ -770,6 +791,7 @@ svo_status svo_reproject_map(svo_ctx* ctx, int cur_slot, const double T_cur[7], 
 svo_status svo_epipolar_match(svo_ctx* ctx, const svo_epi_item* items, int n, const svo_epi_params* prm, svo_epi_result* results)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     if (n < 0 || !prm || (n > 0 && (!items || !results))) SVO_FAIL(SVO_ERR_INVALID, "svo_epipolar_match: null argument");
     if (n > ctx->cfg.max_fa_items) SVO_FAIL(SVO_ERR_CAPACITY, "svo_epipolar_match: more seeds than max_fa_items");
     if (prm->patch_size < 1 || prm->patch_size > 8 || !(prm->patch_size & 1) || prm->mean_mode < SVO_MEAN_EIGEN_U8 ||
@@ -799,6 +821,7 @@ svo_status svo_klt_track(svo_ctx* ctx, int ref_slot, int cur_slot, const float* 
                          const svo_klt_params* prm, uint8_t* status, float* err)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     if (n < 0 || !prm || (n > 0 && (!prev_pts || !next_pts || !status))) SVO_FAIL(SVO_ERR_INVALID, "svo_klt_track: null argument");
     if (bad_slot(ctx, ref_slot) || bad_slot(ctx, cur_slot)) SVO_FAIL(SVO_ERR_INVALID, "svo_klt_track: frame slot out of range");
     if (prm->win < 3 || prm->win > 21 || prm->max_level < 0) SVO_FAIL(SVO_ERR_INVALID, "svo_klt_track: win must be 3..21, max_level >= 0");

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -35,7 +36,13 @@ struct FrontendGraph {
     cudaGraphExec_t exec;
 };
 
+// every entry point that takes a context holds its lock for the duration of the call: calls from several threads (the
+// reference's depth-filter thread next to the tracker) are serialised, never interleaved.  Recursive: the one-call forms
+// (svo_sparse_align, svo_feature_align) are built from the phase-split entry points.
+#define SVO_LOCK(ctx) std::lock_guard<std::recursive_mutex> svo_lock_guard_((ctx)->mu)
+
 struct svo_ctx {
+    std::recursive_mutex mu;
     svo_config cfg;
     cudaStream_t stream;
     bool own_stream;

@@ -190,6 +190,7 @@ svo_status svo_frontend_run(svo_ctx* ctx, const svo_frontend_params* prm, const 
                             svo_feature_px* selected, int max_selected, svo_fa_result* refined)
 {
     if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);
     if (!prm || !img || !job || !result || n_feats < 0 || (n_feats > 0 && !feats) || max_selected < 0 || (max_selected > 0 && !selected))
         SVO_FAIL(SVO_ERR_INVALID, "svo_frontend_run: null argument");
     const LevelGeom& g = ctx->arena.geom[0];

@@ -833,3 +833,44 @@ def test_full_size_batch_properties(pkg, orc, synth):
                                       patch_size=5, mode=orc.GN, max_iter=30)
         assert synth.rotation_angle(res[i]["T_cur"], T) < ROT_TOL
         assert np.abs(res[i]["T_cur"][4:] - np.asarray(T)[4:]).max() < TRANS_TOL
+
+
+def test_two_threads_share_a_context(pkg, synth, pair_cache):
+    """The reference's depth-filter thread works on the frames the tracker thread aligns on: calls on one context from two
+    threads are serialised by the context's lock, and every result equals the one of the same call made alone."""
+    import threading
+    pair = pair_cache(8, 400, motion_scale=3.0)
+    rng = np.random.default_rng(23)
+    items, _ = _epi_items(pkg, synth, pair, rng, 500)
+    pts = pair["feats"]["px"][: pair["n_ref"]].astype(np.float32)
+    with _ctx(pkg, pair) as ctx:
+        ctx.upload(0, np.stack([pair["ref"], pair["cur"]]))
+        job = _job(pkg, pair)
+        want_align, _ = ctx.sparse_align(job, pair["feats"], mode=pkg.capi.GN, max_iter=30)
+        want_epi = ctx.epipolar_match(items)
+        want_klt = ctx.klt_track(0, 1, pts, pts)
+        errors = []
+
+        def tracker():
+            try:
+                for _ in range(40):
+                    res, _ = ctx.sparse_align(job, pair["feats"], mode=pkg.capi.GN, max_iter=30)
+                    assert res.tobytes() == want_align.tobytes()
+                    nxt, st, _ = ctx.klt_track(0, 1, pts, pts)
+                    assert np.array_equal(nxt, want_klt[0]) and np.array_equal(st, want_klt[1])
+            except Exception as e:  # noqa: BLE001 -- reported by the main thread
+                errors.append(e)
+
+        def depth_filter():
+            try:
+                for _ in range(120):
+                    assert ctx.epipolar_match(items).tobytes() == want_epi.tobytes()
+            except Exception as e:  # noqa: BLE001
+                errors.append(e)
+
+        ts = [threading.Thread(target=tracker), threading.Thread(target=depth_filter)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        assert not errors, errors
