@@ -95,6 +95,12 @@ __device__ __forceinline__ void ssc_sync(int C)
         asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// The cell arrays carry a ring of two empty cells (key 0) around the grid: the 5x5 neighbourhood of every real cell is
+// inside the array and the rounds need no bounds test.  Pitch and padded index of cell (r, cc):
+__device__ __forceinline__ int ssc_pitch(int ncc) { return ncc + 5; }
+__device__ __forceinline__ int ssc_pidx(int r, int cc, int ncc) { return (r + 2) * (ncc + 5) + cc + 2; }
+__device__ __forceinline__ long long ssc_padded_cells(int ncr, int ncc) { return (long long)(ncr + 5) * (ncc + 5); }
+
 // One width of the binary search: clear, per-cell champions, rounds of the lexicographically-first maximal independent
 // set, number of keepers.  SM: the cell arrays are the CTA's shared memory (the compiler sees the address space).
 template <bool SM>
@@ -153,13 +159,30 @@ __device__ __forceinline__ void ssc_champions(const SscArgs& a, uint32_t* __rest
                 }
             }
             const uint32_t kv = bestM ? (bestM << 24) | (0xFFFFFFu - bestPos) : 0u;
+            const int pi      = ssc_pidx(r, cc, ncc);
             if (SM && C > 1) {
-                ssc_st_cluster_u32(keyA + 4u * (uint32_t)i, kv);
-                ssc_st_cluster_u8(stateA + (uint32_t)i, 0u);
+                ssc_st_cluster_u32(keyA + 4u * (uint32_t)pi, kv);
+                ssc_st_cluster_u8(stateA + (uint32_t)pi, 0u);
             } else {
-                key[i]   = kv;
-                state[i] = 0;
+                key[pi]   = kv;
+                state[pi] = 0;
             }
+        }
+    }
+    if (crank == 0) {  // the ring: two rows above and below, two columns left and right of every row
+        const int P = ssc_pitch(ncc), R = ncr + 5;
+        for (int t = tid; t < 4 * P + 4 * (R - 4); t += SSC_NT) {
+            int pi;
+            if (t < 2 * P)
+                pi = t;
+            else if (t < 4 * P)
+                pi = (R - 2) * P + (t - 2 * P);
+            else {
+                const int q = t - 4 * P, row = 2 + (q >> 2), k = q & 3;
+                pi = row * P + (k < 2 ? k : P - 4 + k);
+            }
+            key[pi]   = 0;
+            state[pi] = 2;
         }
     }
 }
@@ -169,31 +192,29 @@ template <bool SM>
 __device__ __forceinline__ int ssc_rounds(uint32_t* __restrict__ key, uint8_t* state, int width, int ncc, int ncr, int* s_kept)
 {
     const int tid   = threadIdx.x;
-    const double c  = width / 2.0;
     const int cells = (ncr + 1) * (ncc + 1);
-    const int reach = (int)(width / c);  // 2
+    const int P = ssc_pitch(ncc);
     while (true) {
         int pending = 0;
         for (int i = tid; i < cells; i += SSC_NT) {
-            if ((SM ? state[i] : __ldcg(state + i)) != 0) continue;
-            const uint32_t mine = key[i];
+            const int row = i / (ncc + 1), col = i - row * (ncc + 1);
+            const int pi = ssc_pidx(row, col, ncc);
+            if ((SM ? state[pi] : __ldcg(state + pi)) != 0) continue;
+            const uint32_t mine = key[pi];
             if (mine == 0) {
-                state[i] = 2;
+                state[pi] = 2;
                 continue;
             }
-            const int row = i / (ncc + 1), col = i - row * (ncc + 1);
-            // the whole 5 x 5 neighbourhood is loaded before any of it is looked at (reach = width / c = 2 always):
-            // independent loads instead of 25 dependent load -> branch steps
+            // the whole 5 x 5 neighbourhood (reach = width / c = 2 exactly) is loaded before any of it is looked at:
+            // independent loads at constant offsets instead of 25 dependent load -> branch steps
             uint32_t nk[25], ns[25];
 #pragma unroll
             for (int dr = -2; dr <= 2; dr++)
 #pragma unroll
                 for (int dc = -2; dc <= 2; dc++) {
-                    const int r = row + dr, cc = col + dc, q = (dr + 2) * 5 + dc + 2;
-                    const bool in = r >= 0 && r <= ncr && cc >= 0 && cc <= ncc && reach == 2;
-                    const int j   = in ? r * (ncc + 1) + cc : i;  // outside the grid: the cell itself (never larger than itself)
-                    nk[q]         = key[j];
-                    ns[q]         = SM ? *(volatile uint8_t*)(state + j) : __ldcg(state + j);
+                    const int q = (dr + 2) * 5 + dc + 2, j = pi + dr * P + dc;
+                    nk[q]       = key[j];
+                    ns[q]       = SM ? *(volatile uint8_t*)(state + j) : __ldcg(state + j);
                 }
             bool refused = false, blocked = false;
 #pragma unroll
@@ -202,24 +223,10 @@ __device__ __forceinline__ int ssc_rounds(uint32_t* __restrict__ key, uint8_t* s
                 refused |= higher && ns[q] == 1;
                 blocked |= higher && ns[q] == 0;
             }
-            if (reach != 2) {  // cannot happen for c = width / 2.0; kept as the general (slow) form
-                refused = blocked = false;
-                const int r0 = max(row - reach, 0), r1 = min(row + reach, ncr);
-                const int c0 = max(col - reach, 0), c1 = min(col + reach, ncc);
-                for (int r = r0; r <= r1; r++)
-                    for (int cc = c0; cc <= c1; cc++) {
-                        const int j = r * (ncc + 1) + cc;
-                        if (key[j] > mine) {
-                            const uint32_t st = SM ? *(volatile uint8_t*)(state + j) : __ldcg(state + j);
-                            refused |= st == 1;
-                            blocked |= st == 0;
-                        }
-                    }
-            }
             if (refused)
-                state[i] = 2;
+                state[pi] = 2;
             else if (!blocked)
-                state[i] = 1;
+                state[pi] = 1;
             else
                 pending++;
         }
@@ -230,7 +237,10 @@ __device__ __forceinline__ int ssc_rounds(uint32_t* __restrict__ key, uint8_t* s
     __syncthreads();
     {
         int k = 0;
-        for (int i = tid; i < cells; i += SSC_NT) k += (SM ? state[i] : __ldcg(state + i)) == 1;
+        for (int i = tid; i < cells; i += SSC_NT) {
+            const int row = i / (ncc + 1), pi = ssc_pidx(row, i - row * (ncc + 1), ncc);
+            k += (SM ? state[pi] : __ldcg(state + pi)) == 1;
+        }
         k = __reduce_add_sync(0xffffffffu, k);
         if ((tid & 31) == 0 && k) atomicAdd(s_kept, k);
     }
@@ -315,7 +325,7 @@ __global__ void __launch_bounds__(SSC_NT) k_select_ssc(const SscArgs a)
         const double c  = width / 2.0;
         ncc             = (int)(w / c);
         ncr             = (int)(h / c);
-        const long long cells = (long long)(ncr + 1) * (ncc + 1);
+        const long long cells = ssc_padded_cells(ncr, ncc);
         if (cells > a.cellCap) {
             if (tid == 0) s_err = 1, s_done = 1, s_iters--;
             __syncthreads();
@@ -358,12 +368,14 @@ __global__ void __launch_bounds__(SSC_NT) k_select_ssc(const SscArgs a)
     for (int i = tid; i < SSC_CAP; i += SSC_NT) list[i] = 0;
     __syncthreads();
     if (s_iters > 0 && !s_err) {
-        const long long cells = (long long)(ncr + 1) * (ncc + 1);
-        for (long long i = tid; i < cells; i += SSC_NT)
-            if ((inSmem ? sState[i] : __ldcg(a.cellState + i)) == 1) {
+        const int cells = (ncr + 1) * (ncc + 1);
+        for (int i = tid; i < cells; i += SSC_NT) {
+            const int row = i / (ncc + 1), pi = ssc_pidx(row, i - row * (ncc + 1), ncc);
+            if ((inSmem ? sState[pi] : __ldcg(a.cellState + pi)) == 1) {
                 const int pos = atomicAdd(&s_nsel, 1);
-                if (pos < SSC_CAP) list[pos] = inSmem ? sKey[i] : a.cellKey[i];
+                if (pos < SSC_CAP) list[pos] = inSmem ? sKey[pi] : a.cellKey[pi];
             }
+        }
     }
     __syncthreads();
     if (s_nsel > SSC_CAP) {
@@ -464,7 +476,7 @@ svo_status launch_select_ssc(svo_ctx* ctx, int slot, uint32_t thr, int numCandid
 {
     const LevelGeom& g = ctx->arena.geom[0];
     if ((int64_t)g.w * g.h > (1 << 24)) SVO_FAIL(SVO_ERR_UNSUPPORTED, "svo_select_ssc: images above 2^24 pixels are not supported");
-    const long long cap = (long long)(2 * g.h + 2) * (2 * g.w + 2);  // cells at the smallest width (1 pixel: side 0.5)
+    const long long cap = (long long)(2 * g.h + 6) * (2 * g.w + 6);  // cells at the smallest width (1 pixel: side 0.5) + the ring
     if (!ctx->d_ssc_key) {
         SVO_CUDA(cudaMalloc(&ctx->d_ssc_key, sizeof(uint32_t) * cap));
         SVO_CUDA(cudaMalloc(&ctx->d_ssc_state, sizeof(uint32_t) * cap));
