@@ -49,8 +49,7 @@ void release(svo_ctx* ctx)
     if (ctx->ev_jobs_h2d) cudaEventDestroy(ctx->ev_jobs_h2d);
     cudaFree(ctx->d_ssc_key);
     cudaFree(ctx->d_ssc_state);
-    cudaFree(ctx->d_ssc_info);
-    cudaFreeHost(ctx->h_ssc_info);
+    cudaFreeHost(ctx->h_ssc);  // d_ssc_out, d_ssc_count, d_ssc_info are views of it
     cudaFree(ctx->d_cell_best);
     cudaFree(ctx->d_occupancy);
     cudaFree(ctx->d_sel_out);
@@ -509,21 +508,19 @@ svo_status svo_select_ssc(svo_ctx* ctx, int slot, uint32_t thr, int num_candidat
         std::memcpy(ctx->h_occupancy, occupancy, (size_t)rows * cols);
         SVO_CUDA(cudaMemcpyAsync(ctx->d_occupancy, ctx->h_occupancy, (size_t)rows * cols, cudaMemcpyHostToDevice, ctx->stream));
     }
-    const int cap = std::min(ctx->sel_cap_cells, 4096);  // d_sel_out holds sel_cap_cells records
+    const int cap = 4096;  // records in the mapped result block (SSC_CAP of select_ssc.cu)
     const svo_status st = launch_select_ssc(ctx, slot, thr, num_candidates, cell, rows, cols, occupancy != nullptr, use_bucketing != 0, cap);
     if (st != SVO_OK) return st;
-    SVO_CUDA(cudaMemcpyAsync(ctx->h_sel_count, ctx->d_sel_count, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    SVO_CUDA(cudaMemcpyAsync(ctx->h_ssc_info, ctx->d_ssc_info, sizeof(int32_t) * 5, cudaMemcpyDeviceToHost, ctx->stream));
-    SVO_CUDA(cudaMemcpyAsync(ctx->h_sel_out, ctx->d_sel_out, sizeof(svo_feature_px) * cap, cudaMemcpyDeviceToHost, ctx->stream));
     SVO_CUDA(cudaStreamSynchronize(ctx->stream));
-    const int32_t* hinfo = ctx->h_ssc_info;
+    // the kernel wrote records | count | info to the mapped block
+    const int32_t* hinfo = reinterpret_cast<const int32_t*>(ctx->h_ssc + sizeof(svo_feature_px) * 4096) + 4;
     if (info)
         for (int i = 0; i < 4; i++) info[i] = hinfo[i];
     if (hinfo[4] == 1) SVO_FAIL(SVO_ERR_CAPACITY, "svo_select_ssc: more SSC cells than the scratch holds");
     if (hinfo[4] == 2) SVO_FAIL(SVO_ERR_CAPACITY, "svo_select_ssc: more than 4,096 points survive the suppression (num_candidates too large)");
-    const int n = *ctx->h_sel_count;
+    const int n = *reinterpret_cast<const int32_t*>(ctx->h_ssc + sizeof(svo_feature_px) * 4096);
     *n_out      = n;
-    std::memcpy(out, ctx->h_sel_out, sizeof(svo_feature_px) * std::min(n, std::min(max_out, cap)));
+    std::memcpy(out, ctx->h_ssc, sizeof(svo_feature_px) * std::min(n, std::min(max_out, cap)));
     return SVO_OK;
 }
 

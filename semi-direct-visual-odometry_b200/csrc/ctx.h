@@ -88,8 +88,10 @@ struct svo_ctx {
     int sel_cap_cells;
     uint32_t* d_ssc_key;         // svo_select_ssc: champion key / state per SSC cell (allocated on first use)
     uint32_t* d_ssc_state;
+    unsigned char* h_ssc;        // mapped page-locked block the kernel writes its results to: records | count | info
+    svo_feature_px* d_ssc_out;   // device views of its parts
+    int32_t* d_ssc_count;
     int32_t* d_ssc_info;
-    int32_t* h_ssc_info;         // pinned
     int ssc_cluster;             // CTAs per cluster of k_select_ssc (decided on first use)
     bool sel_use_occupancy;
 

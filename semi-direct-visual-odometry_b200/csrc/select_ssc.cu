@@ -480,8 +480,13 @@ svo_status launch_select_ssc(svo_ctx* ctx, int slot, uint32_t thr, int numCandid
     if (!ctx->d_ssc_key) {
         SVO_CUDA(cudaMalloc(&ctx->d_ssc_key, sizeof(uint32_t) * cap));
         SVO_CUDA(cudaMalloc(&ctx->d_ssc_state, sizeof(uint32_t) * cap));
-        SVO_CUDA(cudaMalloc(&ctx->d_ssc_info, sizeof(int32_t) * 8));
-        SVO_CUDA(cudaHostAlloc(&ctx->h_ssc_info, sizeof(int32_t) * 8, cudaHostAllocDefault));
+        // results travel zero-copy: the kernel writes records, count and info straight to mapped page-locked memory
+        SVO_CUDA(cudaHostAlloc(&ctx->h_ssc, sizeof(svo_feature_px) * SSC_CAP + 64, cudaHostAllocMapped));
+        unsigned char* d = nullptr;
+        SVO_CUDA(cudaHostGetDevicePointer(&d, ctx->h_ssc, 0));
+        ctx->d_ssc_out   = reinterpret_cast<svo_feature_px*>(d);
+        ctx->d_ssc_count = reinterpret_cast<int32_t*>(d + sizeof(svo_feature_px) * SSC_CAP);
+        ctx->d_ssc_info  = ctx->d_ssc_count + 4;
         SVO_CUDA(cudaFuncSetAttribute(k_select_ssc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SSC_DYN_SMEM));
         // a cluster of 8 CTAs scans the pixels (SVO_SSC_CLUSTER=1|2|4|8 overrides); CTA 0 owns the cell arrays
         int C = 8;
@@ -512,7 +517,7 @@ svo_status launch_select_ssc(svo_ctx* ctx, int slot, uint32_t thr, int numCandid
     a.smemCells = SSC_SMEM_CELLS;
     if (const char* e = getenv("SVO_SSC_SMEM_CELLS")) a.smemCells = std::min(std::max(atoi(e), 0), SSC_SMEM_CELLS);  // tests: global-array path
     a.bucket = ctx->d_cell_best;
-    a.out = ctx->d_sel_out, a.maxOut = maxOut, a.count = ctx->d_sel_count, a.info = ctx->d_ssc_info;
+    a.out = ctx->d_ssc_out, a.maxOut = std::min(maxOut, SSC_CAP), a.count = ctx->d_ssc_count, a.info = ctx->d_ssc_info;
     const int C            = ctx->ssc_cluster;
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim            = dim3(C, 1, 1);
