@@ -56,6 +56,7 @@ void release(svo_ctx* ctx)
     cudaFree(ctx->d_sel_count);
     cudaFreeHost(ctx->h_sel_out);
     cudaFreeHost(ctx->h_sel_count);
+    cudaFreeHost(ctx->h_grid);
     cudaFreeHost(ctx->h_occupancy);
     cudaFreeHost(ctx->h_jobs);
     cudaFreeHost(ctx->h_feats);
@@ -477,15 +478,17 @@ svo_status svo_select_grid(svo_ctx* ctx, int slot, int cell, uint32_t thr, const
                                  ctx->stream));
     }
     ctx->sel_use_occupancy = occupancy != nullptr;
-    const svo_status st    = launch_grid_select(ctx, slot, cell, thr, rows, cols);
+    if (!ctx->h_grid)  // zero-copy results: the compaction kernel writes count | records to mapped page-locked memory
+        SVO_CUDA(cudaHostAlloc(&ctx->h_grid, 16 + sizeof(svo_feature_px) * ctx->sel_cap_cells, cudaHostAllocMapped));
+    unsigned char* dGrid = nullptr;
+    SVO_CUDA(cudaHostGetDevicePointer(&dGrid, ctx->h_grid, 0));
+    const svo_status st = launch_grid_select(ctx, slot, cell, thr, rows, cols, reinterpret_cast<svo_feature_px*>(dGrid + 16),
+                                             reinterpret_cast<int32_t*>(dGrid));
     if (st != SVO_OK) return st;
-    SVO_CUDA(cudaMemcpyAsync(ctx->h_sel_count, ctx->d_sel_count, sizeof(int32_t), cudaMemcpyDeviceToHost, ctx->stream));
-    SVO_CUDA(cudaMemcpyAsync(ctx->h_sel_out, ctx->d_sel_out, sizeof(svo_feature_px) * rows * cols, cudaMemcpyDeviceToHost,
-                             ctx->stream));
     SVO_CUDA(cudaStreamSynchronize(ctx->stream));
-    const int n = *ctx->h_sel_count;
+    const int n = *reinterpret_cast<const int32_t*>(ctx->h_grid);
     *n_out      = n;
-    std::memcpy(out, ctx->h_sel_out, sizeof(svo_feature_px) * std::min(n, max_out));
+    std::memcpy(out, ctx->h_grid + 16, sizeof(svo_feature_px) * std::min(n, max_out));
     return SVO_OK;
 }
 

@@ -84,6 +84,7 @@ struct svo_ctx {
     int32_t* d_sel_count;
     svo_feature_px* h_sel_out;   // pinned
     int32_t* h_sel_count;        // pinned
+    unsigned char* h_grid;       // svo_select_grid: mapped page-locked block the compaction writes to (count | records)
     uint8_t* h_occupancy;        // pinned
     int sel_cap_cells;
     uint32_t* d_ssc_key;         // svo_select_ssc: champion key / state per SSC cell (allocated on first use)
@@ -188,7 +189,8 @@ inline ArenaView make_view(const PyramidArena& a)
 // kernel launchers (defined in the .cu files)
 svo_status launch_pyramid_build(svo_ctx* ctx, int first_slot, int n);
 svo_status launch_repack(svo_ctx* ctx, const uint8_t* dsrc, long long src_pitch, long long src_frame_stride, int first_slot, int n);
-svo_status launch_grid_select(svo_ctx* ctx, int slot, int cell, uint32_t thr, int rows, int cols);
+svo_status launch_grid_select(svo_ctx* ctx, int slot, int cell, uint32_t thr, int rows, int cols, svo_feature_px* out = nullptr,
+                              int32_t* count = nullptr);
 svo_status launch_select_ssc(svo_ctx* ctx, int slot, uint32_t thr, int numCandidates, int cell, int rows, int cols, bool useOcc,
                              bool useBucketing, int maxOut);
 svo_status launch_sparse_align(svo_ctx* ctx);

@@ -86,15 +86,16 @@ __global__ void __launch_bounds__(1024) k_cell_compact(const uint32_t* __restric
 
 }  // namespace
 
-svo_status launch_grid_select(svo_ctx* ctx, int slot, int cell, uint32_t thr, int rows, int cols)
+svo_status launch_grid_select(svo_ctx* ctx, int slot, int cell, uint32_t thr, int rows, int cols, svo_feature_px* out, int32_t* count)
 {
+    if (!out) out = ctx->d_sel_out, count = ctx->d_sel_count;  // default: device buffers (front-end graph); else mapped host memory
     const LevelGeom& g  = ctx->arena.geom[0];
     const uint8_t* grad = ctx->arena.grad[0] + (int64_t)slot * g.plane_stride;
     const int n         = rows * cols;
     const int blocks    = (n * 32 + 127) / 128;
     k_cell_argmax<<<blocks, 128, 0, ctx->stream>>>(grad, g.w, g.h, g.pitch, cell, rows, cols, ctx->d_cell_best);
     k_cell_compact<<<1, 1024, 0, ctx->stream>>>(ctx->d_cell_best, ctx->sel_use_occupancy ? ctx->d_occupancy : nullptr, g.w, g.h, cell, rows, cols, thr,
-                                                ctx->d_sel_out, ctx->d_sel_count);
+                                                out, count);
     ctx->launches += 2;
     SVO_CUDA(cudaGetLastError());
     return SVO_OK;
