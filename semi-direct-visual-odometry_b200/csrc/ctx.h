@@ -122,8 +122,9 @@ struct svo_ctx {
     FrontendGraph fe_graphs[8];
     int fe_count;
     int fe_kernel_nodes;           // kernel nodes of the last instantiated front-end graph
-    svo_align_result* h_fe_align;  // pinned
-    svo_fa_result* h_fe_fa;        // pinned, max_features records
+    svo_align_result* h_fe_align;
+    svo_fa_result* h_fe_fa;
+    unsigned char* h_fe_sel;       // count (16 bytes) | selected features; all three are MAPPED: the graph's kernels write them
 
     // Map::reprojectMap batch (svo_reproject_map), capacity max_fa_items candidates / sel_cap_cells cells
     unsigned char* h_rp;  // mapped page-locked block: candidates | cell order | finished matches | projected flags | count
@@ -194,7 +195,7 @@ svo_status launch_grid_select(svo_ctx* ctx, int slot, int cell, uint32_t thr, in
 svo_status launch_select_ssc(svo_ctx* ctx, int slot, uint32_t thr, int numCandidates, int cell, int rows, int cols, bool useOcc,
                              bool useBucketing, int maxOut);
 svo_status launch_sparse_align(svo_ctx* ctx);
-svo_status launch_feature_align(svo_ctx* ctx);
+svo_status launch_feature_align(svo_ctx* ctx, svo_fa_result* results = nullptr);
 svo_status launch_reproject_map(svo_ctx* ctx, int curSlot, const double T[7], int n, int cell, int nCells, int gridCols, int maxItems,
                                 const svo_fa_params& fa);
 svo_status launch_epipolar_match(svo_ctx* ctx, int n, const svo_epi_params& prm);

@@ -336,13 +336,13 @@ __global__ void __launch_bounds__(128) k_feature_align(const FaArgs a)
 
 }  // namespace
 
-svo_status launch_feature_align(svo_ctx* ctx)
+svo_status launch_feature_align(svo_ctx* ctx, svo_fa_result* results)
 {
     if (ctx->staged_fa == 0) return SVO_OK;
     FaArgs args;
     args.view    = make_view(ctx->arena);
     args.items   = ctx->d_fa_items;
-    args.results = ctx->d_fa_results;
+    args.results = results ? results : ctx->d_fa_results;  // override: mapped host memory (front-end graph)
     args.n       = ctx->staged_fa;
     args.prm     = ctx->staged_fa_params;
     const int blocks = (ctx->staged_fa * 32 + 127) / 128;

@@ -7,7 +7,8 @@
 //     -> k_reproject_items: world2image of every tracked point with the ALIGNED pose (Frame::world2image,
 //        src/frame.cpp:84-92) and the in-frame test of Map::addCandidateToFrame (src/map.cpp:601-602)
 //     -> per-feature 2D alignment of those candidates             FeatureAlignment::align (src/map.cpp:538,608)
-//     -> D2H of the pose, the new features and the refined pixel positions.
+//     -> the pose, the new features and the refined pixel positions are written by those kernels straight to mapped
+//        page-locked host memory (no device->host copy node in the chain; all host->device copies come first).
 // The graph is captured once per configuration (frame slots + parameters) and cached; a call copies the inputs into
 // the context's pinned mirrors, launches the graph and reads the pinned outputs.  No host round trip between stages.
 #include <cstring>
@@ -21,6 +22,7 @@ struct ReprojArgs {
     const svo_align_job* job;
     const svo_align_feature* feats;
     const svo_align_result* aligned;
+    svo_align_result* alignedOut;  // mapped host copy of the alignment's result (thread 0 writes it)
     svo_fa_item* items;
     int capacity;
     int w, h;
@@ -32,6 +34,7 @@ struct ReprojArgs {
 __global__ void __launch_bounds__(128) k_reproject_items(const ReprojArgs a)
 {
     const int f = blockIdx.x * blockDim.x + threadIdx.x;
+    if (f == 0 && a.alignedOut) *a.alignedOut = *a.aligned;
     if (f >= a.capacity) return;
     const svo_align_job J = *a.job;
     svo_fa_item it;
@@ -77,43 +80,51 @@ svo_status frontend_enqueue(svo_ctx* ctx, const svo_frontend_params& p)
     const int rows = g.h / p.cell + 1, cols = g.w / p.cell + 1;
     cudaStream_t st = ctx->stream;
     svo_status rc;
-    // new frame
+    // every input first: one queue of host->device copies, none of them between two kernels of the chain
     SVO_CUDA(cudaMemcpyAsync(ctx->d_img_stage[0], ctx->h_img_stage[0], (size_t)frame_sz, cudaMemcpyHostToDevice, st));
+    SVO_CUDA(cudaMemcpyAsync(ctx->d_occupancy, ctx->h_occupancy, (size_t)rows * cols, cudaMemcpyHostToDevice, st));
+    SVO_CUDA(cudaMemcpyAsync(ctx->d_jobs, ctx->h_jobs, sizeof(svo_align_job), cudaMemcpyHostToDevice, st));
+    SVO_CUDA(cudaMemcpyAsync(ctx->d_feats, ctx->h_feats, sizeof(svo_align_feature) * p.max_features, cudaMemcpyHostToDevice, st));
+    // the results travel zero-copy: the kernels write them to mapped page-locked memory, so no device->host copy sits
+    // between (or behind) the kernels either
+    unsigned char* dSel       = nullptr;
+    svo_align_result* dAlign  = nullptr;
+    svo_fa_result* dFa        = nullptr;
+    SVO_CUDA(cudaHostGetDevicePointer(&dSel, ctx->h_fe_sel, 0));
+    SVO_CUDA(cudaHostGetDevicePointer(&dAlign, ctx->h_fe_align, 0));
+    SVO_CUDA(cudaHostGetDevicePointer(&dFa, ctx->h_fe_fa, 0));
+    // new frame
     if ((rc = launch_repack(ctx, ctx->d_img_stage[0], g.w, frame_sz, p.cur_slot, 1)) != SVO_OK) return rc;
     if ((rc = launch_pyramid_build(ctx, p.cur_slot, 1)) != SVO_OK) return rc;
     // new features on it
-    SVO_CUDA(cudaMemcpyAsync(ctx->d_occupancy, ctx->h_occupancy, (size_t)rows * cols, cudaMemcpyHostToDevice, st));
     ctx->sel_use_occupancy = true;
-    if ((rc = launch_grid_select(ctx, p.cur_slot, p.cell, p.thr, rows, cols)) != SVO_OK) return rc;
-    SVO_CUDA(cudaMemcpyAsync(ctx->h_sel_count, ctx->d_sel_count, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    SVO_CUDA(cudaMemcpyAsync(ctx->h_sel_out, ctx->d_sel_out, sizeof(svo_feature_px) * rows * cols, cudaMemcpyDeviceToHost, st));
+    if ((rc = launch_grid_select(ctx, p.cur_slot, p.cell, p.thr, rows, cols, reinterpret_cast<svo_feature_px*>(dSel + 16),
+                                 reinterpret_cast<int32_t*>(dSel))) != SVO_OK)
+        return rc;
     // pose of the new frame
-    SVO_CUDA(cudaMemcpyAsync(ctx->d_jobs, ctx->h_jobs, sizeof(svo_align_job), cudaMemcpyHostToDevice, st));
-    SVO_CUDA(cudaMemcpyAsync(ctx->d_feats, ctx->h_feats, sizeof(svo_align_feature) * p.max_features, cudaMemcpyHostToDevice, st));
     ctx->staged_jobs       = 1;
     ctx->staged_feats      = p.max_features;
     ctx->staged_levels     = p.align.max_level - p.align.min_level + 1;
     ctx->staged_want_stats = 0;
     ctx->staged_params     = p.align;
     if ((rc = launch_sparse_align_v3(ctx, p.max_features)) != SVO_OK) return rc;
-    SVO_CUDA(cudaMemcpyAsync(ctx->h_fe_align, ctx->d_results, sizeof(svo_align_result), cudaMemcpyDeviceToHost, st));
     // candidates with the aligned pose, refined per feature
     ReprojArgs ra;
-    ra.job      = ctx->d_jobs;
-    ra.feats    = ctx->d_feats;
-    ra.aligned  = ctx->d_results;
-    ra.items    = ctx->d_fa_items;
-    ra.capacity = p.max_features;
-    ra.w        = g.w;
-    ra.h        = g.h;
-    ra.border   = 3;
+    ra.job        = ctx->d_jobs;
+    ra.feats      = ctx->d_feats;
+    ra.aligned    = ctx->d_results;
+    ra.alignedOut = dAlign;
+    ra.items      = ctx->d_fa_items;
+    ra.capacity   = p.max_features;
+    ra.w          = g.w;
+    ra.h          = g.h;
+    ra.border     = 3;
     for (int i = 0; i < 4; i++) ra.K[i] = ctx->cfg.K[i];
     k_reproject_items<<<(p.max_features + 127) / 128, 128, 0, st>>>(ra);
     ctx->launches++;
     ctx->staged_fa        = p.max_features;
     ctx->staged_fa_params = p.fa;
-    if ((rc = launch_feature_align(ctx)) != SVO_OK) return rc;
-    SVO_CUDA(cudaMemcpyAsync(ctx->h_fe_fa, ctx->d_fa_results, sizeof(svo_fa_result) * p.max_features, cudaMemcpyDeviceToHost, st));
+    if ((rc = launch_feature_align(ctx, dFa)) != SVO_OK) return rc;
     SVO_CUDA(cudaGetLastError());
     return SVO_OK;
 }
@@ -126,8 +137,9 @@ svo_status frontend_graph(svo_ctx* ctx, const svo_frontend_params& p, cudaGraphE
             return SVO_OK;
         }
     if (!ctx->h_fe_align) {
-        SVO_CUDA(cudaHostAlloc(&ctx->h_fe_align, sizeof(svo_align_result), cudaHostAllocDefault));
-        SVO_CUDA(cudaHostAlloc(&ctx->h_fe_fa, sizeof(svo_fa_result) * std::max(1, ctx->cfg.max_fa_items), cudaHostAllocDefault));
+        SVO_CUDA(cudaHostAlloc(&ctx->h_fe_align, sizeof(svo_align_result), cudaHostAllocMapped));
+        SVO_CUDA(cudaHostAlloc(&ctx->h_fe_fa, sizeof(svo_fa_result) * std::max(1, ctx->cfg.max_fa_items), cudaHostAllocMapped));
+        SVO_CUDA(cudaHostAlloc(&ctx->h_fe_sel, 16 + sizeof(svo_feature_px) * ctx->sel_cap_cells, cudaHostAllocMapped));
     }
     // eager pass: scratch allocation and function attributes happen outside the capture
     svo_status rc = frontend_enqueue(ctx, p);
@@ -177,8 +189,10 @@ void frontend_release(svo_ctx* ctx)
     ctx->fe_count = 0;
     if (ctx->h_fe_align) cudaFreeHost(ctx->h_fe_align);
     if (ctx->h_fe_fa) cudaFreeHost(ctx->h_fe_fa);
+    if (ctx->h_fe_sel) cudaFreeHost(ctx->h_fe_sel);
     ctx->h_fe_align = nullptr;
     ctx->h_fe_fa    = nullptr;
+    ctx->h_fe_sel   = nullptr;
 }
 
 extern "C" {
@@ -245,11 +259,11 @@ svo_status svo_frontend_run(svo_ctx* ctx, const svo_frontend_params* prm, const 
     SVO_CUDA(cudaStreamSynchronize(ctx->stream));
     // ---- outputs ----
     result->align      = *ctx->h_fe_align;
-    result->n_selected = *ctx->h_sel_count;
+    result->n_selected = *reinterpret_cast<const int32_t*>(ctx->h_fe_sel);
     int nfa = 0;
     for (int f = 0; f < n_feats; f++) nfa += ctx->h_fe_fa[f].status != SVO_ST_FAILED || ctx->h_fe_fa[f].iterations != 0;
     result->n_candidates = nfa;
-    if (selected) std::memcpy(selected, ctx->h_sel_out, sizeof(svo_feature_px) * std::min(result->n_selected, max_selected));
+    if (selected) std::memcpy(selected, ctx->h_fe_sel + 16, sizeof(svo_feature_px) * std::min(result->n_selected, max_selected));
     if (refined && n_feats) std::memcpy(refined, ctx->h_fe_fa, sizeof(svo_fa_result) * n_feats);
     return SVO_OK;
 }
