@@ -347,11 +347,14 @@ def run_b200(a, rank, world):
         pin2.free()
         ctx.close()
 
-    traffic = None  # DRAM bytes of the dominant kernel per launch, from the committed ncu --set full capture
+    traffic, issue = None, None  # DRAM bytes of the dominant kernel per launch, from the committed ncu --set full capture
     try:
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_k_align_cluster.json")))
         if a.features == tj["features"] and a.mode == "gn":
             traffic = tj["dram_bytes_per_pair"] * n
+            # what actually bounds the kernel (same capture): issue-slot utilisation and the stall reasons per issue
+            issue = {"issue_slots_busy_pct": tj.get("issue_slots_busy_pct"), "warp_instructions_per_pair": tj.get("warp_instructions_per_pair"),
+                     "stalls_per_issue": tj.get("top_stalls_per_issue")}
     except Exception:
         pass
     if rank == 0:
@@ -386,7 +389,7 @@ def run_b200(a, rank, world):
                          "frac": achieved / hbm_peak, "peak_source": peak_src, "traffic": traffic,
                          "traffic_source": "profiles/traffic_k_align_cluster.json: dram__bytes_read+write of one 148-pair launch, scaled per pair" if traffic else None,
                          "algorithmic_bytes_per_launch": alg_bytes, "sector_bytes_per_launch": sector_bytes,
-                         "kernel_ms": kern_ms,
+                         "kernel_ms": kern_ms, "issue": issue,
                          "note": "sparse gather + exact order statistics: bound by integer issue and block barriers, not by HBM (DESIGN.md 4, profiles/)"},
         }
         if world == 1 and not a.no_cpu_baseline:
