@@ -135,6 +135,7 @@ __global__ void __launch_bounds__(128) k_epipolar_match(const EpiArgs a)
     const bool eigenMean = a.prm.mean_mode == SVO_MEAN_EIGEN_U8;
     const uint32_t rsum  = __reduce_add_sync(0xffffffffu, r0 + r1);
     const double refMean = eigenMean ? (double)((rsum & 255u) / (uint32_t)(area & 255)) : (double)rsum / area;
+    const int refMeanI   = (int)((rsum & 255u) / (uint32_t)(area & 255));
 
     if (norm < 2.0) {  // :469-483
         const double cx = (locMax[0] + locMin[0]) / 2.0, cy = (locMax[1] + locMin[1]) / 2.0;
@@ -157,13 +158,24 @@ __global__ void __launch_bounds__(128) k_epipolar_match(const EpiArgs a)
             if (has0) c0 = __float2uint_rz(epi_bilinear_float(curI, pitch, lx + (A[0] * j0 + A[1] * i0), ly + (A[2] * j0 + A[3] * i0)));
             if (has1) c1 = __float2uint_rz(epi_bilinear_float(curI, pitch, lx + (A[0] * j1 + A[1] * i1), ly + (A[2] * j1 + A[3] * i1)));
         }
-        const uint32_t csum  = __reduce_add_sync(0xffffffffu, c0 + c1);
-        const double curMean = eigenMean ? (double)((csum & 255u) / (uint32_t)(area & 255)) : (double)csum / area;
-        double z = 0.0;
-        if (has0) z += fabs(((double)r0 - refMean) - ((double)c0 - curMean));
-        if (has1) z += fabs(((double)r1 - refMean) - ((double)c1 - curMean));
+        const uint32_t csum = __reduce_add_sync(0xffffffffu, c0 + c1);
+        double z;
+        if (eigenMean) {
+            // the reference's means are integers here ((sum mod 256) / area in uint8 arithmetic): every term of the score is
+            // an integer, the double sum is exact in any order -- one hardware reduction instead of a double butterfly
+            const int cm = (int)((csum & 255u) / (uint32_t)(area & 255));
+            int zi       = 0;
+            if (has0) zi += abs(((int)r0 - refMeanI) - ((int)c0 - cm));
+            if (has1) zi += abs(((int)r1 - refMeanI) - ((int)c1 - cm));
+            z = (double)__reduce_add_sync(0xffffffffu, zi);
+        } else {
+            const double curMean = (double)csum / area;
+            z                    = 0.0;
+            if (has0) z += fabs(((double)r0 - refMean) - ((double)c0 - curMean));
+            if (has1) z += fabs(((double)r1 - refMean) - ((double)c1 - curMean));
 #pragma unroll
-        for (int o = 16; o >= 1; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+            for (int o = 16; o >= 1; o >>= 1) z += __shfl_xor_sync(0xffffffffu, z, o);
+        }
         if (z < minScore) {
             minScore = z;
             bestX = lx, bestY = ly;
