@@ -77,7 +77,6 @@ void release(svo_ctx* ctx)
     cudaFreeHost(ctx->h_epi_items);
     cudaFreeHost(ctx->h_epi_results);
     cudaFree(ctx->d_epi_items);
-    cudaFree(ctx->d_epi_results);
     cudaFreeHost(ctx->h_fa_items);
     cudaFreeHost(ctx->h_fa_results);
     cudaFree(ctx->d_fa_items);
@@ -176,9 +175,10 @@ svo_status init(svo_ctx* ctx)
     SVO_CUDA(cudaMalloc(&ctx->d_fa_items, sizeof(svo_fa_item) * nf));
     SVO_CUDA(cudaMalloc(&ctx->d_fa_results, sizeof(svo_fa_result) * nf));
     SVO_CUDA(cudaHostAlloc(&ctx->h_epi_items, sizeof(svo_epi_item) * nf, cudaHostAllocDefault));
-    SVO_CUDA(cudaHostAlloc(&ctx->h_epi_results, sizeof(svo_epi_result) * nf, cudaHostAllocDefault));
+    // mapped: k_epipolar_match writes its one record per seed straight to the host (no device->host copy behind the kernel)
+    SVO_CUDA(cudaHostAlloc(&ctx->h_epi_results, sizeof(svo_epi_result) * nf, cudaHostAllocMapped));
     SVO_CUDA(cudaMalloc(&ctx->d_epi_items, sizeof(svo_epi_item) * nf));
-    SVO_CUDA(cudaMalloc(&ctx->d_epi_results, sizeof(svo_epi_result) * nf));
+    SVO_CUDA(cudaHostGetDevicePointer(&ctx->d_epi_results, ctx->h_epi_results, 0));  // a view, not an allocation
     SVO_CUDA(cudaStreamSynchronize(ctx->stream));
     return SVO_OK;
 }
@@ -808,7 +808,6 @@ svo_status svo_epipolar_match(svo_ctx* ctx, const svo_epi_item* items, int n, co
     if (st != SVO_OK) return st;
     SVO_CUDA(cudaMemcpyAsync(ctx->d_epi_items, ctx->h_epi_items, sizeof(svo_epi_item) * n, cudaMemcpyHostToDevice, ctx->stream));
     if ((st = launch_epipolar_match(ctx, n, *prm)) != SVO_OK) return st;
-    SVO_CUDA(cudaMemcpyAsync(ctx->h_epi_results, ctx->d_epi_results, sizeof(svo_epi_result) * n, cudaMemcpyDeviceToHost, ctx->stream));
     SVO_CUDA(cudaStreamSynchronize(ctx->stream));
     std::memcpy(results, ctx->h_epi_results, sizeof(svo_epi_result) * n);
     return SVO_OK;
