@@ -18,8 +18,12 @@
  *   - orc_se3_exp       against the closed form / scipy Rotation
  *   - orc_sparse_align  (reference mode, four levels) against a second, independent numpy restatement to 1e-9 per
  *                       level (tests/test_oracle_numerics.py::test_align_against_independent_numpy)
- *   - orc_select_ssc, orc_epipolar_match  against direct python / numpy restatements and the golden vectors they
- *                       produced (tests/golden/next_rows_golden.npz)
+ *   - orc_feature_align (reference mode) against a second, independent numpy restatement: RMSE to 1e-9, moved pixel to
+ *                       1e-7 (tests/test_oracle_numerics.py::test_feature_align_against_independent_numpy)
+ *   - orc_select_ssc, orc_epipolar_match, orc_reproject_map  against direct python / numpy restatements and the golden
+ *                       vectors they produced (tests/golden/next_rows_golden.npz)
+ *   - orc_klt_track     against the RUNNING cv2 4.13 binary (cv2.calcOpticalFlowPyrLK with the reference's arguments) and
+ *                       golden vectors that binary wrote (tests/test_oracle_klt.py, tests/golden/klt_golden.npz)
  * The alignment numerics (H, g, pose) are therefore "parity unpinned" against a
  * running reference binary; they are pinned to this line-by-line restatement and to the
  * independent restatements above.

@@ -609,3 +609,83 @@ def test_reproject_map_against_python(orc, pkg, pair_cache, cell, max_matches):
     assert np.array_equal(got[:, 2:5], want[:, 2:5], equal_nan=True)
     if max_matches == 25:
         assert len(got) == 26
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# FeatureAlignment::align in the reference's mode: a second, independent restatement in numpy (src/feature_alignment.cpp:25-62
+# align, :64-110 computeJacobian, :113-168 computeResiduals, :200-205 update; Optimizer::optimizeLM src/optimizer.cpp:161-370 with
+# its one damped step; tukeyWeighting :485-507).  float32 bilinear taps as algorithm::bilinearInterpolation (:885-894).
+def _np_bilin_f32(img, x, y):
+    x1, y1 = int(x), int(y)
+    a = np.float32((x1 + 1 - x) * float(img[y1, x1]) + (x - x1) * float(img[y1, x1 + 1]))
+    b = np.float32((x1 + 1 - x) * float(img[y1 + 1, x1]) + (x - x1) * float(img[y1 + 1, x1 + 1]))
+    return float(np.float32((y1 + 1 - y) * float(a) + (y - y1) * float(b)))
+
+
+def _np_feature_align_faithful(ref_grad, cur_grad, ref_px, px, P=7):
+    h, w = ref_grad.shape
+    half, area = P // 2, P * P
+    border = half + 2
+    inside = lambda p: p[0] >= border and p[1] >= border and p[0] < w - border and p[1] < h - border   # isInFrame(px, border)
+    J, T = np.zeros((area, 3)), np.zeros(area)
+    if inside(ref_px):                                                      # else J and the template stay zero (:74-77)
+        k = 0
+        for y in range(-half, half + 1):
+            for x in range(-half, half + 1):
+                r, c = ref_px[1] + y, ref_px[0] + x
+                T[k] = _np_bilin_f32(ref_grad, c, r)
+                dx = 0.5 * (_np_bilin_f32(ref_grad, c + 1, r) - _np_bilin_f32(ref_grad, c - 1, r))
+                dy = 0.5 * (_np_bilin_f32(ref_grad, c, r + 1) - _np_bilin_f32(ref_grad, c, r - 1))
+                J[k] = (dx, dy, 1.0)
+                k += 1
+    pose = np.array([px[0], px[1], 0.0])
+    if not inside(pose[:2]):                                                # computeResiduals returns 0: chi2 / 0 (:126-129)
+        return float("nan"), pose[:2]
+    res = np.zeros(area)
+    k = 0
+    for y in range(-half, half + 1):
+        for x in range(-half, half + 1):
+            res[k] = -(_np_bilin_f32(cur_grad, pose[0] + x, pose[1] + y) - T[k] + pose[2])
+            k += 1
+    med = np.sort(res)[area // 2]                                           # 49 or 25 residuals: odd, the plain median
+    mad = np.sort(np.abs(res - med))[area // 2]
+    sigma = max(1.482602218505602 * mad, np.finfo(float).eps)
+    c = 4.6851 * sigma
+    wgt = np.where(np.abs(res) <= c, (1 - res**2 / c**2) ** 2, 0.0)
+    chi2 = float((wgt * res * res).sum())
+    H = J.T @ (wgt[:, None] * J)
+    g = J.T @ (wgt * res)
+    lam = 1e-2 * H.diagonal().max()
+    try:
+        dxv = np.linalg.solve(H + lam * np.eye(3), g)
+    except np.linalg.LinAlgError:                                           # zero Jacobian: Eigen's LDLT::solve treats zero
+        dxv = np.linalg.pinv(H) @ g                                         # pivots as a pseudo-inverse does -> dx = 0
+    pose = pose + dxv                                                       # FeatureAlignment::update
+    return np.sqrt(chi2 / area), pose[:2]                                   # the pre-step RMSE and the moved pixel
+
+
+@pytest.mark.parametrize("patch", [7, 5])
+def test_feature_align_against_independent_numpy(orc, pair_cache, patch):
+    pair = pair_cache(3, 200)
+    gref, gcur = orc.abs_gradient(pair["ref"]), orc.abs_gradient(pair["cur"])
+    rng = np.random.default_rng(12)
+    f = pair["feats"][: pair["n_ref"]]
+    n = 0
+    for i in rng.choice(len(f), 60, replace=False):
+        ref_px = f["px"][i].astype(float)
+        start = ref_px + rng.uniform(-6, 6, 2)                              # sub-pixel starts around the feature
+        want_rmse, want_px = _np_feature_align_faithful(gref, gcur, ref_px, start, patch)
+        rmse, px, status, it = orc.feature_align(gref, gcur, ref_px, start, patch_size=patch, mode=orc.LM_FAITHFUL)
+        if np.isnan(want_rmse):
+            assert np.isnan(rmse)
+            continue
+        assert abs(rmse - want_rmse) <= 1e-9 * max(1.0, want_rmse), (i, rmse, want_rmse)
+        assert np.abs(px - want_px).max() <= 1e-7, (i, px, want_px)
+        n += 1
+    assert n > 40
+    # a reference pixel too close to the border: zero template and Jacobian (:74-77), and a start outside: NaN (0 / 0)
+    want_rmse, want_px = _np_feature_align_faithful(gref, gcur, np.array([2.0, 3.0]), np.array([40.0, 40.0]), patch)
+    rmse, px, _, _ = orc.feature_align(gref, gcur, [2.0, 3.0], [40.0, 40.0], patch_size=patch, mode=orc.LM_FAITHFUL)
+    assert abs(rmse - want_rmse) <= 1e-9 * max(1.0, want_rmse)              # the pre-step RMSE of the raw current patch
+    rmse, px, _, _ = orc.feature_align(gref, gcur, f["px"][0], [1.0, 1.0], patch_size=patch, mode=orc.LM_FAITHFUL)
+    assert np.isnan(rmse)
