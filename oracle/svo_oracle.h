@@ -18,6 +18,9 @@
  *   - orc_se3_exp       against the closed form / scipy Rotation
  *   - orc_sparse_align  (reference mode, four levels) against a second, independent numpy restatement to 1e-9 per
  *                       level (tests/test_oracle_numerics.py::test_align_against_independent_numpy)
+ *   - orc_sparse_align  (GN mode: Optimizer::optimizeGN, the headline benchmark's) against an independent numpy restatement
+ *                       of the loop and its exits: same evaluation counts, pose to 1e-10 per level
+ *                       (tests/test_oracle_numerics.py::test_align_gn_against_independent_numpy)
  *   - orc_feature_align (reference mode) against a second, independent numpy restatement: RMSE to 1e-9, moved pixel to
  *                       1e-7 (tests/test_oracle_numerics.py::test_feature_align_against_independent_numpy)
  *   - orc_select_ssc, orc_epipolar_match, orc_reproject_map  against direct python / numpy restatements and the golden

@@ -689,3 +689,137 @@ def test_feature_align_against_independent_numpy(orc, pair_cache, patch):
     assert abs(rmse - want_rmse) <= 1e-9 * max(1.0, want_rmse)              # the pre-step RMSE of the raw current patch
     rmse, px, _, _ = orc.feature_align(gref, gcur, f["px"][0], [1.0, 1.0], patch_size=patch, mode=orc.LM_FAITHFUL)
     assert np.isnan(rmse)
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# ImageAlignment::align with Optimizer::optimizeGN (src/optimizer.cpp:41-159) -- the mode of the headline benchmark (GN, <= 30
+# iterations per level) -- as a second, independent numpy restatement: same per-level set-up as _np_align_faithful, then the
+# Gauss-Newton loop with its exits (dx.maxCoeff() > 1e3, NaN, chi2 increase -> rollback, dx.dx < 1e-16 or chi2 < 0.1 after
+# the update, iteration cap).
+def _np_align_gn(ref_pyr, cur_pyr, feats, T_ref, T_cur, K, P=5, levels=(3, 2, 1, 0), max_iter=30):
+    from scipy.linalg import expm
+    from scipy.spatial.transform import Rotation
+
+    def to_mat(T):
+        M = np.eye(4)
+        M[:3, :3] = Rotation.from_quat(T[:4]).as_matrix()
+        M[:3, 3] = T[4:]
+        return M
+    Mref, Mcur = to_mat(np.asarray(T_ref, float)), to_mat(np.asarray(T_cur, float))
+    half, area = P // 2, P * P
+    F = len(feats)
+    out = []
+    for level in levels:
+        ref, cur = ref_pyr[level], cur_pyr[level]
+        lh, lw = ref.shape
+        scale = 1.0 / (1 << level)
+        fx, fy = K[0] / (1 << level), K[1] / (1 << level)
+        J = np.zeros((F * area, 6))
+        T_patch = np.zeros(F * area)
+        vis_ref = np.zeros(F, bool)
+        pW = np.zeros((F, 3))
+        Minv = np.linalg.inv(Mref)
+        Cref = Minv[:3, 3]                                   # camera centre in the world: -R^T t
+        b = half + 2
+        for f in range(F):
+            ft = feats[f]
+            if not ft["has_point"]:
+                continue
+            u, v = ft["px"][0] * scale, ft["px"][1] * scale
+            uI, vI = int(np.floor(u)), int(np.floor(v))
+            if uI - b < 0 or vI - b < 0 or uI + b >= lw or vI + b >= lh:
+                continue
+            vis_ref[f] = True
+            pw = Minv[:3, :3] @ (ft["bearing"] * np.linalg.norm(ft["point"] - Cref)) + Minv[:3, 3]
+            pW[f] = pw
+            x, y, z = pw
+            J0 = np.array([fx / z, 0, -fx * x / z**2, -fx * x * y / z**2, fx * x * x / z**2 + fx, -fx * y / z])
+            J1 = np.array([0, fy / z, -fy * y / z**2, -fy * y * y / z**2 - fy, fy * x * y / z**2, fy * x / z])
+            k = 0
+            for yy in range(-half, half + 1):
+                for xx in range(-half, half + 1):
+                    T_patch[f * area + k] = _np_bilin(ref, u + xx, v + yy)
+                    gx = 0.5 * (_np_bilin(ref, u + xx + 1, v + yy) - _np_bilin(ref, u + xx - 1, v + yy))
+                    gy = 0.5 * (_np_bilin(ref, u + xx, v + yy + 1) - _np_bilin(ref, u + xx, v + yy - 1))
+                    J[f * area + k] = gx * J0 + gy * J1
+                    k += 1
+
+        def evaluate(M):
+            r = np.zeros(F * area)
+            valid = np.zeros(F * area, bool)
+            for f in range(F):
+                if not vis_ref[f]:
+                    continue
+                pc = M[:3, :3] @ pW[f] + M[:3, 3]
+                u = (K[0] * pc[0] / pc[2] + K[2]) * scale
+                v = (K[1] * pc[1] / pc[2] + K[3]) * scale
+                uI, vI = int(np.floor(u)), int(np.floor(v))
+                if uI - b < 0 or vI - b < 0 or uI + b >= lw or vI + b >= lh:
+                    continue
+                k = 0
+                for yy in range(-half, half + 1):
+                    for xx in range(-half, half + 1):
+                        r[f * area + k] = _np_bilin(cur, u + xx, v + yy) - T_patch[f * area + k]
+                        valid[f * area + k] = True
+                        k += 1
+            nv = int(valid.sum())
+            med = _np_median_rule(r[valid], nv, F * area)
+            mad = _np_median_rule(np.abs(r[valid] - med), nv, F * area)
+            sigma = max(1.482602218505602 * mad, np.finfo(float).eps)
+            c = 4.6851 * sigma
+            wgt = np.where(valid & (np.abs(r) <= c), (1 - r**2 / c**2) ** 2, 0.0)
+            return float((wgt * r * r).sum()), J.T @ (wgt[:, None] * J), J.T @ (wgt * r), nv
+
+        pre_chi2, preM, it, evals, first = np.finfo(float).max, Mcur.copy(), 0, 0, None
+        while it < max_iter:
+            chi2, H, g, nv = evaluate(Mcur)
+            evals += 1
+            dx = np.linalg.solve(H, g)
+            if first is None:
+                first = dict(H=H, g=g, chi2=chi2)
+            if dx.max() > 1e3 or np.isnan(dx).any():
+                break
+            if chi2 > pre_chi2:
+                Mcur = preM.copy()
+                break
+            preM, pre_chi2 = Mcur.copy(), chi2
+            tw = np.zeros((4, 4))
+            tw[:3, :3] = np.array([[0, dx[5], -dx[4]], [-dx[5], 0, dx[3]], [dx[4], -dx[3], 0]])      # hat(-omega)
+            tw[:3, 3] = -dx[:3]
+            Mcur = Mcur @ expm(tw)
+            if dx @ dx < 1e-16 or chi2 < 1e-1:
+                break
+            it += 1
+        out.append(dict(first=first, pose=Mcur.copy(), rmse=np.sqrt(chi2 / nv), evaluations=evals))
+    return out
+
+
+def test_align_gn_against_independent_numpy(orc, pkg):
+    cv2 = pytest.importorskip("cv2")
+    from scipy.spatial.transform import Rotation
+    synth = pkg.synth
+    T_ref = synth.se3_from_Rt(synth.rodrigues(np.array([0.02, -0.03, 0.01])), [0.4, -0.2, 1.5])   # world != ref frame
+    pair = synth.make_pair(index=12, n_features=150, T_ref=tuple(T_ref))   # (with ~45 features the coarsest level sees ONE
+    T0 = synth.se3_mul(synth.se3_from_Rt(synth.rodrigues(np.array([1e-3, -2e-3, 5e-4])), [0.01, -0.02, -0.1]), pair["T_ref"])
+    feats = pair["feats"][:pair["n_ref"]]                                   # feature: singular normal equations, chaotic in any arithmetic)
+
+    def pyr(img):
+        out = [img]
+        for _ in range(3):
+            out.append(cv2.pyrDown(out[-1]))
+        return out
+    want = _np_align_gn(pyr(pair["ref"]), pyr(pair["cur"]), feats, pair["T_ref"], T0, pair["K"], max_iter=30)
+    rp, cp = orc.build_pyramid(pair["ref"], 4)[0], orc.build_pyramid(pair["cur"], 4)[0]
+    rmse, T, status, lv = orc.sparse_align(rp, rp, cp, pair["w"], pair["h"], feats, len(feats), 0, pair["T_ref"], pair["T_ref"],
+                                           pair["K"], T0, mode=orc.GN, max_iter=30)
+    for s, (o, w_) in enumerate(zip(lv, want)):
+        # the first iteration of the level: same normal equations
+        assert np.abs(o["H"] - w_["first"]["H"]).max() <= 1e-9 * np.abs(w_["first"]["H"]).max(), s
+        assert abs(o["chi2"] - w_["first"]["chi2"]) <= 1e-9 * w_["first"]["chi2"], s
+        # the level's result: same number of evaluations (same exits taken), same pose
+        assert o["evaluations"] == w_["evaluations"], (s, o["evaluations"], w_["evaluations"])
+        R = Rotation.from_quat(o["pose_after"][:4]).as_matrix()
+        assert np.abs(R - w_["pose"][:3, :3]).max() < 1e-10 and np.abs(o["pose_after"][4:] - w_["pose"][:3, 3]).max() < 1e-9, s
+        assert abs(o["rmse"] - w_["rmse"]) <= 1e-9 * w_["rmse"], s
+    assert abs(rmse - want[-1]["rmse"]) <= 1e-9 * want[-1]["rmse"]
+    assert sum(w_["evaluations"] for w_ in want) >= 10                       # the loop really iterates
