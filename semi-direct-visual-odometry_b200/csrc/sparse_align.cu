@@ -727,7 +727,11 @@ svo_status launch_sparse_align(svo_ctx* ctx)
     // fallback anywhere.
     {
         const char* e = getenv("SVO_ALIGN_GENERIC");
-        if (!(e && e[0] == '1') && sparse_align_v3_supported(ctx, maxF)) return launch_sparse_align_v3(ctx, maxF);
+        const char* v = getenv("SVO_ALIGN_V4");  // "0": keep the cluster kernel for <= 512 features too (A/B measurements)
+        if (!(e && e[0] == '1')) {
+            if (!(v && v[0] == '0') && sparse_align_v4_supported(ctx, maxF)) return launch_sparse_align_v4(ctx, maxF);
+            if (sparse_align_v3_supported(ctx, maxF)) return launch_sparse_align_v3(ctx, maxF);
+        }
     }
     maxF = (maxF + 15) & ~15;
     if ((int64_t)maxF * area >= 65536) SVO_FAIL(SVO_ERR_CAPACITY, "features * patch area must stay below 65536");
