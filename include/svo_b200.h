@@ -364,6 +364,43 @@ svo_status svo_frontend_run(svo_ctx* ctx, const svo_frontend_params* prm, const 
                             int max_selected, svo_fa_result* refined);
 uint8_t* svo_frontend_image_buffer(svo_ctx* ctx);
 
+/* ---------------------------------------------------------------------------------------------
+ * Several GPUs from one process (BASELINE config 5: 8,192 independent frame pairs over 2 / 4 / 8
+ * B200s).  The reference's System runs one sequence on one thread (src/system.cpp:36-60); a host
+ * that serves many sequences hands this layer a batch of independent ImageAlignment::align calls
+ * (src/image_alignment.cpp:25-67).  One context and one host worker thread per device; item j of a
+ * batch of n belongs to the device whose contiguous block svo_multi_shard() holds j; there is no
+ * exchange between devices, the final gather is every device writing its block of the caller's
+ * result array.  cfg: as svo_create, capacities PER DEVICE, cfg->device and cfg->stream ignored.
+ * devices: CUDA ordinals (NULL: 0 .. n_devices-1).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct svo_multi svo_multi;
+svo_status svo_multi_create(const svo_config* cfg, const int32_t* devices, int n_devices, svo_multi** out);
+void svo_multi_destroy(svo_multi* m);
+int svo_multi_devices(const svo_multi* m);
+svo_ctx* svo_multi_ctx(svo_multi* m, int i); /* the i-th device's context, for every per-context call above */
+const char* svo_multi_last_error(const svo_multi* m);
+/* block [lo, hi) of part `part` when n_items are cut into n_parts contiguous blocks (sizes differ by at most one) */
+void svo_multi_shard(int n_items, int n_parts, int part, int* lo, int* hi);
+/* svo_frames_upload (prefetch = 0) / svo_frames_prefetch (1) of n frames: frame j goes to the device of its block, into
+ * that device's slot first_slot + (j - lo) */
+svo_status svo_multi_frames_upload(svo_multi* m, int first_slot, int n, const uint8_t* imgs, int pitch,
+                                   int64_t frame_stride, int prefetch);
+/* svo_sparse_align over the devices.  jobs[j] runs on the device of its block; its slots are slots of THAT device;
+ * feat_offset indexes the global feats array.  results / stats: n_jobs (x levels) records, written block by block. */
+svo_status svo_multi_sparse_align(svo_multi* m, const svo_align_job* jobs, int n_jobs, const svo_align_feature* feats,
+                                  int n_feats, const svo_align_params* params, svo_align_result* results,
+                                  svo_align_level_stats* stats);
+/* the same in phases: stage (+ H2D), launch (asynchronous on every device), fetch (D2H + copy out) */
+svo_status svo_multi_sparse_align_stage(svo_multi* m, const svo_align_job* jobs, int n_jobs, const svo_align_feature* feats,
+                                        int n_feats, const svo_align_params* params, int want_stats);
+svo_status svo_multi_sparse_align_launch(svo_multi* m);
+svo_status svo_multi_sparse_align_fetch(svo_multi* m, svo_align_result* results, svo_align_level_stats* stats);
+svo_status svo_multi_sync(svo_multi* m);
+/* `steps` launches of the staged batch on every device after `warmup` untimed ones, timed per device with CUDA events on
+ * its stream; *ms_max = the slowest device's time for all steps */
+svo_status svo_multi_time_launches(svo_multi* m, int warmup, int steps, double* ms_max);
+
 #ifdef __cplusplus
 }
 #endif

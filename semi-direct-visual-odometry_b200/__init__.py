@@ -7,4 +7,4 @@ it with importlib.import_module("semi-direct-visual-odometry_b200") (the repo ro
 Nothing in this package touches oracle/ -- that is test infrastructure.
 """
 from . import capi, shard, synth  # noqa: F401
-from .capi import Context, SvoError, load  # noqa: F401
+from .capi import Context, MultiContext, SvoError, load  # noqa: F401

@@ -27,6 +27,9 @@ SYMBOLS = [
     "svo_feature_align", "svo_feature_align_stage", "svo_feature_align_h2d", "svo_feature_align_launch",
     "svo_feature_align_d2h", "svo_feature_align_fetch", "svo_frontend_run", "svo_frontend_image_buffer",
     "svo_epipolar_match", "svo_select_ssc", "svo_reproject_map", "svo_klt_track",
+    "svo_multi_create", "svo_multi_destroy", "svo_multi_devices", "svo_multi_ctx", "svo_multi_last_error", "svo_multi_shard",
+    "svo_multi_frames_upload", "svo_multi_sparse_align", "svo_multi_sparse_align_stage", "svo_multi_sparse_align_launch",
+    "svo_multi_sparse_align_fetch", "svo_multi_sync", "svo_multi_time_launches",
 ]
 
 
@@ -134,6 +137,23 @@ def load():
     L.svo_sparse_align_fetch.argtypes = [vp, vp, vp]
     L.svo_sparse_align_results_device.argtypes = [vp]
     L.svo_debug_cycles.argtypes = [vp, vp]
+    L.svo_multi_create.argtypes = [C.POINTER(Config), vp, i, C.POINTER(vp)]
+    L.svo_multi_destroy.argtypes = [vp]
+    L.svo_multi_destroy.restype = None
+    L.svo_multi_devices.argtypes = [vp]
+    L.svo_multi_ctx.argtypes = [vp, i]
+    L.svo_multi_ctx.restype = vp
+    L.svo_multi_last_error.argtypes = [vp]
+    L.svo_multi_last_error.restype = C.c_char_p
+    L.svo_multi_shard.argtypes = [i, i, i, C.POINTER(i), C.POINTER(i)]
+    L.svo_multi_shard.restype = None
+    L.svo_multi_frames_upload.argtypes = [vp, i, i, vp, i, i64, i]
+    L.svo_multi_sparse_align.argtypes = [vp, vp, i, vp, i, C.POINTER(AlignParams), vp, vp]
+    L.svo_multi_sparse_align_stage.argtypes = [vp, vp, i, vp, i, C.POINTER(AlignParams), i]
+    L.svo_multi_sparse_align_launch.argtypes = [vp]
+    L.svo_multi_sparse_align_fetch.argtypes = [vp, vp, vp]
+    L.svo_multi_sync.argtypes = [vp]
+    L.svo_multi_time_launches.argtypes = [vp, i, i, C.POINTER(C.c_double)]
     L.svo_sparse_align_results_device.restype = vp
     L.svo_reproject_map.argtypes = [vp, i, vp, vp, i, i, vp, i, i, C.POINTER(FaParams), vp, C.POINTER(i), vp]
     L.svo_klt_track.argtypes = [vp, i, i, vp, vp, i, C.POINTER(KltParams), vp, vp]
@@ -173,6 +193,85 @@ class PinnedBuffer:
             self._ctx.L.svo_host_free(self._ctx.h, self.ptr)
             self.ptr = None
             self.array = None
+
+
+def shard(n_items, n_parts, part):
+    """svo_multi_shard: block [lo, hi) of `part` when n_items are cut into n_parts contiguous blocks"""
+    lo, hi = C.c_int(), C.c_int()
+    load().svo_multi_shard(n_items, n_parts, part, C.byref(lo), C.byref(hi))
+    return lo.value, hi.value
+
+
+class MultiContext:
+    """svo_multi: one context + host worker thread per device of this process, batches cut into contiguous shards."""
+
+    def __init__(self, width, height, K, n_devices, devices=None, levels=4, max_frames=4, max_jobs=1, max_features=1024,
+                 max_fa_items=16):
+        self.L = load()
+        cfg = Config(0, width, height, levels, max_frames, max_jobs, max_features, max_fa_items, 0, None,
+                     (C.c_double * 4)(*[float(k) for k in K]))
+        dv = None if devices is None else np.ascontiguousarray(devices, dtype=np.int32)
+        h = C.c_void_p()
+        st = self.L.svo_multi_create(C.byref(cfg), _ptr(dv), n_devices, C.byref(h))
+        if st != OK:
+            raise SvoError(st, self.L.svo_last_error(None).decode())
+        self.h, self.n, self.width, self.height = h, n_devices, width, height
+        self._staged = None
+
+    def _check(self, st):
+        if st != OK:
+            raise SvoError(st, self.L.svo_multi_last_error(self.h).decode())
+
+    def close(self):
+        if self.h:
+            self.L.svo_multi_destroy(self.h)
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def upload(self, first_slot, imgs, prefetch=False):
+        a = np.ascontiguousarray(imgs, dtype=np.uint8)
+        assert a.ndim == 3 and a.shape[1:] == (self.height, self.width)
+        self._check(self.L.svo_multi_frames_upload(self.h, first_slot, a.shape[0], a.ctypes.data, a.strides[1], a.strides[0],
+                                                   1 if prefetch else 0))
+        return a
+
+    def sparse_align(self, jobs, feats, patch_size=5, min_level=0, max_level=3, mode=LM_FAITHFUL, max_iter=20, want_stats=True):
+        jobs = np.ascontiguousarray(jobs, dtype=ALIGN_JOB_DTYPE).reshape(-1)
+        feats = np.ascontiguousarray(feats, dtype=ALIGN_FEATURE_DTYPE).reshape(-1)
+        prm = AlignParams(patch_size, min_level, max_level, mode, max_iter, 0)
+        res = np.zeros(jobs.size, ALIGN_RESULT_DTYPE)
+        stats = np.zeros((jobs.size, max_level - min_level + 1), ALIGN_STATS_DTYPE) if want_stats else None
+        self._check(self.L.svo_multi_sparse_align(self.h, _ptr(jobs), jobs.size, _ptr(feats), feats.size, C.byref(prm), _ptr(res),
+                                                  _ptr(stats)))
+        return res, stats
+
+    def stage(self, jobs, feats, patch_size=5, min_level=0, max_level=3, mode=LM_FAITHFUL, max_iter=20):
+        jobs = np.ascontiguousarray(jobs, dtype=ALIGN_JOB_DTYPE).reshape(-1)
+        feats = np.ascontiguousarray(feats, dtype=ALIGN_FEATURE_DTYPE).reshape(-1)
+        prm = AlignParams(patch_size, min_level, max_level, mode, max_iter, 0)
+        self._check(self.L.svo_multi_sparse_align_stage(self.h, _ptr(jobs), jobs.size, _ptr(feats), feats.size, C.byref(prm), 0))
+        self._staged = jobs.size
+
+    def launch(self):
+        self._check(self.L.svo_multi_sparse_align_launch(self.h))
+
+    def fetch(self):
+        res = np.zeros(self._staged, ALIGN_RESULT_DTYPE)
+        self._check(self.L.svo_multi_sparse_align_fetch(self.h, _ptr(res), None))
+        return res
+
+    def sync(self):
+        self._check(self.L.svo_multi_sync(self.h))
+
+    def time_launches(self, warmup, steps):
+        ms = C.c_double()
+        self._check(self.L.svo_multi_time_launches(self.h, warmup, steps, C.byref(ms)))
+        return ms.value
 
 
 class Context:

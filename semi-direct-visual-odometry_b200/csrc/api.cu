@@ -244,7 +244,12 @@ svo_status svo_create(const svo_config* cfg, svo_ctx** out)
 
 void svo_destroy(svo_ctx* ctx) { release(ctx); }
 
-const char* svo_last_error(const svo_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+const char* svo_last_error(const svo_ctx* ctx)
+{
+    if (!ctx) return g_create_error.c_str();
+    std::lock_guard<std::recursive_mutex> guard(const_cast<svo_ctx*>(ctx)->mu);  // (the string is replaced under this lock)
+    return ctx->err.c_str();
+}
 
 svo_status svo_sync(svo_ctx* ctx)
 {
@@ -652,6 +657,8 @@ const void* svo_sparse_align_results_device(const svo_ctx* ctx) { return ctx ? c
 svo_status svo_sparse_align(svo_ctx* ctx, const svo_align_job* jobs, int n_jobs, const svo_align_feature* feats, int n_feats,
                             const svo_align_params* prm, svo_align_result* results, svo_align_level_stats* stats)
 {
+    if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);  // the five phases share the staged state: one caller at a time runs all of them (recursive lock)
     svo_status st = svo_sparse_align_stage(ctx, jobs, n_jobs, feats, n_feats, prm, stats != nullptr);
     if (st != SVO_OK) return st;
     if ((st = svo_sparse_align_h2d(ctx)) != SVO_OK) return st;
@@ -722,6 +729,8 @@ svo_status svo_feature_align_fetch(svo_ctx* ctx, svo_fa_result* results)
 
 svo_status svo_feature_align(svo_ctx* ctx, const svo_fa_item* items, int n, const svo_fa_params* prm, svo_fa_result* results)
 {
+    if (!ctx) return SVO_ERR_INVALID;
+    SVO_LOCK(ctx);  // (as svo_sparse_align)
     svo_status st = svo_feature_align_stage(ctx, items, n, prm);
     if (st != SVO_OK) return st;
     if ((st = svo_feature_align_h2d(ctx)) != SVO_OK) return st;

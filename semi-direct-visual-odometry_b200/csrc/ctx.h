@@ -202,6 +202,7 @@ svo_status launch_epipolar_match(svo_ctx* ctx, int n, const svo_epi_params& prm)
 svo_status launch_klt_track(svo_ctx* ctx, int refSlot, int curSlot, int n, const svo_klt_params& prm, int topLevel);
 size_t klt_smem_bytes(int win);
 void frontend_release(svo_ctx* ctx);
+void frontend_invalidate_graphs(svo_ctx* ctx);  // destroys the captured front-end graphs (their kernel arguments went stale)
 size_t sparse_align_smem_bytes(int nthreads, int max_features, int patch_area);
 bool sparse_align_v3_supported(const svo_ctx* ctx, int maxF);
 svo_status launch_sparse_align_v3(svo_ctx* ctx, int maxF);

@@ -107,7 +107,15 @@ svo_status frontend_enqueue(svo_ctx* ctx, const svo_frontend_params& p)
     ctx->staged_levels     = p.align.max_level - p.align.min_level + 1;
     ctx->staged_want_stats = 0;
     ctx->staged_params     = p.align;
-    if ((rc = launch_sparse_align_v3(ctx, p.max_features)) != SVO_OK) return rc;
+    // (<= 512 features: the single-CTA kernel, which owns no scratch memory; beyond: the cluster kernel, whose scratch
+    // pointer is a captured argument -- frontend_invalidate_graphs drops the graphs whenever it is reallocated)
+    if (sparse_align_v4_supported(ctx, p.max_features))
+        rc = launch_sparse_align_v4(ctx, p.max_features);
+    else if (sparse_align_v3_supported(ctx, p.max_features))
+        rc = launch_sparse_align_v3(ctx, p.max_features);
+    else
+        SVO_FAIL(SVO_ERR_CAPACITY, "svo_frontend_run: more features than the alignment kernels hold");
+    if (rc != SVO_OK) return rc;
     // candidates with the aligned pose, refined per feature
     ReprojArgs ra;
     ra.job        = ctx->d_jobs;
@@ -129,8 +137,10 @@ svo_status frontend_enqueue(svo_ctx* ctx, const svo_frontend_params& p)
     return SVO_OK;
 }
 
-svo_status frontend_graph(svo_ctx* ctx, const svo_frontend_params& p, cudaGraphExec_t* out)
+// *ranEagerly: the configuration was new, its eager pass has already processed the staged inputs
+svo_status frontend_graph(svo_ctx* ctx, const svo_frontend_params& p, cudaGraphExec_t* out, bool* ranEagerly)
 {
+    *ranEagerly = false;
     for (int i = 0; i < ctx->fe_count; i++)
         if (same_params(ctx->fe_graphs[i].prm, p)) {
             *out = ctx->fe_graphs[i].exec;
@@ -156,37 +166,68 @@ svo_status frontend_graph(svo_ctx* ctx, const svo_frontend_params& p, cudaGraphE
     const int64_t launches_before = ctx->launches;
     SVO_CUDA(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed));
     rc = frontend_enqueue(ctx, p);
+    G.graph       = nullptr;
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &G.graph);
-    ctx->launches = launches_before;  // capturing is not launching
-    if (rc != SVO_OK) return rc;
-    SVO_CUDA(e);
-    SVO_CUDA(cudaGraphInstantiate(&G.exec, G.graph, 0));
+    const int64_t eager_launches = ctx->launches - launches_before;  // kernels of one pass
+    ctx->launches                = launches_before;                  // capturing is not launching
+    auto drop = [&]() {  // no graph object outlives a failure
+        if (G.graph) cudaGraphDestroy(G.graph);
+        G.graph = nullptr;
+    };
+    if (rc != SVO_OK) {
+        drop();
+        return rc;
+    }
+    if (e != cudaSuccess) {
+        drop();
+        SVO_CUDA(e);
+    }
+    e = cudaGraphInstantiate(&G.exec, G.graph, 0);
+    if (e != cudaSuccess) {
+        drop();
+        SVO_CUDA(e);
+    }
     ctx->fe_kernel_nodes = 0;
     {
         size_t n = 0;
-        SVO_CUDA(cudaGraphGetNodes(G.graph, nullptr, &n));
-        std::vector<cudaGraphNode_t> nodes(n);
-        SVO_CUDA(cudaGraphGetNodes(G.graph, nodes.data(), &n));
-        for (size_t i = 0; i < n; i++) {
+        std::vector<cudaGraphNode_t> nodes;
+        e = cudaGraphGetNodes(G.graph, nullptr, &n);
+        if (e == cudaSuccess) {
+            nodes.resize(n);
+            e = cudaGraphGetNodes(G.graph, nodes.data(), &n);
+        }
+        for (size_t i = 0; e == cudaSuccess && i < n; i++) {
             cudaGraphNodeType t;
-            SVO_CUDA(cudaGraphNodeGetType(nodes[i], &t));
-            if (t == cudaGraphNodeTypeKernel) ctx->fe_kernel_nodes++;
+            e = cudaGraphNodeGetType(nodes[i], &t);
+            if (e == cudaSuccess && t == cudaGraphNodeTypeKernel) ctx->fe_kernel_nodes++;
+        }
+        if (e != cudaSuccess) {
+            cudaGraphExecDestroy(G.exec);
+            drop();
+            SVO_CUDA(e);
         }
     }
+    (void)eager_launches;
     ctx->fe_count++;
-    *out = G.exec;
+    *out        = G.exec;
+    *ranEagerly = true;
     return SVO_OK;
 }
 
 }  // namespace
 
-void frontend_release(svo_ctx* ctx)
+void frontend_invalidate_graphs(svo_ctx* ctx)
 {
     for (int i = 0; i < ctx->fe_count; i++) {
         cudaGraphExecDestroy(ctx->fe_graphs[i].exec);
         cudaGraphDestroy(ctx->fe_graphs[i].graph);
     }
     ctx->fe_count = 0;
+}
+
+void frontend_release(svo_ctx* ctx)
+{
+    frontend_invalidate_graphs(ctx);
     if (ctx->h_fe_align) cudaFreeHost(ctx->h_fe_align);
     if (ctx->h_fe_fa) cudaFreeHost(ctx->h_fe_fa);
     if (ctx->h_fe_sel) cudaFreeHost(ctx->h_fe_sel);
@@ -252,11 +293,14 @@ svo_status svo_frontend_run(svo_ctx* ctx, const svo_frontend_params* prm, const 
         std::memset(ctx->h_occupancy, 0, (size_t)rows * cols);
     // ---- one graph launch ----
     cudaGraphExec_t exec;
-    const svo_status rc = frontend_graph(ctx, p, &exec);
+    bool ranEagerly = false;
+    const svo_status rc = frontend_graph(ctx, p, &exec, &ranEagerly);
     if (rc != SVO_OK) return rc;
-    SVO_CUDA(cudaGraphLaunch(exec, ctx->stream));
+    if (!ranEagerly) {  // (a new configuration has just processed this frame while it was set up: no second pass)
+        SVO_CUDA(cudaGraphLaunch(exec, ctx->stream));
+        SVO_CUDA(cudaStreamSynchronize(ctx->stream));
+    }
     ctx->launches += ctx->fe_kernel_nodes;
-    SVO_CUDA(cudaStreamSynchronize(ctx->stream));
     // ---- outputs ----
     result->align      = *ctx->h_fe_align;
     result->n_selected = *reinterpret_cast<const int32_t*>(ctx->h_fe_sel);

@@ -847,7 +847,10 @@ svo_status launch_v3(svo_ctx* ctx, int maxF)
     const long long chunk_stride = 6LL * NT + (long long)nLevels * G::ROWW * NT;  // floats
     const long long job_stride   = chunk_stride * C;
     const size_t need            = (size_t)job_stride * 4 * nJobs;
+    if ((long long)NT * C < maxF) SVO_FAIL(SVO_ERR_CAPACITY, "sparse alignment: more than 4,096 features per pair");
     if (need > ctx->scratch2_bytes) {
+        // the front-end graphs captured this pointer as a kernel argument: they are stale once it is freed
+        frontend_invalidate_graphs(ctx);
         SVO_CUDA(cudaStreamSynchronize(ctx->stream));
         if (ctx->d_scratch2) SVO_CUDA(cudaFree(ctx->d_scratch2));
         ctx->d_scratch2     = nullptr;
@@ -889,14 +892,14 @@ svo_status launch_v3(svo_ctx* ctx, int maxF)
 
 }  // namespace
 
-// returns true when the cluster fast path handles this batch: patch 4 / 5, at most 8 CTAs per pair
+// returns true when the cluster fast path handles this batch: patch 4 / 5, at most 8 CTAs (4,096 features) per pair
 bool sparse_align_v3_supported(const svo_ctx* ctx, int maxF)
 {
     const svo_align_params& prm = ctx->staged_params;
     if (prm.patch_size != 4 && prm.patch_size != 5) return false;
     int NT, C;
     v3_shape(ctx, maxF, ctx->staged_jobs, &NT, &C);
-    return C <= 8;
+    return C <= 8 && (long long)NT * C >= maxF;  // 8 CTAs of 512 threads hold 4,096 features
 }
 
 svo_status launch_sparse_align_v3(svo_ctx* ctx, int maxF)

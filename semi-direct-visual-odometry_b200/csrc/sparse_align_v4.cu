@@ -71,7 +71,7 @@ __host__ __device__ constexpr size_t v4_smem_bytes()
     size_t b = 0;
     b += (size_t)G::AREA * NT * 4;      // T
     b += (size_t)G::AREA * NT * 8;      // (gx, gy)
-    b += s4_smem_words<NT>() * 4;       // selection
+    b += s4_smem_words<NT, G::AREA>() * 4;       // selection
     b = (b + 15) & ~size_t(15);
     b += (size_t)(NT / 32) * 32 * 8;    // red
     b += sizeof(Ctrl) + 64;
@@ -97,8 +97,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_align_v4(const V4Args a)
     sp += (size_t)G::AREA * NT * 4;
     float2* Gm = reinterpret_cast<float2*>(sp);        // [AREA][NT]
     sp += (size_t)G::AREA * NT * 8;
-    S4Smem<NT, G::AREA * NT * 12> sel;  // (views derived from the shared-memory symbol: LDS / STS / ATOMS, never generic)
-    sp += (s4_smem_words<NT>() * 4 + 15) & ~size_t(15);
+    S4Smem<NT, G::AREA * NT * 12, G::AREA> sel;  // (views derived from the shared-memory symbol: LDS / STS / ATOMS, never generic)
+    sp += (s4_smem_words<NT, G::AREA>() * 4 + 15) & ~size_t(15);
     double* red = reinterpret_cast<double*>(sp);       // [NW][32]
     sp += (size_t)NW * 32 * 8;
     Ctrl* ctrl = reinterpret_cast<Ctrl*>(sp);
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_align_v4(const V4Args a)
                             const int y = gy - 2;  // patch row: grid rows y, y + 1, y + 2 are g0, g1, g2
 #pragma unroll
                             for (int xx = 0; xx < P; xx++) {
-                                Tm[(size_t)(y * P + xx) * NT + f] = g1[xx + 1];
+                                Tm[(size_t)(y * P + xx) * NT + f] = g1[xx + 1] * 65536.f;  // exact: the residuals are kept x 2^16
                                 Gm[(size_t)(y * P + xx) * NT + f] = make_float2(g1[xx + 2] - g1[xx], g2[xx + 1] - g0[xx + 1]);
                             }
                         }
@@ -272,6 +272,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_align_v4(const V4Args a)
         const bool faithful = a.prm.mode == SVO_LM_FAITHFUL;
         const int maxIter   = a.prm.max_iter > 0 ? a.prm.max_iter : 20;
         bool lmFirst        = true;  // thread 0 only
+        int evalInLevel     = 0;
 #ifdef SVO_PROFILE
         long long tph[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #define V4_TICK(var) const long long var = clock64()
@@ -291,8 +292,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_align_v4(const V4Args a)
                 const double cyp = R[3] * pwx + R[4] * pwy + R[5] * pwz + ctrl->t[1];
                 const double czp = R[6] * pwx + R[7] * pwy + R[8] * pwz + ctrl->t[2];
                 // PinholeCamera::project2d, src/pinhole_camera.cpp:55-56 (no z > 0 test)
-                const double u = (fx0 * (cxp / czp) + cx0) * scale;
-                const double v = (fy0 * (cyp / czp) + cy0) * scale;
+                const double rz = 1.0 / czp;  // one reciprocal for both coordinates (<= 1 ulp from the two divisions)
+                const double u  = (fx0 * (cxp * rz) + cx0) * scale;
+                const double v  = (fy0 * (cyp * rz) + cy0) * scale;
                 if (isfinite(u) && isfinite(v) && fabs(u) < 1e6 && fabs(v) < 1e6) {
                     const double uf = floor(u), vf = floor(v);
                     uI = (int)uf;
@@ -316,7 +318,8 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_align_v4(const V4Args a)
                     for (int r = 0; r < G::FW; r++) load8(curImg + (long long)(wy + r) * lpitch + wx, winLo[r], winHi[r]);
                 }
                 const uint32_t off = (uint32_t)(x0 - wx);  // 0 .. 8 - FW
-                const float wu0 = 1.f - fu, wv0 = 1.f - fv;
+                const float wu0 = 1.f - fu;
+                const float wv0s = (1.f - fv) * 65536.f, fvs = fv * 65536.f;  // vertical weights x 2^16 (exact scaling)
                 float prevRow[P];
 #pragma unroll
                 for (int r = 0; r < G::FW; r++) {
@@ -332,9 +335,9 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_align_v4(const V4Args a)
                     if (r > 0) {
 #pragma unroll
                         for (int c = 0; c < P; c++) {
-                            const float val      = wv0 * prevRow[c] + fv * curRow[c];
-                            const float T        = Tm[(size_t)((r - 1) * P + c) * NT + f];
-                            rs[(r - 1) * P + c] = (val - T) * 65536.f;
+                            // 2^16 (I - T) in two fused multiply-adds
+                            const float Ts       = Tm[(size_t)((r - 1) * P + c) * NT + f];
+                            rs[(r - 1) * P + c] = fmaf(fvs, curRow[c], fmaf(wv0s, prevRow[c], -Ts));
                         }
                     }
 #pragma unroll
@@ -358,14 +361,18 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_align_v4(const V4Args a)
                     const double mad = 0.5 * ((double)so.dHi + (double)so.dLo);  // deviations are doubled: 2^-17 units
                     sigma            = 1.482602218505602 * mad * (1.0 / 131072.0);
                     if (sigma <= DBL_EPSILON) sigma = DBL_EPSILON;
-                    tierCount += tier == 1 ? 1 : (tier == 2 ? 0x100 : 0x10000);
-                    lastWhy = sel.why;
+                    tierCount += tier == 0 ? 0x1000000 : (tier == 1 ? 1 : (tier == 2 ? 0x100 : 0x10000));  // bracket << 24 | hot | cold << 8 | generic << 16
+                    lastWhy = (sel.why & 0xf) | (sel.shiftUsed << 4);
+                    // Below the coarsest level the pose is already close: from the first to the second evaluation of a level
+                    // the median and the deviation move by a few hundredths of an intensity unit (measured: < 0.05), while the
+                    // jump ACROSS the level change, which `moved` holds now, says nothing about it.
+                    if (evalInLevel == 0 && si > 0) pred.moved = 3277u, pred.haveMove = true;
                 }
+                evalInLevel++;
             }
             V4_TICK(c2);
-            const double cD = 4.6851 * sigma;
-            const float cF  = (float)cD;
-            const float ic2 = (float)(1.0 / (cD * cD));
+            const double cD  = 4.6851 * sigma;
+            const float nic2 = (float)(-1.0 / (cD * cD * 4294967296.0));  // -1 / c^2 for residuals x 2^16
 
             // --- per-feature patch sums (FP32) and the feature's 28 contributions ---
             float val[32];
@@ -375,13 +382,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_align_v4(const V4Args a)
                 float sxx = 0.f, sxy = 0.f, syy = 0.f, bx = 0.f, by = 0.f, ch = 0.f;
 #pragma unroll
                 for (int i = 0; i < G::AREA; i++) {
-                    const float rr = rs[i] * (1.f / 65536.f);
+                    const float rr = rs[i];                   // 2^16 r: rescaled once per feature
                     const float2 g = Gm[(size_t)i * NT + f];  // twice the central differences: rescaled once per feature
-                    float w        = 0.f;
-                    if (fabsf(rr) <= cF) {
-                        const float t = 1.f - rr * rr * ic2;
-                        w             = t * t;
-                    }
+                    const float t  = fmaxf(fmaf(rr * rr, nic2, 1.f), 0.f);  // Tukey: (1 - r^2 / c^2)^2 for |r| <= c, else 0
+                    const float w  = t * t;
                     const float wgx = w * g.x, wgy = w * g.y, wr = w * rr;
                     sxx += wgx * g.x;
                     sxy += wgx * g.y;
@@ -390,7 +394,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_align_v4(const V4Args a)
                     by += wr * g.y;
                     ch += wr * rr;
                 }
-                sxx *= 0.25f, sxy *= 0.25f, syy *= 0.25f, bx *= 0.5f, by *= 0.5f;
+                sxx *= 0.25f, sxy *= 0.25f, syy *= 0.25f, bx *= 0.5f / 65536.f, by *= 0.5f / 65536.f, ch *= 1.f / 4294967296.f;
                 // J_row = gx A + gy B:  H += sxx A A^T + sxy (A B^T + B A^T) + syy B B^T = A u^T + B v^T
                 float uu[6], vv[6];
 #pragma unroll
@@ -438,7 +442,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_align_v4(const V4Args a)
                         const long long n = a.dbg[0];
                         if (n < 31) {
                             a.dbg[1 + 2 * n] = __double_as_longlong(sigma);
-                            a.dbg[2 + 2 * n] = (long long)(tierCount & 0xffffffu) | ((long long)(lastWhy & 0xff) << 24) | ((long long)numValid << 32);
+                            a.dbg[2 + 2 * n] = (long long)(tierCount & 0xffffffu) | ((long long)(lastWhy & 0xff) << 24) | ((long long)numValid << 32) | ((long long)(tierCount >> 24) << 56);
                             a.dbg[0]         = n + 1;
                         }
                     }

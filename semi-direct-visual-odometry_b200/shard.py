@@ -5,17 +5,20 @@ import numpy as np
 
 
 def shard_range(n_total, rank, world):
-    """Contiguous block of pair indices [lo, hi) owned by `rank`: pair i -> rank i // ceil(n_total / world)."""
+    """Contiguous block of pair indices [lo, hi) owned by `rank`; block sizes differ by at most one, the first
+    n_total % world blocks are the larger ones.  The same arithmetic as svo_multi_shard (csrc/multi.cu), which the
+    single-process C++ multi-GPU layer uses; tests/test_shard_gloo.py checks the two against each other."""
     if world < 1 or not 0 <= rank < world:
         raise ValueError("bad rank / world size")
-    per = -(-n_total // world)
-    lo = min(n_total, rank * per)
-    return lo, min(n_total, lo + per)
+    q, r = divmod(n_total, world)
+    lo = rank * q + min(rank, r)
+    return lo, lo + q + (1 if rank < r else 0)
 
 
 def owner_of(pair, n_total, world):
-    per = -(-n_total // world)
-    return pair // per
+    q, r = divmod(n_total, world)
+    big = r * (q + 1)
+    return pair // (q + 1) if pair < big else r + (pair - big) // q
 
 
 def gather_records(local_bytes, dist, dst=0, out=None):

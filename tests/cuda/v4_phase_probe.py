@@ -4,7 +4,7 @@ import importlib, os, sys, numpy as np
 sys.path.insert(0, "/root/repo")
 pkg = importlib.import_module("semi-direct-visual-odometry_b200")
 NAMES = ["hot fill", "hot scan", "hot locate", "lists", "priv fill", "priv reduce", "priv scan", "priv locate", "atomic fill", "atomic scan",
-         "atomic locate", "generic"]
+         "atomic locate", "generic", "bracket"]
 os.environ["SVO_ALIGN_V4"] = "1"
 for idx in (0, 3):
     pair = pkg.synth.make_pair(idx, 500)
@@ -24,5 +24,5 @@ for idx in (0, 3):
             print(d[:, :7])
             tot = d[:, :6].sum(0); n = d[:, 6].sum()
             print("cycles per evaluation:", (tot / n).round(0), "total", (tot.sum() / n).round(0), "=> us/eval %.2f" % (tot.sum() / n / 1965))
-            sel = dd.reshape(-1)[32:44]
+            sel = dd.reshape(-1)[32:45]
             print("selection cycles (total over the pair):", ", ".join("%s %d" % (nm, v) for nm, v in zip(NAMES, sel)))

@@ -30,7 +30,7 @@ def trace(dbg):
     for e in range(min(n, 31)):
         sig = np.array([dbg[1 + 2 * e]], np.int64).view(np.float64)[0]
         t = int(dbg[2 + 2 * e])
-        out.append((sig, t & 0xffffff, (t >> 24) & 0xff, t >> 32))
+        out.append((sig, (t & 0xffffff) | ((t >> 56) << 24), (t >> 24) & 0xff, (t >> 32) & 0xffffff))
     return out
 
 
@@ -100,9 +100,9 @@ def main():
                 ctx.sparse_align_d2h()
                 res = ctx.sparse_align_fetch()[0]
                 tiers = res["reserved"].astype(np.int64)
-                print("%s %s: %.1f us per launch, evals/pair %.2f, tiers hot %d cold %d generic %d" % (
-                    "v4" if v4 else "v3", label, dt * 1e6, res["evaluations"].mean(), (tiers & 0xff).sum(), ((tiers >> 8) & 0xff).sum(),
-                    ((tiers >> 16) & 0xff).sum()))
+                print("%s %s: %.1f us per launch, evals/pair %.2f, tiers bracket %d hot %d cold %d generic %d" % (
+                    "v4" if v4 else "v3", label, dt * 1e6, res["evaluations"].mean(), ((tiers >> 24) & 0xff).sum(), (tiers & 0xff).sum(),
+                    ((tiers >> 8) & 0xff).sum(), ((tiers >> 16) & 0xff).sum()))
             rot = np.array([synth.rotation_angle(res[i]["T_cur"], batch["T_true"][i]) for i in range(n)])
             print("   median rot err %.2e" % np.median(rot))
 

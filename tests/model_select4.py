@@ -103,10 +103,23 @@ def locate(hists, k, need_pred, w):
         lo0 = max(w.gR - bMax - 1, bMin - w.gL - w.nbL)
         lo1, lo0 = max(lo1, 1), max(lo0, 0)
     kk = k if need_pred else k + 1
-    j1 = first_true(lo1, hi1, lambda j: Glo(j) >= k + 1)
-    if j1 > hi1:
+    # The kernel probes with one thread per bin: thread t of window X takes the UPPER edge gX + t + 1 of its bin as the
+    # upper argument of Glo / Ghi (only R's edges without contiguity).  The lowest edge of a window is therefore no
+    # probe; an unprobed lo1 only loosens j1, the unprobed lo0 is checked explicitly.
+    edges = []
+    for X, (g, nb) in enumerate(((w.gM, w.nbM), (w.gL, w.nbL), (w.gR, w.nbR))):
+        if X != 2 and not w.contig:
+            continue
+        edges += [g + t + 1 for t in range(nb)]
+    c1 = [b - bMin for b in edges if lo1 <= b - bMin <= hi1 and Glo(b - bMin) >= k + 1]
+    if not c1:
         return MISS
-    jz = first_true(lo0, min(hi0, j1), lambda j: Ghi(j) >= kk)
+    j1 = min(c1)
+    c0 = [b - bMax - 1 for b in edges if lo0 <= b - bMax - 1 <= hi0 and Ghi(b - bMax - 1) >= kk]
+    jz = min(c0) if c0 else hi0 + 1
+    if lo0 <= hi0 and jz > lo0 and Ghi(lo0) >= kk:
+        jz = lo0
+    jz = min(jz, min(hi0, j1) + 1)
     j0 = jz - 1
     if j0 < lo0:
         if not w.contig:

@@ -50,6 +50,14 @@ def test_shard_ranges(pkg):
         shard.shard_range(10, 2, 2)
 
 
+def test_shard_ranges_match_the_c_layer(pkg):
+    """svo_multi_shard (the C++ multi-GPU layer of libsvo_b200.so) and shard.shard_range (the torch.distributed path) cut a
+    batch the same way."""
+    for n, w in [(8192, 8), (8192, 3), (1024, 2), (37, 2), (5, 8), (0, 2), (1000, 7)]:
+        for r in range(w):
+            assert pkg.capi.shard(n, w, r) == pkg.shard.shard_range(n, r, w)
+
+
 def test_two_rank_gather_gloo(pkg):
     import torch.multiprocessing as mp
     s = socket.socket()
