@@ -45,7 +45,8 @@ namespace {
 constexpr unsigned S4_FULL    = 0xffffffffu;
 constexpr uint32_t S4_BIAS    = 0x4B400000u;  // bits of 1.5 * 2^23
 constexpr float S4_MAGIC      = 12582912.f;
-constexpr uint32_t S4_DMAX    = 1u << 21;     // deviations up to 32 intensity units are handled by the window tiers
+constexpr uint32_t S4_DMAX    = 30u << 16;    // deviations up to 30 intensity units are handled by the window tiers: the widest span
+                                              // (64 bins of one unit around a median within 16 units of zero) ends inside the linear range
 constexpr int S4_CAPM         = 64;  // candidate list of the median
 constexpr int S4_CAPD         = 128; // candidate list of the deviation
 constexpr int S4_ATOMIC_LIMIT = 3072;  // a round with more keys inside its windows than this is counted privately instead
@@ -863,7 +864,7 @@ __device__ __forceinline__ bool s4_sigma(const float (&rs)[AREA], bool vis, int 
     sm.tlast = clock64();
 #endif
     // the window tiers need LINEAR keys inside their windows: median within 16 units of zero, deviation below 30 units
-    // (16 + 30 x 1.75 / ... all windows end below 64 units); anything else is the generic tier's
+    // (16 + 30 + margins: every window ends below 64 units); anything else is the generic tier's
     const uint32_t mOff = pr.m > S4_BIAS ? pr.m - S4_BIAS : S4_BIAS - pr.m;
     const bool inRange  = (!pr.haveM || mOff <= (1u << 20)) && (!pr.haveD || pr.d <= S4_DMAX - (1u << 18));
     // ---- bracket: the previous evaluation predicts both statistics to within 1/64 of an intensity unit ----
@@ -924,8 +925,8 @@ __device__ __forceinline__ bool s4_sigma(const float (&rs)[AREA], bool vis, int 
     if (!o.ok && inRange) {
         *tier        = 2;
         uint32_t m0  = pr.haveM ? pr.m : S4_BIAS;
-        uint32_t dhi = pr.haveD ? pr.d + (pr.d >> 1) + (pr.d >> 2) + 8192u : S4_DMAX;  // 1.75 x the last deviation; 32 units
-        // (m0 within 16 units, dhi <= 32 units, margins of a few bins: every window ends inside +/- 64 units)
+        uint32_t dhi = pr.haveD ? pr.d + (pr.d >> 1) + (pr.d >> 2) + 8192u : S4_DMAX;  // 1.75 x the last deviation; 30 units
+        // (m0 within 16 units, dhi <= 30 units -> bins of at most one unit, span of 32 bins either side: inside +/- 64 units)
         bool full    = !pr.haveD;
 #pragma unroll 1
         for (int attempt = 0; attempt < 4 && !o.ok; attempt++) {

@@ -292,9 +292,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_align_v4(const V4Args a)
                 const double cyp = R[3] * pwx + R[4] * pwy + R[5] * pwz + ctrl->t[1];
                 const double czp = R[6] * pwx + R[7] * pwy + R[8] * pwz + ctrl->t[2];
                 // PinholeCamera::project2d, src/pinhole_camera.cpp:55-56 (no z > 0 test)
-                const double rz = 1.0 / czp;  // one reciprocal for both coordinates (<= 1 ulp from the two divisions)
-                const double u  = (fx0 * (cxp * rz) + cx0) * scale;
-                const double v  = (fy0 * (cyp * rz) + cy0) * scale;
+                // (two true divisions, as the reference: with an identity prior the features project onto INTEGER pixels, and
+                // a reciprocal-multiply that is 1 ulp off flips floor() and with it the border test)
+                const double u = (fx0 * (cxp / czp) + cx0) * scale;
+                const double v = (fy0 * (cyp / czp) + cy0) * scale;
                 if (isfinite(u) && isfinite(v) && fabs(u) < 1e6 && fabs(v) < 1e6) {
                     const double uf = floor(u), vf = floor(v);
                     uI = (int)uf;
