@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--pairs", type=int, default=1024, help="frame pairs per GPU")
+    ap.add_argument("--total-pairs", type=int, default=0, help="strong scaling: this many pairs in total, sharded over the GPUs "
+                    "(BASELINE config 5: 8192); overrides --pairs")
     ap.add_argument("--features", type=int, default=500)
     ap.add_argument("--mode", default="gn", choices=sorted(MODES))
     ap.add_argument("--max-iter", type=int, default=30)
@@ -53,6 +55,12 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=10.0, help="CPU-baseline budget: the sample is repeated until it is spent")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     return ap.parse_args()
+
+
+def config_dict(a):
+    """identical in both arms (the driver compares them key by key); run-specific remarks go to `notes`"""
+    return {"workload": workload_name(a), "pairs_per_gpu": a.pairs, "features": a.features, "levels": LEVELS, "patch": PATCH,
+            "mode": a.mode, "max_iter": a.max_iter}
 
 
 def workload_name(a):
@@ -114,7 +122,7 @@ def run_reference(a, rank):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": a.gpus, "steps": a.steps,
         "warmup": a.warmup, "ms_per_step": 1e3 * t_total / a.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": workload_name(a), "sample_pairs_per_step": sample},
+        "config": config_dict(a), "notes": {"sample_pairs_per_step": sample},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }))
@@ -237,9 +245,9 @@ def run_b200(a, rank, world):
         sector_bytes = float((nvis * (32.0 * (PATCH + 3) + ev * 32.0 * (PATCH + 1))).sum() + 32.0 * batch["n_feat"].sum()
                              + 256.0 * LEVELS * n)
         evals_total = int(res["evaluations"].sum())
-        tiers = res["reserved"].astype(np.int64)  # fast-path diagnostics: selections served hot | cold << 8 | generic << 16
-        sel_tiers = {"hot": int((tiers & 0xff).sum()), "cold": int(((tiers >> 8) & 0xff).sum()),
-                     "generic": int(((tiers >> 16) & 0xff).sum())}
+        tiers = res["reserved"].astype(np.int64)  # diagnostics: evaluations whose robust scale came from the tier hot | cold << 8 |
+        sel_tiers = {"bracket": int(((tiers >> 24) & 0xff).sum()), "hot": int((tiers & 0xff).sum()),   # generic << 16 | bracket << 24
+                     "cold": int(((tiers >> 8) & 0xff).sum()), "generic": int(((tiers >> 16) & 0xff).sum())}
 
         gather_buf = None
         if world > 1:
@@ -348,8 +356,10 @@ def run_b200(a, rank, world):
         ctx.close()
 
     traffic, issue = None, None  # DRAM bytes of the dominant kernel per launch, from the committed ncu --set full capture
+    kernel_name = "k_align_v4"
     try:
-        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_k_align_cluster.json")))
+        kernel_name = "k_align_v4" if F <= 512 and os.environ.get("SVO_ALIGN_V4") != "0" else "k_align_cluster"
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_%s.json" % kernel_name)))
         if a.features == tj["features"] and a.mode == "gn":
             traffic = tj["dram_bytes_per_pair"] * n
             # what actually bounds the kernel (same capture): issue-slot utilisation and the stall reasons per issue
@@ -363,17 +373,18 @@ def run_b200(a, rank, world):
         achieved = alg_bytes / (kern_ms * 1e-3) / 1e9
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": a.steps, "warmup": a.warmup,
-            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "ms_per_step": ms_total / a.steps, "higher_is_better": True, "scaling": a.scaling, "vs_baseline": None,
             "dtype": "f32 (FP64 pose/warp/solve, FP32 pixels, FP64 accumulation over features)", "data": "synthetic",
-            "config": {"workload": workload_name(a), "pairs_total": world * n,
-                       "l2": "inputs larger than L2: %.2f GB of pyramids per GPU, every pair reads its own frames"
-                             % (2 * n * 620e3 / 1e9),
-                       "multi_gpu": "contiguous shards of pairs, no collective on the alignment path, one NCCL gather "
-                                    "of 80 B/pair per step" if world > 1 else "single GPU"},
+            "config": config_dict(a),
+            "notes": {"pairs_total": world * n,
+                      "l2": "inputs larger than L2: %.2f GB of pyramids per GPU, every pair reads its own frames"
+                            % (2 * n * 620e3 / 1e9),
+                      "multi_gpu": "contiguous shards of pairs, no collective on the alignment path, one NCCL gather "
+                                   "of 80 B/pair per step" if world > 1 else "single GPU"},
             "us_per_pair": 1e6 / value,
             "latency_us_single_pair": lat_us,
             "evaluations_per_pair": evals_total / n,
-            "sigma_selections": sel_tiers,
+            "sigma_evaluations_by_tier": sel_tiers,
             "accuracy": {"median_rot_err_rad": float(np.median(rot_err)), "median_trans_err_m": float(np.median(tr_err)),
                          "pairs_within_1e-3rad_1e-2m": float(np.mean((rot_err < 1e-3) & (tr_err < 1e-2)))},
             "gpu_launches": int(launches),
@@ -385,9 +396,9 @@ def run_b200(a, rank, world):
                             "repack + pyramid kernels on the ingest streams, double-buffered slots) overlapped with the "
                             "previous step's alignment; svo_sparse_align_stage/h2d/launch/d2h/fetch (jobs + features "
                             "H2D, kernels, poses D2H)"},
-            "roofline": {"bound": "hbm", "kernel": "k_align_cluster", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
+            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "peak_source": peak_src, "traffic": traffic,
-                         "traffic_source": "profiles/traffic_k_align_cluster.json: dram__bytes_read+write of one 148-pair launch, scaled per pair" if traffic else None,
+                         "traffic_source": ("profiles/traffic_%s.json: dram__bytes_read+write of one 148-pair launch, scaled per pair" % kernel_name) if traffic else None,
                          "algorithmic_bytes_per_launch": alg_bytes, "sector_bytes_per_launch": sector_bytes,
                          "kernel_ms": kern_ms, "issue": issue,
                          "note": "sparse gather + exact order statistics: bound by integer issue and block barriers, not by HBM (DESIGN.md 4, profiles/)"},
@@ -414,6 +425,9 @@ def main():
     a = parse()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
+    a.scaling = "weak"
+    if a.total_pairs:
+        a.pairs, a.scaling = a.total_pairs // world, "strong"
     if a.impl == "reference":
         run_reference(a, rank)
     else:

@@ -2,7 +2,7 @@
 // (src/feature_selection.cpp:91-146): per grid cell the first (raster order) pixel with the largest
 // gradient magnitude, emitted in cell raster order iff magnitude > threshold and the cell is free.
 //
-// k_cell_argmax: one warp per cell.  Each lane scans a strided share of the cell and keeps the packed
+// k_cell_argmax: one warp per cell.  Each lane scans whole cell rows (aligned 32-bit loads) and keeps the packed
 //   key (value << 24) | (0xFFFFFF - index_in_cell); the maximum key is the largest value and, among
 //   ties, the smallest raster index -- exactly the strict `>` scan of the reference.  The warp maximum
 //   is one __reduce_max_sync.
@@ -23,14 +23,26 @@ __global__ void __launch_bounds__(128) k_cell_argmax(const uint8_t* __restrict__
     const int ch = (r + 1) * cell < h ? cell : h - r * cell;
     uint32_t key = 0;
     if (cw > 0 && ch > 0) {
+        // lane i takes cell rows i, i + 32, ...: the row segment is read as aligned 32-bit words (the pitched rows are
+        // padded to 16 bytes, so the last word of a row exists), no division and no byte load per pixel
         const uint8_t* base = grad + (long long)(r * cell) * pitch + c * cell;
-        const int n         = cw * ch;
-        for (int t = lane; t < n; t += 32) {
-            const int i      = t / cw;
-            const int j      = t - i * cw;
-            const uint32_t v = __ldg(base + (long long)i * pitch + j);
-            const uint32_t k = (v << 24) | (0xFFFFFFu - (uint32_t)t);
-            key              = max(key, k);
+        for (int i = lane; i < ch; i += 32) {
+            const uintptr_t ad  = reinterpret_cast<uintptr_t>(base + (long long)i * pitch);
+            const uint32_t* w4  = reinterpret_cast<const uint32_t*>(ad & ~uintptr_t(3));
+            const int off       = (int)(ad & 3u);
+            const int nwords    = (off + cw + 3) >> 2;
+            const uint32_t tidx = 0xFFFFFFu - (uint32_t)(i * cw) + (uint32_t)off;  // 0xFFFFFF - (i cw + j) for byte q 4 + k: minus (4 q + k)
+            for (int q = 0; q < nwords; q++) {
+                const uint32_t wv = __ldg(w4 + q);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int j = 4 * q + k - off;  // column inside the cell
+                    if (j >= 0 && j < cw) {
+                        const uint32_t v = (wv >> (8 * k)) & 0xffu;
+                        key              = max(key, (v << 24) | (tidx - (uint32_t)(4 * q + k)));
+                    }
+                }
+            }
         }
     }
     key = __reduce_max_sync(0xffffffffu, key);

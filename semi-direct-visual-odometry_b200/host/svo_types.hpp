@@ -128,3 +128,53 @@ struct Mat8 {
 };
 
 }  // namespace svo
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Adapters to the reference's real types, compiled in wherever their headers exist (the build image of this project has
+// none of them; tests/test_integration_compile.py compiles this block and INTEGRATION.md's bindings against minimal
+// stand-ins that carry the real signatures).  Frame::m_absPose is a Sophus::SE3d (include/frame.hpp:198), the pyramids
+// are std::vector<cv::Mat> (include/image_pyramid.hpp:147-148), FeatureAlignment::align takes an Eigen::Vector2d&
+// (include/feature_alignment.hpp:25).
+// ---------------------------------------------------------------------------------------------------------------------
+#if defined(__has_include)
+#if __has_include(<Eigen/Core>)
+#include <Eigen/Core>
+#define SVO_HAVE_EIGEN 1
+namespace svo {
+inline Vec2 fromEigen(const Eigen::Vector2d& v) { return Vec2(v.x(), v.y()); }
+inline Vec3 fromEigen(const Eigen::Vector3d& v) { return Vec3(v.x(), v.y(), v.z()); }
+inline Eigen::Vector2d toEigen(const Vec2& v) { return Eigen::Vector2d(v.x(), v.y()); }
+inline Eigen::Vector3d toEigen(const Vec3& v) { return Eigen::Vector3d(v.x(), v.y(), v.z()); }
+}  // namespace svo
+#endif
+#if __has_include(<sophus/se3.hpp>)
+#include <sophus/se3.hpp>
+#define SVO_HAVE_SOPHUS 1
+namespace svo {
+// Sophus::SE3d::params() is qx qy qz qw tx ty tz: the order of every pose in include/svo_b200.h
+inline SE3 fromSophus(const Sophus::SE3d& T)
+{
+    const auto p = T.params();
+    return SE3::fromParams(p.data());
+}
+inline Sophus::SE3d toSophus(const SE3& T)
+{
+    return Sophus::SE3d(Eigen::Quaterniond(T.q[3], T.q[0], T.q[1], T.q[2]), Eigen::Vector3d(T.t[0], T.t[1], T.t[2]));
+}
+}  // namespace svo
+#endif
+#if __has_include(<opencv2/core.hpp>)
+#include <opencv2/core.hpp>
+#define SVO_HAVE_OPENCV 1
+namespace svo {
+inline Mat8 fromCv(const cv::Mat& m)  // CV_8UC1, any row step
+{
+    Mat8 o(m.rows, m.cols);
+    for (int r = 0; r < m.rows; r++) std::memcpy(o.ptr(r), m.ptr<uint8_t>(r), (size_t)m.cols);
+    return o;
+}
+inline cv::Mat toCv(const Mat8& m) { return cv::Mat(m.rows, m.cols, CV_8UC1, (void*)m.ptr()).clone(); }
+}  // namespace svo
+#endif
+#endif
+

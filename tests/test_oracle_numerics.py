@@ -101,6 +101,87 @@ def test_ldlt_solve(orc):
     assert np.array_equal(orc.ldlt_solve(np.zeros((6, 6)), np.ones(6)), np.zeros(6))  # Eigen: zero pivots -> 0
 
 
+def test_se3_exp_adversarial_angles(orc):
+    """The contracts of Sophus::SE3d::exp the alignment leans on (ImageAlignment::update, src/image_alignment.cpp:372-380),
+    pinned against scipy.linalg.expm where closed forms lose digits: theta -> 0 (the series branch and its switch-over),
+    theta next to pi (sin theta / theta -> 0, the quaternion's real part -> 0), theta beyond pi (double cover) and a pure
+    translation.  The rotation must hold to 1e-12 everywhere.  V(omega) upsilon too, EXCEPT for the cancellation Sophus has
+    itself: above its series threshold (theta >= 1e-10) it evaluates (1 - cos theta) / theta^2 directly, which carries an
+    absolute error of eps / theta^2, i.e. eps |upsilon| / theta in the translation (5e-9 |upsilon| at theta = 1e-8).  The
+    oracle restates that formula, so the bound is part of the contract; the CUDA code uses half-angle forms that do not
+    cancel and sits inside the same bound (csrc/math.cuh)."""
+    from scipy.linalg import expm
+    from scipy.spatial.transform import Rotation
+    rng = np.random.default_rng(40)
+    axis = rng.normal(size=3)
+    axis /= np.linalg.norm(axis)
+    thetas = [0.0, 1e-300, 1e-160, 1e-20, 1e-11, 9.9e-11, 1.1e-10, 1e-9, 1e-8, 3e-8, 1e-6, 1e-4, 1e-2, 0.5, np.pi / 2, 3.0,
+              np.pi - 1e-6, np.pi - 1e-12, np.pi, np.pi + 1e-12, np.pi + 1e-6, 4.0, 2 * np.pi - 1e-9, 2 * np.pi, 7.5]
+    for th in thetas:
+        for ups in (np.zeros(3), rng.normal(size=3), 1e6 * rng.normal(size=3)):
+            xi = np.concatenate([ups, th * axis])
+            T = np.asarray(orc.se3_exp(xi))
+            w = xi[3:]
+            M = np.zeros((4, 4))
+            M[:3, :3] = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+            M[:3, 3] = ups
+            E = expm(M)
+            assert abs(np.linalg.norm(T[:4]) - 1.0) < 1e-14, th
+            assert np.abs(Rotation.from_quat(T[:4]).as_matrix() - E[:3, :3]).max() < 1e-12, th
+            cancel = 4 * np.finfo(float).eps / th if th >= 1e-10 else 0.0
+            assert np.abs(T[4:] - E[:3, 3]).max() <= (1e-12 + cancel) * max(1.0, np.abs(ups).max()), (th, T[4:], E[:3, 3])
+    # exp(xi) exp(-xi) = identity, also across the branch switch
+    for th in (1e-11, 1e-9, 0.3, np.pi - 1e-9):
+        xi = np.concatenate([rng.normal(size=3), th * axis])
+        I = np.asarray(orc.se3_mul(orc.se3_exp(xi), orc.se3_exp(-xi)))
+        assert np.abs(I[:3]).max() < 1e-15 and abs(abs(I[3]) - 1) < 1e-15 and np.abs(I[4:]).max() < 1e-12 + 8e-16 / th
+
+
+def test_ldlt_adversarial_systems(orc):
+    """Eigen::LDLT::solve as the optimisers call it (src/optimizer.cpp:96,306), restated with its symmetric pivoting on the
+    largest |diagonal| and its D^-1 rule.  Against numpy on the systems where pivoting and the zero-pivot rule matter:
+    the alignment's own badly scaled normal equations (rotation ~1e6 x translation), near-singular ones, an exactly
+    rank-deficient one (Eigen returns the minimum-effort solution with zeros for the null pivots: A x = b still holds on
+    the range), an indefinite one (LM with a rejected step can produce it) and permuted diagonals."""
+    rng = np.random.default_rng(41)
+    # badly scaled SPD, as J^T W J of the alignment: columns differ by 1e3, entries by 1e6
+    for trial in range(20):
+        S = np.diag(10.0 ** rng.uniform(-3, 3, 6))
+        A = rng.normal(size=(40, 6)) @ S
+        H = A.T @ A
+        b = A.T @ rng.normal(size=40)
+        x = np.asarray(orc.ldlt_solve(H, b))
+        xr = np.linalg.solve(H, b)
+        assert np.abs((x - xr) / np.maximum(np.abs(xr), 1e-300)).max() < 1e-6, trial
+        assert np.abs(H @ x - b).max() <= 1e-9 * np.abs(b).max()
+    # near-singular: condition 1e14 -- compare residuals, not solutions
+    U, _ = np.linalg.qr(rng.normal(size=(6, 6)))
+    H = U @ np.diag([1, 1e-2, 1e-5, 1e-8, 1e-11, 1e-14]) @ U.T
+    H = 0.5 * (H + H.T)
+    b = H @ rng.normal(size=6)
+    x = np.asarray(orc.ldlt_solve(H, b))
+    assert np.abs(H @ x - b).max() < 1e-12
+    # the largest diagonal is pivoted first: a matrix whose leading entry is tiny must not lose the solution
+    H = np.diag([1e-18, 3.0, 2.0, 5.0, 1.0, 4.0]) + 1e-3 * np.ones((6, 6))
+    b = rng.normal(size=6)
+    assert np.allclose(orc.ldlt_solve(H, b), np.linalg.solve(H, b), rtol=1e-9)
+    # exactly rank deficient (two features on one line): zeros for the null pivots, consistent on the range
+    B = rng.normal(size=(4, 6))
+    H = B.T @ B
+    b = H @ rng.normal(size=6)
+    x = np.asarray(orc.ldlt_solve(H, b))
+    assert np.isfinite(x).all() and np.abs(H @ x - b).max() < 1e-9 * max(1.0, np.abs(b).max())
+    # symmetric indefinite with a dominant diagonal: LDLT with diagonal pivoting still solves it
+    H = np.diag([4.0, -3.0, 5.0, -6.0, 2.0, 7.0]) + 0.1 * (lambda R: R + R.T)(rng.normal(size=(6, 6)))
+    b = rng.normal(size=6)
+    assert np.allclose(orc.ldlt_solve(H, b), np.linalg.solve(H, b), rtol=1e-8)
+    # 3 x 3 (FeatureAlignment's system) with a zero row / column: the reference's pseudo-inverse-like answer 0 there
+    H = np.array([[2.0, 0.5, 0.0], [0.5, 3.0, 0.0], [0.0, 0.0, 0.0]])
+    b = np.array([1.0, -2.0, 0.0])
+    x = np.asarray(orc.ldlt_solve(H, b))
+    assert x[2] == 0.0 and np.allclose(H[:2, :2] @ x[:2], b[:2])
+
+
 def _align(orc, pair, mode, **kw):
     rp, _ = orc.build_pyramid(pair["ref"], 4)
     cp, _ = orc.build_pyramid(pair["cur"], 4)
