@@ -68,7 +68,7 @@ def wall_time(fn, reps):
 
 def main():
     ap = argparse.ArgumentParser()
-    ap.add_argument("--configs", default="0,1,2,3,5,6,7,8")
+    ap.add_argument("--configs", default="0,1,2,3,5,6,7,8,9")
     ap.add_argument("--out", default=None)
     a = ap.parse_args()
     want = set(int(x) for x in a.configs.split(","))
@@ -396,6 +396,52 @@ def main():
                                        "sample": "the same frame through the oracle port (threshold scan, stable sort, SSC, bucketing), median of 3"}})
         pin.free()
         ctx.close()
+
+    # ---------------- config 9: rows a1 + a2 + a5 on a batch of frames ----------------
+    if 9 in want:
+        nb = 64
+        batch = synth.make_batch(nb, 500)
+        with torch.cuda.stream(stream):
+            with pkg.Context(w, h, K, levels=4, max_frames=nb, max_jobs=1, max_features=512, max_fa_items=16, stream=stream.cuda_stream) as c9:
+                c9.upload(0, batch["cur"])
+                c9.sync()
+                for _ in range(3):
+                    c9.rebuild(0, nb)
+                pyr_us = ev_time(torch, stream, lambda: c9.rebuild(0, nb), 20)
+                sel = [c9.select_grid(i, 30, 50) for i in range(nb)]
+
+                def sel_all():
+                    for i in range(nb):
+                        c9.select_grid(i, 30, 50)
+
+                sel_all()
+                sel_us = wall_time(sel_all, 5)
+                t0 = time.perf_counter()
+                same = True
+                for i in range(8):
+                    op = orc.unpack_pyramid(orc.build_pyramid(batch["cur"][i], 4)[1], w, h, 4)
+                    want_sel = orc.grid_select(op[0], 30, 50)
+                    same = same and np.array_equal(np.stack([sel[i]["x"], sel[i]["y"], sel[i]["magnitude"]], 1), want_sel)
+                cpu_us = (time.perf_counter() - t0) * 1e6 / 8
+        dims = [(w, h)]
+        for _ in range(3):
+            dims.append(((dims[-1][0] + 1) // 2, (dims[-1][1] + 1) // 2))
+        pyr_bytes = float(nb * (2 * w * h + 2 * sum(a_ * b_ for a_, b_ in dims[1:]) + sum(2 * a_ * b_ for a_, b_ in dims[1:3])))  # read L0, write G0 + both stacks; levels 1-2 re-read
+        emit({"config": {"workload": "rows a1 + a2: ImagePyramid::createImagePyramid (AbsGradientSaturatedSum + pyrDown of both stacks, 4 levels) of %d "
+                                     "resident 1241x376 frames (svo_frames_rebuild)" % nb},
+              "metric": "us_per_frame_pyramid", "unit": "us", "higher_is_better": False, "value": pyr_us / nb, "dtype": "u8",
+              "roofline": roof(pyr_bytes, pyr_us), "e2e": {"value": pyr_us / nb, "unit": "us", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                                                         "what": "device time of the three pyramid kernels over the batch (CUDA events), frames resident"},
+              "cpu_baseline": {"value": None, "unit": "us", "cores": 1, "kind": "port", "sample": "see the next line (pyramid + selection timed together)"}})
+        emit({"config": {"workload": "rows a4 + a5: FeatureSelection::gradientMagnitudeByValue (grid argmax, cell 30, threshold 50) on each of %d resident "
+                                     "frames, one svo_select_grid call per frame (as Frame by Frame in the reference)" % nb},
+              "metric": "us_per_frame_select_grid", "unit": "us", "higher_is_better": False, "value": sel_us / nb, "dtype": "u8",
+              "identical_to_oracle": bool(same),
+              "roofline": roof(float(nb * (w * h + 12 * 546)), sel_us),
+              "e2e": {"value": sel_us / nb, "unit": "us", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": int(12 * 546 + 16),
+                      "what": "svo_select_grid per frame: two kernels, features written zero-copy to mapped host memory, host wall clock"},
+              "cpu_baseline": {"value": cpu_us, "unit": "us", "cores": 1, "kind": "port",
+                               "sample": "oracle port on one host thread: pyramid (gradient + pyrDown x 2 stacks) + grid selection per frame, mean of 8 frames"}})
 
     # ---------------- config 3 ----------------
     if 3 in want:

@@ -30,8 +30,10 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __global__ void __launch_bounds__(NT) probe(const __grid_constant__ CUtensorMap tmap, const int* coords, uint8_t* out,
                                             long long* cycles, int variant)
 {
-    extern __shared__ __align__(1024) uint8_t smem[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     __shared__ __align__(8) unsigned long long bar;
+    // (the runtime only guarantees 16 bytes for the dynamic part: align by hand, the launch reserves 1 KB of slack)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     const int tid = threadIdx.x;
     if (tid == 0) {
         asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(&bar)), "r"(NT));
