@@ -208,3 +208,5 @@ bool sparse_align_v3_supported(const svo_ctx* ctx, int maxF);
 svo_status launch_sparse_align_v3(svo_ctx* ctx, int maxF);
 bool sparse_align_v4_supported(const svo_ctx* ctx, int maxF);
 svo_status launch_sparse_align_v4(svo_ctx* ctx, int maxF);
+bool sparse_align_v5_supported(const svo_ctx* ctx, int maxF);
+svo_status launch_sparse_align_v5(svo_ctx* ctx, int maxF);

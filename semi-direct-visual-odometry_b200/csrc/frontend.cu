@@ -109,8 +109,8 @@ svo_status frontend_enqueue(svo_ctx* ctx, const svo_frontend_params& p)
     ctx->staged_params     = p.align;
     // (<= 512 features: the single-CTA kernel, which owns no scratch memory; beyond: the cluster kernel, whose scratch
     // pointer is a captured argument -- frontend_invalidate_graphs drops the graphs whenever it is reallocated)
-    if (sparse_align_v4_supported(ctx, p.max_features))
-        rc = launch_sparse_align_v4(ctx, p.max_features);
+    if (sparse_align_v5_supported(ctx, p.max_features))
+        rc = launch_sparse_align_v5(ctx, p.max_features);
     else if (sparse_align_v3_supported(ctx, p.max_features))
         rc = launch_sparse_align_v3(ctx, p.max_features);
     else

@@ -165,6 +165,22 @@ __device__ __noinline__ void ldlt_solve(double* A, const double* b, double* x)
     for (int i = 0; i < N; i++) x[perm[i]] = y[i];
 }
 
+// 1 / d for a normal, finite d: hardware seed (about 20 bits) and three Newton steps, no special-case branch; the result is
+// within an ulp or two of the correctly rounded quotient.  On the serial path of the solver every cycle is paid by the whole
+// CTA waiting at a barrier.
+__device__ __forceinline__ double rcp_newton(double d)
+{
+    double x;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(x) : "d"(d));
+    double e = fma(-d, x, 1.0);
+    x        = fma(x, e, x);
+    e        = fma(-d, x, 1.0);
+    x        = fma(x, e, x);
+    e        = fma(-d, x, 1.0);
+    x        = fma(x, e, x);
+    return x;
+}
+
 // Fast path of the 6x6 solve: LDL^T without pivoting, fully unrolled so the whole factorisation lives in registers.
 // E: upper triangle of the symmetric matrix, row-major (21 values); diag_add is added to the diagonal (LM damping).
 // Returns false when a pivot is not safely positive (semi-definite / degenerate systems): the caller then falls back
@@ -200,7 +216,7 @@ __device__ __forceinline__ bool ldlt6_nopivot(const double* E, double diag_add, 
         }
         D[j]    = d;
         ok      = ok && (d > tiny);
-        invD[j] = 1.0 / d;
+        invD[j] = rcp_newton(d);  // (d > tiny > 0 is checked below; a failed check discards everything computed here)
 #pragma unroll
         for (int r = j + 1; r < 6; r++) {
             double sacc = A[r][j];

@@ -136,7 +136,7 @@ def _check_levels(stats, lv, synth, faithful):
 
 
 def _set_align_path(monkeypatch, name):
-    for k in ("SVO_ALIGN_GENERIC", "SVO_ALIGN_NT", "SVO_ALIGN_C", "SVO_ALIGN_V4"):
+    for k in ("SVO_ALIGN_GENERIC", "SVO_ALIGN_NT", "SVO_ALIGN_C", "SVO_ALIGN_V4", "SVO_S5_FORCE"):
         monkeypatch.delenv(k, raising=False)
     if name == "generic":
         monkeypatch.setenv("SVO_ALIGN_GENERIC", "1")
@@ -150,7 +150,7 @@ def _set_align_path(monkeypatch, name):
 
 @pytest.fixture(params=["fast", "cluster1", "cluster4", "cluster8", "generic"])
 def align_path(request, monkeypatch):
-    """The CUDA implementations of the alignment: the single-CTA kernel (sparse_align_v4.cu, what runs up to 512 features
+    """The CUDA implementations of the alignment: the single-CTA kernel (sparse_align_v5.cu, what runs up to 512 features
     per pair), the cluster kernel (sparse_align_v3.cu, what runs beyond) as one CTA and forced into thread-block clusters
     of 4 x 128 / 8 x 64 threads per pair (distributed shared memory exchange), and the generic kernel."""
     _set_align_path(monkeypatch, request.param)
@@ -589,8 +589,21 @@ def test_sparse_align_degenerate_residuals(pkg, orc, synth, pair_cache, monkeypa
         if faithful:
             assert synth.rotation_angle(res[0]["T_cur"], T) < 1e-4 and np.abs(res[0]["T_cur"][4:] - T[4:]).max() < 1e-3
             hot, cold, generic = _tiers(res[0])
-            if case in ("bright", "dark"):
+            if case in ("bright", "dark") and shape != "fast":
                 assert generic > 0, (hot, cold, generic)   # the tier under test really ran
+        if shape == "fast":
+            # the single-CTA kernel (select5.cuh): every selection tier forced in turn gives the SAME bits -- count passes only
+            # (no prediction), then the bisection safety net only
+            for force, want_tier in (("1", 1), ("2", 2)):
+                monkeypatch.setenv("SVO_S5_FORCE", force)
+                with _ctx(pkg, pair) as ctx:
+                    ctx.upload(0, np.stack([ref, cur]))
+                    rf, sf = ctx.sparse_align(_job(pkg, pair, 0, 0, 1, T_cur=T0), pair["feats"], mode=getattr(pkg.capi, mode),
+                                              max_iter=8)
+                monkeypatch.delenv("SVO_S5_FORCE")
+                assert np.array_equal(rf["T_cur"], res["T_cur"]) and np.array_equal(sf["sigma"], stats["sigma"]), (case, mode, force)
+                assert np.array_equal(sf["evaluations"], stats["evaluations"]) and np.array_equal(sf["pose_after"], stats["pose_after"])
+                assert _tiers(rf[0])[want_tier] > 0   # cold (force 1) / generic (force 2) really ran
 
 
 # ------------------------------------------------------------------------------------------------
