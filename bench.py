@@ -245,9 +245,12 @@ def run_b200(a, rank, world):
         sector_bytes = float((nvis * (32.0 * (PATCH + 3) + ev * 32.0 * (PATCH + 1))).sum() + 32.0 * batch["n_feat"].sum()
                              + 256.0 * LEVELS * n)
         evals_total = int(res["evaluations"].sum())
-        tiers = res["reserved"].astype(np.int64)  # diagnostics: evaluations whose robust scale came from the tier hot | cold << 8 |
-        sel_tiers = {"bracket": int(((tiers >> 24) & 0xff).sum()), "hot": int((tiers & 0xff).sum()),   # generic << 16 | bracket << 24
-                     "cold": int(((tiers >> 8) & 0xff).sum()), "generic": int(((tiers >> 16) & 0xff).sum())}
+        # diagnostics (select5.cuh): evaluations whose robust scale came from the predicted brackets alone (<< 24), from a
+        # prediction that needed count passes (low byte), from no prediction (<< 8: first evaluation of a level), from the
+        # bisection safety net (<< 16)
+        tiers = res["reserved"].astype(np.int64)
+        sel_tiers = {"predicted_brackets": int(((tiers >> 24) & 0xff).sum()), "predicted_plus_count_passes": int((tiers & 0xff).sum()),
+                     "no_prediction": int(((tiers >> 8) & 0xff).sum()), "bisection": int(((tiers >> 16) & 0xff).sum())}
 
         gather_buf = None
         if world > 1:
@@ -356,9 +359,9 @@ def run_b200(a, rank, world):
         ctx.close()
 
     traffic, issue = None, None  # DRAM bytes of the dominant kernel per launch, from the committed ncu --set full capture
-    kernel_name = "k_align_v4"
+    kernel_name = "k_align_v5"
     try:
-        kernel_name = "k_align_v4" if F <= 512 and os.environ.get("SVO_ALIGN_V4") != "0" else "k_align_cluster"
+        kernel_name = "k_align_v5" if F <= 512 and os.environ.get("SVO_ALIGN_V4") != "0" else "k_align_cluster"
         tj = json.load(open(os.path.join(ROOT, "profiles", "traffic_%s.json" % kernel_name)))
         if a.features == tj["features"] and a.mode == "gn":
             traffic = tj["dram_bytes_per_pair"] * n

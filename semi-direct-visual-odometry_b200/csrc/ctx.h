@@ -206,7 +206,5 @@ void frontend_invalidate_graphs(svo_ctx* ctx);  // destroys the captured front-e
 size_t sparse_align_smem_bytes(int nthreads, int max_features, int patch_area);
 bool sparse_align_v3_supported(const svo_ctx* ctx, int maxF);
 svo_status launch_sparse_align_v3(svo_ctx* ctx, int maxF);
-bool sparse_align_v4_supported(const svo_ctx* ctx, int maxF);
-svo_status launch_sparse_align_v4(svo_ctx* ctx, int maxF);
 bool sparse_align_v5_supported(const svo_ctx* ctx, int maxF);
 svo_status launch_sparse_align_v5(svo_ctx* ctx, int maxF);

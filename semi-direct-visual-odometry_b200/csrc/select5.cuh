@@ -286,7 +286,7 @@ __device__ __forceinline__ bool s5_sigma(const float (&rs)[AREA], bool vis, int 
             if (!ovf && CM <= kLow && k < CM + nM) {
                 float hi, lw;
                 s5_rank<NT>(sm, n, k - CM + Lb, needPred, &hi, &lw);
-                result0    = needPred ? (float)(0.5 * ((double)hi + (double)lw)) : hi;
+                result0    = needPred ? fmaf(0.5f, hi, 0.5f * lw) : hi;
                 pr.rho[0]  = __fdividef((float)max(nM, 1u), wM);
                 phaseStart = 1;
                 center     = result0;
@@ -302,7 +302,7 @@ __device__ __forceinline__ bool s5_sigma(const float (&rs)[AREA], bool vis, int 
                     s5_rank<NT>(sm, n, k - CI, needPred, &hi, &lw);
                     const float mgn = 2.f + 1.0e-6f * (dA + wD0);
                     if (lw >= dA + mgn && hi < dA + wD0 - mgn) {  // the proof (see above)
-                        result1    = needPred ? (float)(0.5 * ((double)hi + (double)lw)) : hi;
+                        result1    = needPred ? fmaf(0.5f, hi, 0.5f * lw) : hi;
                         pr.rho[1]  = __fdividef((float)max(nD, 1u), wD);
                         phaseStart = 2;
                     }
@@ -449,7 +449,7 @@ __device__ __forceinline__ bool s5_sigma(const float (&rs)[AREA], bool vis, int 
                 if (inside && n <= (uint32_t)CAP && !ovf) {
                     float hi, lw;
                     s5_rank<NT>(sm, n, k - C0, needPred, &hi, &lw);
-                    found  = needPred ? (float)(0.5 * ((double)hi + (double)lw)) : hi;
+                    found  = needPred ? fmaf(0.5f, hi, 0.5f * lw) : hi;
                     rhoNew = __fdividef((float)max(n, 1u), W);
                     done   = true;
                     S5_T(1);
@@ -538,7 +538,7 @@ __device__ __forceinline__ bool s5_sigma(const float (&rs)[AREA], bool vis, int 
             }
             const float hi = s5_unord(T);
             const float lw = (needPred && lessT > kLow) ? s5_unord(maxBelow) : hi;  // (lessT <= k - 1: element k - 1 equals element k)
-            found  = needPred ? (float)(0.5 * ((double)hi + (double)lw)) : hi;
+            found  = needPred ? fmaf(0.5f, hi, 0.5f * lw) : hi;
             rhoNew = 0.f;
             S5_T(11);
         }

@@ -729,7 +729,6 @@ svo_status launch_sparse_align(svo_ctx* ctx)
         const char* e = getenv("SVO_ALIGN_GENERIC");
         const char* v = getenv("SVO_ALIGN_V4");  // "0": keep the cluster kernel for <= 512 features too (A/B measurements)
         if (!(e && e[0] == '1')) {
-            if (v && v[0] == '4' && sparse_align_v4_supported(ctx, maxF)) return launch_sparse_align_v4(ctx, maxF);  // (A/B: the previous single-CTA kernel)
             if (!(v && v[0] == '0') && sparse_align_v5_supported(ctx, maxF)) return launch_sparse_align_v5(ctx, maxF);
             if (sparse_align_v3_supported(ctx, maxF)) return launch_sparse_align_v3(ctx, maxF);
         }

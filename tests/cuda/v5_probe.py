@@ -1,5 +1,5 @@
-"""A/B probe of the single-CTA alignment kernel (sparse_align_v5.cu, select5.cuh) against its predecessor
-(sparse_align_v4.cu, SVO_ALIGN_V4=4) and the oracle, with every selection tier forced in turn (SVO_S5_FORCE): level stats,
+"""A/B probe of the single-CTA alignment kernel (sparse_align_v5.cu, select5.cuh) against the cluster kernel
+(sparse_align_v3.cu, SVO_ALIGN_V4=0) and the oracle, with every selection tier forced in turn (SVO_S5_FORCE): level stats,
 evaluation counts, the sigma trace of job 0, single-pair latency and one-wave / batch throughput.
 
     python tests/cuda/v5_probe.py [n_pairs_for_timing]
@@ -19,7 +19,7 @@ import oracle as orc
 
 
 def run(ctx, jobs, feats, v4, mode, force=0, **kw):
-    os.environ["SVO_ALIGN_V4"] = "1" if v4 else "4"   # (v4=True: the kernel under test, v5)
+    os.environ["SVO_ALIGN_V4"] = "1" if v4 else "0"   # (v4=True: the kernel under test, v5; else the cluster kernel)
     os.environ["SVO_S5_FORCE"] = str(force)
     res, st = ctx.sparse_align(jobs, feats, mode=mode, max_iter=30, **kw)
     dbg = ctx.debug_cycles().reshape(-1).copy()
@@ -60,23 +60,23 @@ def main():
                     ok_all = ok_all and same
                 rmse, T, status, lv = orc.sparse_align(rp, rp, cp, pair["w"], pair["h"], pair["feats"], pair["n_ref"], 0, pair["T_ref"],
                                                        pair["T_kf"], pair["K"], pair["T_cur_init"], patch_size=5, mode=mode, max_iter=30)
-                print("--- features %d pair %d mode %d: evals v4 %d v5 %d oracle %d; tiers v4 %s v5 %s" % (
+                print("--- features %d pair %d mode %d: evals v3 %d v5 %d oracle %d; tiers v3 %s v5 %s" % (
                     nfeat, idx, mode, r3[0]["evaluations"], r4[0]["evaluations"], sum(l["evaluations"] for l in lv),
                     hex(r3[0]["reserved"]), hex(r4[0]["reserved"])))
                 for s in range(4):
                     a, b, o = s3[0, s], s4[0, s], lv[s]
                     hrel = np.abs(b["H"] - o["H"]).max() / np.abs(o["H"]).max()
-                    print("  level %d: sigma v4 %.9f v5 %.9f orc %.9f | n_px %d %d %d | evals %d %d %d | status %d %d %d | H rel(v5,orc) %.1e | "
+                    print("  level %d: sigma v3 %.9f v5 %.9f orc %.9f | n_px %d %d %d | evals %d %d %d | status %d %d %d | H rel(v5,orc) %.1e | "
                           "dpose(v5,orc) %.1e" % (s, a["sigma"], b["sigma"], o["sigma"], a["n_px"], b["n_px"], o["n_px"], a["evaluations"],
                                                   b["evaluations"], o["evaluations"], a["status"], b["status"], o["status"], hrel,
                                                   np.abs(b["pose_after"] - o["pose_after"]).max()))
                     if abs(a["sigma"] - b["sigma"]) > 2e-6 * b["sigma"] or a["n_px"] != b["n_px"] or b["evaluations"] != o["evaluations"]:
                         ok_all = False
                 dT = np.abs(r4[0]["T_cur"] - T)
-                print("  final |dT| v5-orc %.2e, v4-orc %.2e" % (dT.max(), np.abs(r3[0]["T_cur"] - T).max()))
+                print("  final |dT| v5-orc %.2e, v3-orc %.2e" % (dT.max(), np.abs(r3[0]["T_cur"] - T).max()))
                 if mode == 2:
                     print("  sigma trace v5 (sigma, tiers miss|cold<<8|generic<<16|hit<<24, attempts, n):", [("%.6f" % s, hex(t), hex(w), n) for s, t, w, n in trace(d4)])
-    print("A/B", "sigma within 2e-6 of v4, n_px / evaluation counts identical, forced tiers bit-identical" if ok_all else "DIFFERENCES (see above)")
+    print("A/B", "sigma within 2e-6 of v3, n_px / evaluation counts identical, forced tiers bit-identical" if ok_all else "DIFFERENCES (see above)")
 
     # ---- timing: single pair and a batch ----
     import torch
@@ -92,7 +92,7 @@ def main():
         jobs["n_ref"], jobs["n_kf"], jobs["feat_offset"] = batch["n_feat"], 0, batch["feat_offset"]
         jobs["T_ref"], jobs["T_kf"], jobs["T_cur"] = ident, ident, ident
         for v4 in (False, True):
-            os.environ["SVO_ALIGN_V4"] = "1" if v4 else "4"
+            os.environ["SVO_ALIGN_V4"] = "1" if v4 else "0"
             os.environ["SVO_S5_FORCE"] = "0"
             for label, jj, ff in (("single", jobs[:1], batch["feats"][:int(batch["n_feat"][0])]), ("batch %d" % n, jobs, batch["feats"])):
                 ctx.sparse_align_stage(jj, ff, patch_size=5, min_level=0, max_level=3, mode=2, max_iter=30)
@@ -110,7 +110,7 @@ def main():
                 res = ctx.sparse_align_fetch()[0]
                 tiers = res["reserved"].astype(np.int64)
                 print("%s %s: %.1f us per launch, evals/pair %.2f, tiers hit/bracket %d miss/hot %d cold %d generic %d" % (
-                    "v5" if v4 else "v4", label, dt * 1e6, res["evaluations"].mean(), ((tiers >> 24) & 0xff).sum(), (tiers & 0xff).sum(),
+                    "v5" if v4 else "v3", label, dt * 1e6, res["evaluations"].mean(), ((tiers >> 24) & 0xff).sum(), (tiers & 0xff).sum(),
                     ((tiers >> 8) & 0xff).sum(), ((tiers >> 16) & 0xff).sum()))
             rot = np.array([synth.rotation_angle(res[i]["T_cur"], batch["T_true"][i]) for i in range(n)])
             print("   median rot err %.2e" % np.median(rot))
