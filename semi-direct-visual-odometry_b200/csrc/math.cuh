@@ -181,6 +181,92 @@ __device__ __forceinline__ double rcp_newton(double d)
     return x;
 }
 
+// 1 / sqrt(x) for a normal, finite x > 0: hardware seed and three Newton steps (see rcp_newton)
+__device__ __forceinline__ double rsqrt_newton(double x)
+{
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+        const double e = fma(-x * r, r, 1.0);
+        r              = fma(0.5 * r, e, r);
+    }
+    return r;
+}
+
+// sin and cos of |x| <= 0.5 by their Taylor polynomials (next terms 2e-20 / 7e-19): the half angle of a Gauss-Newton step
+// never leaves that range; sincos() beyond it
+__device__ __forceinline__ void sincos_small(double x, double* s, double* c)
+{
+    if (fabs(x) > 0.5) {
+        sincos(x, s, c);
+        return;
+    }
+    const double z = x * x;
+    double ps = -1.0 / 1307674368000.0;
+    ps        = fma(ps, z, 1.0 / 6227020800.0);
+    ps        = fma(ps, z, -1.0 / 39916800.0);
+    ps        = fma(ps, z, 1.0 / 362880.0);
+    ps        = fma(ps, z, -1.0 / 5040.0);
+    ps        = fma(ps, z, 1.0 / 120.0);
+    ps        = fma(ps, z, -1.0 / 6.0);
+    *s        = fma(x * z, ps, x);
+    double pc = -1.0 / 87178291200.0;
+    pc        = fma(pc, z, 1.0 / 479001600.0);
+    pc        = fma(pc, z, -1.0 / 3628800.0);
+    pc        = fma(pc, z, 1.0 / 40320.0);
+    pc        = fma(pc, z, -1.0 / 720.0);
+    pc        = fma(pc, z, 1.0 / 24.0);
+    pc        = fma(pc, z, -0.5);
+    *c        = fma(z, pc, 1.0);
+}
+
+// pose_update_right_exp_neg for the single-CTA kernel, where every cycle of it is paid by 511 waiting threads: inlined (no
+// stack traffic), reciprocal square roots by Newton steps, polynomial sin / cos.  Same formulas, results within a few ulp.
+__device__ __forceinline__ void pose_update_right_exp_neg_fast(Pose& p, const double dx[6])
+{
+    const double ups[3] = {-dx[0], -dx[1], -dx[2]};
+    const double om[3]  = {-dx[3], -dx[4], -dx[5]};
+    const double th2 = om[0] * om[0] + om[1] * om[1] + om[2] * om[2];
+    double imag, real, a, b;
+    if (th2 < 1e-20) {
+        const double th4 = th2 * th2;
+        imag = 0.5 - th2 / 48.0 + th4 / 3840.0;
+        real = 1.0 - th2 / 8.0 + th4 / 384.0;
+        a    = 0.5;
+        b    = 1.0 / 6.0;
+    } else {
+        const double r  = rsqrt_newton(th2), th = th2 * r, r2 = r * r;
+        double sh, ch;
+        sincos_small(0.5 * th, &sh, &ch);
+        imag           = sh * r;
+        real           = ch;
+        const double s = 2.0 * sh * ch;       // sin th
+        a              = 2.0 * sh * sh * r2;  // (1 - cos th) / th^2
+        b              = (th - s) * r2 * r;
+    }
+    const double eq[4] = {imag * om[0], imag * om[1], imag * om[2], real};
+    double c1[3], c2[3], et[3];
+    cross3(om, ups, c1);
+    cross3(om, c1, c2);
+#pragma unroll
+    for (int i = 0; i < 3; i++) et[i] = ups[i] + a * c1[i] + b * c2[i];
+    double rt[3];
+    quat_rotate(p.q, et, rt);
+#pragma unroll
+    for (int i = 0; i < 3; i++) p.t[i] += rt[i];
+    const double ax = p.q[0], ay = p.q[1], az = p.q[2], aw = p.q[3];
+    double q[4];
+    q[0] = aw * eq[0] + ax * eq[3] + ay * eq[2] - az * eq[1];
+    q[1] = aw * eq[1] + ay * eq[3] + az * eq[0] - ax * eq[2];
+    q[2] = aw * eq[2] + az * eq[3] + ax * eq[1] - ay * eq[0];
+    q[3] = aw * eq[3] - ax * eq[0] - ay * eq[1] - az * eq[2];
+    const double n2   = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+    const double ninv = fabs(n2 - 1.0) < 1e-9 ? fma(-0.5, n2, 1.5) : rsqrt_newton(n2);  // (first-order: its error is 3/8 (n2 - 1)^2)
+#pragma unroll
+    for (int i = 0; i < 4; i++) p.q[i] = q[i] * ninv;
+}
+
 // Fast path of the 6x6 solve: LDL^T without pivoting, fully unrolled so the whole factorisation lives in registers.
 // E: upper triangle of the symmetric matrix, row-major (21 values); diag_add is added to the diagonal (LM damping).
 // Returns false when a pivot is not safely positive (semi-definite / degenerate systems): the caller then falls back

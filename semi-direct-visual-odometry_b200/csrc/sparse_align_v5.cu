@@ -65,6 +65,17 @@ __device__ __forceinline__ void load8(const uint8_t* p, uint32_t& lo, uint32_t& 
     hi = __funnelshift_r(a1, a2, s4 * 8u);
 }
 
+// dx = (H + diag_add I)^-1 g, E = (21 H upper triangle, 6 g) in shared memory: copied to registers, register-resident LDLT,
+// pivoted Eigen-rule fallback (out of line) for semi-definite systems
+__device__ __forceinline__ void solve6_inline(const double* E, double diag_add, double* dx)
+{
+    double e[27];
+#pragma unroll
+    for (int i = 0; i < 27; i++) e[i] = E[i];
+    if (svo::ldlt6_nopivot(e, diag_add, e + 21, dx)) return;
+    solve6(E, diag_add, dx);
+}
+
 template <int P, int NT>
 __host__ __device__ constexpr size_t v5_smem_bytes()
 {
@@ -500,7 +511,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_align_v5(const V5Args a)
                         if (ctrl->first) ctrl->first_sigma = ctrl->sigma;
                         const bool wasFirst = ctrl->first;
                         record_first(ctrl->E, chi2, 0.0, ctrl->n_eval);
-                        solve6(ctrl->E, 0.0, dx);
+                        solve6_inline(ctrl->E, 0.0, dx);
                         if (wasFirst && statsOut)
                             for (int i = 0; i < 6; i++) statsOut[(size_t)job * nLevels + si].dx[i] = dx[i];
                         ctrl->iters_level++;
@@ -525,7 +536,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_align_v5(const V5Args a)
                             ctrl->preChi2  = chi2;
                             double step    = 0;
                             for (int i = 0; i < 6; i++) step += dx[i] * dx[i];
-                            svo::pose_update_right_exp_neg(ctrl->pose, dx);
+                            svo::pose_update_right_exp_neg_fast(ctrl->pose, dx);
                             if (step < 1e-16 || chi2 < 1e-1) {
                                 int st = ctrl->status;
                                 st     = step < 1e-16 ? SVO_ST_SMALL_STEP : st;
@@ -572,10 +583,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_align_v5(const V5Args a)
                             const double lambda = ctrl->lambda;
                             const bool wasFirst = ctrl->first;
                             record_first(ctrl->curE, ctrl->curE[27], lambda, ctrl->cur_n);
-                            solve6(ctrl->curE, lambda, dx);
+                            solve6_inline(ctrl->curE, lambda, dx);
                             if (wasFirst && statsOut)
                                 for (int i = 0; i < 6; i++) statsOut[(size_t)job * nLevels + si].dx[i] = dx[i];
-                            svo::pose_update_right_exp_neg(ctrl->pose, dx);  // :310 applied before any check
+                            svo::pose_update_right_exp_neg_fast(ctrl->pose, dx);  // :310 applied before any check
                             ctrl->iters_level++;
                             double mx = dx[0], step = 0;
                             bool nan = false;
