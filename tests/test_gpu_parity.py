@@ -487,6 +487,43 @@ def test_sparse_align_repeatable_bitwise(pkg, synth, monkeypatch, shape):
     assert np.median(rot) < 1e-4 and (rot < 1e-3).all()
 
 
+@pytest.mark.parametrize("n_features", [37, 120, 257, 500])
+@pytest.mark.parametrize("mode", ["GN", "LM_ITERATED"])
+def test_selection_tiers_agree_bitwise_on_a_batch(pkg, synth, monkeypatch, n_features, mode):
+    """The robust scale of the single-CTA kernel (select5.cuh) reaches its result through predicted brackets (one fused pass),
+    count passes or the bisection safety net, depending on what the previous evaluation predicts.  All routes select the same
+    order statistics of the same floats: 24 pairs x every CTA width (64 .. 512 threads) x two iterated modes, forced through
+    each route in turn, must give the SAME BITS -- poses, rmse, evaluation counts, status.  (Each route against the oracle:
+    test_sparse_align_degenerate_residuals and the parity tests above.)"""
+    _set_align_path(monkeypatch, "fast")
+    n = 24
+    batch = synth.make_batch(n, n_features)
+    capi = pkg.capi
+    with pkg.Context(batch["w"], batch["h"], batch["K"], levels=4, max_frames=2 * n, max_jobs=n, max_features=512,
+                     max_fa_items=16) as ctx:
+        ctx.upload(0, batch["ref"])
+        ctx.upload(n, batch["cur"])
+        jobs = capi.make_jobs(n)
+        ident = np.array([0, 0, 0, 1, 0, 0, 0], dtype=np.float64)
+        jobs["ref_slot"], jobs["kf_slot"], jobs["cur_slot"] = np.arange(n), np.arange(n), np.arange(n) + n
+        jobs["n_ref"], jobs["n_kf"], jobs["feat_offset"] = batch["n_feat"], 0, batch["feat_offset"]
+        jobs["T_ref"], jobs["T_kf"], jobs["T_cur"] = ident, ident, ident
+        runs = {}
+        for force in ("0", "1", "2"):
+            monkeypatch.setenv("SVO_S5_FORCE", force)
+            runs[force] = ctx.sparse_align(jobs, batch["feats"], mode=getattr(capi, mode), max_iter=12, want_stats=False)[0]
+        monkeypatch.delenv("SVO_S5_FORCE")
+    base = runs["0"]
+    for force in ("1", "2"):
+        r = runs[force]
+        assert np.array_equal(r["T_cur"], base["T_cur"]) and np.array_equal(r["rmse"], base["rmse"], equal_nan=True), force   # (rmse is 0 / 0 when a level sees no feature)
+        assert np.array_equal(r["evaluations"], base["evaluations"]) and np.array_equal(r["status"], base["status"]), force
+    t = base["reserved"].astype(np.int64)
+    assert ((t >> 24) & 0xff).sum() > 0 and ((t >> 8) & 0xff).sum() > 0       # predicted brackets and cold starts both ran
+    t2 = runs["2"]["reserved"].astype(np.int64)   # bisection only (evaluations that see no feature select nothing)
+    assert ((t2 >> 16) & 0xff).sum() > 0 and ((t2 & 0xffff) == 0).all() and ((t2 >> 24) == 0).all()
+
+
 # ------------------------------------------------------------------------------------------------
 # epipolar search of the depth filter (SURVEY 8f row f3): algorithm::matchEpipolarConstraint
 # ------------------------------------------------------------------------------------------------
