@@ -293,8 +293,10 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_align_v5(const V5Args a)
         __syncthreads();  // ctrl init visible
         pred.haveMove = false;  // the deviation changes with the level: no hot attempt at its first evaluation
 
-        // current-image window of this feature: FW rows x 8 bytes starting at column wx, row wy
-        uint32_t winLo[G::FW], winHi[G::FW];
+        // current-image window of this feature: FW + 1 rows x 8 bytes starting at column wx, row wy -- one column of slack on
+        // either side and one row: a warp re-fetches (an L2 round trip for all its lanes) only when one of its features moves
+        // by more than about half a pixel from where its window was loaded, not at every integer crossing
+        uint32_t winLo[G::FW + 1], winHi[G::FW + 1];
         int wx = 0, wy = 0;
         bool winValid = false;
 
@@ -344,21 +346,23 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_align_v5(const V5Args a)
             float rs[G::AREA];
             if (vis) {
                 const int x0 = uI + G::PB, y0 = vI + G::PB;  // footprint origin
-                if (!winValid || y0 != wy || x0 < wx || x0 + G::FW > wx + 8) {
+                if (!winValid || (y0 != wy && y0 != wy + 1) || x0 < wx || x0 + G::FW > wx + 8) {
                     wx       = x0 - 1;
-                    wy       = y0;
+                    wy       = fv >= 0.5f ? y0 : y0 - 1;  // (the spare row on the side the feature is closer to; both are inside the image)
                     winValid = true;
 #pragma unroll
-                    for (int r = 0; r < G::FW; r++) load8(curImg + (long long)(wy + r) * lpitch + wx, winLo[r], winHi[r]);
+                    for (int r = 0; r <= G::FW; r++) load8(curImg + (long long)(wy + r) * lpitch + wx, winLo[r], winHi[r]);
                 }
+                const bool down = y0 != wy;  // the footprint starts at window row 1
                 const uint32_t off = (uint32_t)(x0 - wx);  // 0 .. 8 - FW
                 const float wu0 = 1.f - fu;
                 const float wv0s = (1.f - fv) * 65536.f, fvs = fv * 65536.f;  // vertical weights x 2^16 (exact scaling)
                 float prevRow[P];
 #pragma unroll
                 for (int r = 0; r < G::FW; r++) {
-                    const uint32_t lo = __funnelshift_r(winLo[r], winHi[r], off * 8u);
-                    const uint32_t hi = winHi[r] >> (off * 8u);
+                    const uint32_t rl = down ? winLo[r + 1] : winLo[r], rh = down ? winHi[r + 1] : winHi[r];
+                    const uint32_t lo = __funnelshift_r(rl, rh, off * 8u);
+                    const uint32_t hi = rh >> (off * 8u);
                     float px[G::FW];
 #pragma unroll
                     for (int c = 0; c < G::FW; c++)  // byte -> float without the conversion pipe: 0x4B0000bb is 2^23 + bb

@@ -3,7 +3,7 @@
 //   * the shared-memory layout such a box gets under CU_TENSOR_MAP_SWIZZLE_128B vs SWIZZLE_NONE
 //   * zero fill of out-of-bounds coordinates
 //   * issue -> completion latency for 512 boxes
-// build: nvcc -gencode arch=compute_100a,code=sm_100a -o tma_probe tma_probe.cu
+// build: nvcc -gencode arch=compute_100a,code=sm_100a --cudart=shared -lcuda -o tma_probe tma_probe.cu
 #include <cuda.h>
 #include <cuda_runtime.h>
 
