@@ -399,15 +399,17 @@ def main():
 
     # ---------------- config 9: rows a1 + a2 + a5 on a batch of frames ----------------
     if 9 in want:
-        nb = 64
+        nb = 64          # distinct frames (the selection line works on these)
+        npyr = 1024      # resident frames of the pyramid line: the batch size of the headline workload
         batch = synth.make_batch(nb, 500)
         with torch.cuda.stream(stream):
-            with pkg.Context(w, h, K, levels=4, max_frames=nb, max_jobs=1, max_features=512, max_fa_items=16, stream=stream.cuda_stream) as c9:
-                c9.upload(0, batch["cur"])
+            with pkg.Context(w, h, K, levels=4, max_frames=npyr, max_jobs=1, max_features=512, max_fa_items=16, stream=stream.cuda_stream) as c9:
+                for i0 in range(0, npyr, nb):
+                    c9.upload(i0, batch["cur"])
                 c9.sync()
                 for _ in range(3):
-                    c9.rebuild(0, nb)
-                pyr_us = ev_time(torch, stream, lambda: c9.rebuild(0, nb), 20)
+                    c9.rebuild(0, npyr)
+                pyr_us = ev_time(torch, stream, lambda: c9.rebuild(0, npyr), 10)
                 sel = [c9.select_grid(i, 30, 50) for i in range(nb)]
 
                 def sel_all():
@@ -426,12 +428,13 @@ def main():
         dims = [(w, h)]
         for _ in range(3):
             dims.append(((dims[-1][0] + 1) // 2, (dims[-1][1] + 1) // 2))
-        pyr_bytes = float(nb * (2 * w * h + 2 * sum(a_ * b_ for a_, b_ in dims[1:]) + sum(2 * a_ * b_ for a_, b_ in dims[1:3])))  # read L0, write G0 + both stacks; levels 1-2 re-read
+        pyr_bytes = float(npyr * (2 * w * h + 2 * sum(a_ * b_ for a_, b_ in dims[1:]) + sum(2 * a_ * b_ for a_, b_ in dims[1:3])))  # read L0, write G0 + both stacks; levels 1-2 re-read
         emit({"config": {"workload": "rows a1 + a2: ImagePyramid::createImagePyramid (AbsGradientSaturatedSum + pyrDown of both stacks, 4 levels) of %d "
-                                     "resident 1241x376 frames (svo_frames_rebuild)" % nb},
-              "metric": "us_per_frame_pyramid", "unit": "us", "higher_is_better": False, "value": pyr_us / nb, "dtype": "u8",
-              "roofline": roof(pyr_bytes, pyr_us), "e2e": {"value": pyr_us / nb, "unit": "us", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
-                                                         "what": "device time of the three pyramid kernels over the batch (CUDA events), frames resident"},
+                                     "resident 1241x376 frames (svo_frames_rebuild)" % npyr},
+              "metric": "us_per_frame_pyramid", "unit": "us", "higher_is_better": False, "value": pyr_us / npyr, "dtype": "u8",
+              "roofline": dict(roof(pyr_bytes, pyr_us), note="instruction-bound u8 stencil (DESIGN.md 4): ~66 instructions per lane and source row for both stacks"),
+              "e2e": {"value": pyr_us / npyr, "unit": "us", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0,
+                                                         "what": "device time of the pyramid kernels over the batch (k_pyr_march: level 0 -> 1 with the gradient fused, then one launch pair per level; CUDA events), frames resident"},
               "cpu_baseline": {"value": None, "unit": "us", "cores": 1, "kind": "port", "sample": "see the next line (pyramid + selection timed together)"}})
         emit({"config": {"workload": "rows a4 + a5: FeatureSelection::gradientMagnitudeByValue (grid argmax, cell 30, threshold 50) on each of %d resident "
                                      "frames, one svo_select_grid call per frame (as Frame by Frame in the reference)" % nb},

@@ -6,6 +6,10 @@
 // Both kernels are HBM-bound integer stencils: every input byte is read once from DRAM (row reuse
 // is served by L1/L2), every output byte written once.  Rows are padded to 16 B so 32-bit and
 // 128-bit accesses are aligned.
+#include <algorithm>
+#include <type_traits>
+#include <stdlib.h>
+
 #include "ctx.h"
 
 namespace {
@@ -283,6 +287,179 @@ __global__ void __launch_bounds__(256) k_pyr_level(const uint8_t* __restrict__ s
     }
 }
 
+// ------------------------------------------------------------------------------------------------------------
+// cv::pyrDown of both stacks for BATCHES of frames, register-marching: a warp owns a strip of 32 source words (128
+// columns, 2 words of overlap on either side: the inner 28 words give 56 output columns) and walks down the rows of its
+// row segment.  Per source row and lane: one coalesced 32-bit load per stack, the neighbour words by shuffle, the
+// horizontal [1 4 6 4 1] of the lane's two outputs as three dp4a; the last four rows of horizontal sums stay in
+// registers (two 16-bit lanes per register), every second row emits one output row: (sum + 128) >> 8, two bytes per lane,
+// paired by shuffle into 32-bit stores.  No shared memory, no barrier, no index arithmetic beyond a row pointer.
+// BORDER_REFLECT_101: rows by mapping the row index, columns by one byte permute whose selector depends on the lane only.
+// The tile kernel above needs ~760 instructions per thread and tile (index arithmetic of five staged loops); this one ~30
+// per lane and source row for both stacks.  grid: (strips, row segments / 4, frames), block (32, 4).
+// ------------------------------------------------------------------------------------------------------------
+constexpr int PM_INNER = 28;   // inner words of a strip
+
+__device__ __forceinline__ uint32_t pm_hsum(uint32_t wl, uint32_t w, uint32_t wr)
+{
+    const uint32_t h0 = __dp4a(wl, 0x04010000u, __dp4a(w, 0x00010406u, 0u));  // centre = byte 0 of w
+    const uint32_t h1 = __dp4a(w, 0x04060401u, wr & 0xffu);                    // centre = byte 2 of w
+    return h0 | (h1 << 16);
+}
+
+// BASE (level 0 -> 1): reads ONLY the level-0 image; the gradient (Simd::AbsGradientSaturatedSum) of every row is computed
+// in registers from three image rows, written out as gradient level 0 by the lane that owns the word, and decimated with
+// the image.  Rows and columns beyond the image follow BORDER_REFLECT_101 of the GRADIENT image (whose first / last row and
+// column are 0): walking virtual rows over the reflected image reproduces it, except for those zeros, which are forced.
+// EDGE: the strips that hold the first columns (strip 0) or columns beyond the image (from strip `edge0` on) apply the column
+// reflection; the strips in between (launched separately: nothing but the blockIdx differs) carry none of that code.  A CTA is
+// ONE warp and every loop bound derives from blockIdx: the compiler sees warp-uniform control flow around the shuffles.
+template <bool BASE, bool EDGE>
+__global__ void __launch_bounds__(32) k_pyr_march(const uint8_t* __restrict__ src_img, const uint8_t* __restrict__ src_grad,
+                                                  uint8_t* __restrict__ dst_img, uint8_t* __restrict__ dst_grad,
+                                                  uint8_t* __restrict__ grad0, int sw, int sh, int spitch, long long sstride,
+                                                  int dw, int dh, int dpitch, long long dstride, int edge0, int rows)
+{
+    constexpr unsigned FULL = 0xffffffffu;
+    const int lane = threadIdx.x, frame = blockIdx.z;
+    const int strip = EDGE ? (blockIdx.x == 0 ? 0 : edge0 + (int)blockIdx.x - 1) : 1 + (int)blockIdx.x;
+    const int wi    = strip * PM_INNER - 2 + lane;  // source word of this lane (columns 4 wi .. 4 wi + 3)
+    const int oy0   = blockIdx.y * rows;
+    const int oy1   = min(oy0 + rows, dh);
+    const uint8_t* sI = src_img + (long long)frame * sstride;
+    const uint8_t* sG = BASE ? nullptr : src_grad + (long long)frame * sstride;
+    const bool ld     = wi >= 0 && 4 * wi < spitch;
+    const bool inner  = lane >= 2 && lane < 2 + PM_INNER;
+    // column reflection: byte k of this lane's word is column c = 4 wi + k; columns sw, sw + 1 (the only ones beyond the image
+    // a tap can reach) are columns sw - 2, sw - 3, which live in this word or the one to the left; columns -2, -1 (word -1) are
+    // columns 2, 1 of word 0.  gmask (BASE): the columns where the gradient is defined as 0 (first, last, beyond).
+    uint32_t sel = 0x7654u, gmask = 0xffffffffu;
+    bool fixR    = false;
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+        const int c = 4 * wi + k;
+        if (c >= sw && c <= sw + 1) {
+            const int sc = 2 * (sw - 1) - c;
+            const int nb = (sc >> 2) == wi ? 4 + (sc & 3) : (sc & 3);
+            sel          = (sel & ~(0xfu << (4 * k))) | ((uint32_t)nb << (4 * k));
+            fixR         = true;
+        }
+        if (c <= 0 || c >= sw - 1) gmask &= ~(0xffu << (8 * k));
+    }
+    (void)fixR;
+    const bool fixL = strip == 0;  // lane 1 holds word -1
+    // rows: a segment away from the first / last rows of the image walks a pointer; the others fold the row index
+    const int y0        = 2 * oy0 - 2;  // first virtual source row of this segment
+    const bool interior = y0 - 1 >= 0 && 2 * oy1 + 2 < sh;
+    auto run = [&](auto interiorTag) {
+    constexpr bool INTERIOR = decltype(interiorTag)::value;
+    auto rowOf = [&](int y) {  // BORDER_REFLECT_101 of a row index (|y| small: one fold)
+        if (INTERIOR) return y;
+        int yy = y < 0 ? -y : y;
+        return yy >= sh ? 2 * sh - 2 - yy : yy;
+    };
+    const long long wofs = ld ? 4ll * wi : 0ll;  // (lanes outside the pitched row read word 0 and discard it)
+    auto ldraw = [&](const uint8_t* base, int y) -> uint32_t {
+        const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(base + (long long)rowOf(y) * spitch + wofs));
+        return ld ? v : 0u;
+    };
+    auto fixcols = [&](uint32_t w) -> uint32_t {  // (all lanes; the selector of a lane that needs no fix is the identity)
+        if (EDGE) {
+            w                 = __byte_perm(__shfl_up_sync(FULL, w, 1), w, sel);
+            const uint32_t w0 = __shfl_sync(FULL, w, 2);
+            if (fixL && lane == 1) w = __byte_perm(w0, 0u, 0x1200u);
+        }
+        return w;
+    };
+    auto hsumOf = [&](uint32_t w) -> uint32_t {
+        return pm_hsum(__shfl_up_sync(FULL, w, 1), w, __shfl_down_sync(FULL, w, 1));
+    };
+    // output words: even inner lanes store bytes 2 wi .. 2 wi + 3; what lies beyond the image width is written as zeros
+    const int ox        = 2 * wi;
+    const bool ostore   = inner && !(lane & 1) && ox < dpitch;
+    const int orem      = dw - ox;
+    const uint32_t omsk = orem <= 0 ? 0u : (orem < 4 ? (1u << (8 * orem)) - 1u : 0xffffffffu);
+    uint8_t* oI = dst_img + (long long)frame * dstride + (long long)oy0 * dpitch + (ostore ? ox : 0);
+    uint8_t* oG = dst_grad + (long long)frame * dstride + (long long)oy0 * dpitch + (ostore ? ox : 0);
+    auto emit = [&](uint8_t* dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e) {
+        const uint32_t acc = a + 4u * b + 6u * c + 4u * d + e + 0x00800080u;  // two 16-bit lanes, <= 65,408 each
+        const uint32_t two = __byte_perm(acc, 0u, 0x4431u);                   // bytes: out(2 wi), out(2 wi + 1), 0, 0
+        const uint32_t nxt = __shfl_down_sync(FULL, two, 1);
+        if (ostore) *reinterpret_cast<uint32_t*>(dst) = (two | (nxt << 16)) & omsk;
+    };
+    if (!BASE) {
+        // both stacks are read; the loads of the NEXT output row are issued before the arithmetic of this one
+        uint32_t i1 = hsumOf(fixcols(ldraw(sI, y0))), i2 = hsumOf(fixcols(ldraw(sI, y0 + 1)));
+        uint32_t i3 = hsumOf(fixcols(ldraw(sI, y0 + 2))), i4 = hsumOf(fixcols(ldraw(sI, y0 + 3)));
+        uint32_t g1 = hsumOf(fixcols(ldraw(sG, y0))), g2 = hsumOf(fixcols(ldraw(sG, y0 + 1)));
+        uint32_t g3 = hsumOf(fixcols(ldraw(sG, y0 + 2))), g4 = hsumOf(fixcols(ldraw(sG, y0 + 3)));
+        uint32_t ra = ldraw(sI, y0 + 4), rb = ldraw(sI, y0 + 5), rc = ldraw(sG, y0 + 4), rd = ldraw(sG, y0 + 5);
+#pragma unroll 1
+        for (int oy = oy0; oy < oy1; oy++) {
+            const uint32_t na = ldraw(sI, 2 * oy + 4), nb = ldraw(sI, 2 * oy + 5), nc = ldraw(sG, 2 * oy + 4), nd = ldraw(sG, 2 * oy + 5);
+            const uint32_t in1 = hsumOf(fixcols(ra)), gn1 = hsumOf(fixcols(rc));
+            emit(oI, i1, i2, i3, i4, in1);
+            emit(oG, g1, g2, g3, g4, gn1);
+            oI += dpitch, oG += dpitch;
+            const uint32_t in2 = hsumOf(fixcols(rb)), gn2 = hsumOf(fixcols(rd));
+            i1 = i3, i2 = i4, i3 = in1, i4 = in2;
+            g1 = g3, g2 = g4, g3 = gn1, g4 = gn2;
+            ra = na, rb = nb, rc = nc, rd = nd;
+        }
+    } else {
+        // image rows y - 1, y, y + 1 in registers: up, cur (with its neighbour words), dn.  Gradient rows [2 oy0, 2 oy1) of
+        // the image belong to this segment: its first two and last two virtual rows are the halo of the taps.
+        const bool gstore = inner && ld;
+        uint8_t* pG0      = grad0 + (long long)frame * sstride + (long long)(2 * oy0) * spitch + wofs;
+        uint32_t up = fixcols(ldraw(sI, y0 - 1)), cur = fixcols(ldraw(sI, y0));
+        uint32_t r1 = ldraw(sI, y0 + 1), r2 = ldraw(sI, y0 + 2), r3 = ldraw(sI, y0 + 3), r4 = ldraw(sI, y0 + 4);
+        auto step = [&](int y, bool own, uint32_t rawDn, uint32_t& hi, uint32_t& hg) {  // virtual row y: its two horizontal sums
+            const uint32_t dn = fixcols(rawDn);
+            const uint32_t wl = __shfl_up_sync(FULL, cur, 1), wr = __shfl_down_sync(FULL, cur, 1);
+            hi                = pm_hsum(wl, cur, wr);
+            const uint32_t left = __funnelshift_r(wl, cur, 24), right = __funnelshift_r(cur, wr, 8);  // columns x - 1 / x + 1
+            uint32_t g          = __vaddus4(__vabsdiffu4(right, left), __vabsdiffu4(dn, up)) & gmask;
+            if (!INTERIOR) {
+                const int yr = rowOf(y);
+                if (yr == 0 || yr == sh - 1) g = 0u;  // SimdLib.h:856-884: first / last row
+                own = own && y >= 0 && y < sh;
+            }
+            if (own) {
+                if (gstore) *reinterpret_cast<uint32_t*>(pG0) = g;
+                pG0 += spitch;
+            }
+            hg  = hsumOf(fixcols(g));
+            up  = cur;
+            cur = dn;
+        };
+        uint32_t i1, i2, i3, i4, g1, g2, g3, g4;
+        step(y0, false, r1, i1, g1);
+        step(y0 + 1, false, r2, i2, g2);
+        step(y0 + 2, true, r3, i3, g3);
+        step(y0 + 3, true, r4, i4, g4);
+        uint32_t ra = ldraw(sI, y0 + 5), rb = ldraw(sI, y0 + 6);
+#pragma unroll 1
+        for (int oy = oy0; oy < oy1; oy++) {
+            const uint32_t na = ldraw(sI, 2 * oy + 5), nb = ldraw(sI, 2 * oy + 6);  // (rows y0 + 7, y0 + 8 at the first pass)
+            const bool own = oy + 1 < oy1;  // (the last output row's two new rows are the halo below the segment)
+            uint32_t in1, gn1, in2, gn2;
+            step(2 * oy + 2, own, ra, in1, gn1);
+            emit(oI, i1, i2, i3, i4, in1);
+            emit(oG, g1, g2, g3, g4, gn1);
+            oI += dpitch, oG += dpitch;
+            step(2 * oy + 3, own, rb, in2, gn2);
+            i1 = i3, i2 = i4, i3 = in1, i4 = in2;
+            g1 = g3, g2 = g4, g3 = gn1, g4 = gn2;
+            ra = na, rb = nb;
+        }
+    }
+    };  // run
+    if (interior)
+        run(std::true_type{});
+    else
+        run(std::false_type{});
+}
+
 // cv::pyrDown, one level, both stacks, byte-wise: only for levels smaller than 8 x 8, where the reflection can wrap
 // more than once.  grid: (ceil(dw/TX), ceil(dh/TY), 2 * n_frames)
 constexpr int TX = 64, TY = 8;
@@ -334,6 +511,59 @@ svo_status launch_pyramid_build(svo_ctx* ctx, int first_slot, int n)
     const PyramidArena& a = ctx->arena;
     const LevelGeom& g0   = a.geom[0];
     bool grad0_done       = false;
+    // Batches: the register-marching kernels (level 0 -> 1 with the gradient fused).  One launch pair per level over the whole
+    // batch: chunking the batch so that L2 holds what a level hands to the next saves 19 % of the DRAM reads and loses more than
+    // that to the extra launches (measured, tests/cuda/pyr_probe.py).  A single frame (the per-frame front end) keeps the fused
+    // tile kernel: a handful of CTAs either way, and one launch instead of two.
+    if (n >= 4 && a.levels >= 2 && g0.w >= 64 && g0.h >= 8) {
+        const char* ce  = getenv("SVO_PYR_CHUNK");  // (measurements) frames per chunk
+        const int chunk = ce ? std::max(1, atoi(ce)) : 1 << 30;
+        for (int c0 = 0; c0 < n; c0 += chunk) {
+            const int m = std::min(chunk, n - c0), fs = first_slot + c0;
+            for (int l = 1; l < a.levels; l++) {
+                const LevelGeom& s = a.geom[l - 1];
+                const LevelGeom& d = a.geom[l];
+                if (s.w >= 64 && s.h >= 8) {
+                    // strips 1 .. edge0 - 1 need no column reflection; strip 0 and the strips from edge0 on (the first whose
+                    // words reach column sw) do.  Row segments: long (less halo) when the batch fills the device anyway.
+                    const int strips = (d.w + 2 * PM_INNER - 1) / (2 * PM_INNER);
+                    int edge0        = 1;
+                    while (edge0 < strips && 4 * (PM_INNER * edge0 + 30) <= s.w) edge0++;
+                    const int rows = (long long)strips * ((d.h + 23) / 24) * m >= 148 * 32 ? 24 : ((long long)strips * ((d.h + 11) / 12) * m >= 148 * 16 ? 12 : 6);
+                    const int segs = (d.h + rows - 1) / rows;
+                    const uint8_t* sg = l == 1 ? nullptr : a.grad[l - 1] + fs * s.plane_stride;
+                    uint8_t* g0w      = l == 1 ? a.grad[0] + fs * s.plane_stride : nullptr;
+                    const dim3 gEdge(1 + (strips - edge0), segs, m), gMid(std::max(edge0 - 1, 0), segs, m);
+#define SVO_MARCH(BASE, EDGE, GRID)                                                                                                   \
+    k_pyr_march<BASE, EDGE><<<GRID, 32, 0, ctx->pyr_stream>>>(a.img[l - 1] + fs * s.plane_stride, sg, a.img[l] + fs * d.plane_stride,   \
+                                                            a.grad[l] + fs * d.plane_stride, g0w, s.w, s.h, s.pitch, s.plane_stride,  \
+                                                            d.w, d.h, d.pitch, d.plane_stride, edge0, rows)
+                    if (l == 1) {
+                        SVO_MARCH(true, true, gEdge);
+                        if (gMid.x) SVO_MARCH(true, false, gMid);
+                    } else {
+                        SVO_MARCH(false, true, gEdge);
+                        if (gMid.x) SVO_MARCH(false, false, gMid);
+                    }
+#undef SVO_MARCH
+                    if (gMid.x) ctx->launches++;
+                } else if (s.w >= 8 && s.h >= 8) {
+                    dim3 grid((d.w + PT_X - 1) / PT_X, (d.h + PT_Y - 1) / PT_Y, m);
+                    k_pyr_level<false><<<grid, 256, 0, ctx->pyr_stream>>>(
+                        a.img[l - 1] + fs * s.plane_stride, a.grad[l - 1] + fs * s.plane_stride, a.img[l] + fs * d.plane_stride,
+                        a.grad[l] + fs * d.plane_stride, nullptr, s.w, s.h, s.pitch, s.plane_stride, d.w, d.h, d.pitch, d.plane_stride);
+                } else {
+                    dim3 grid((d.w + TX - 1) / TX, (d.h + TY - 1) / TY, 2 * m);
+                    k_pyrdown_small<<<grid, 256, 0, ctx->pyr_stream>>>(a.img[l - 1] + fs * s.plane_stride, a.img[l] + fs * d.plane_stride,
+                                                                   a.grad[l - 1] + fs * s.plane_stride, a.grad[l] + fs * d.plane_stride,
+                                                                   s.w, s.h, s.pitch, s.plane_stride, d.w, d.h, d.pitch, d.plane_stride);
+                }
+                ctx->launches++;
+            }
+        }
+        SVO_CUDA(cudaGetLastError());
+        return SVO_OK;
+    }
     for (int l = 1; l < a.levels; l++) {
         const LevelGeom& s = a.geom[l - 1];
         const LevelGeom& d = a.geom[l];

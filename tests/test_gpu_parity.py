@@ -49,6 +49,34 @@ def test_pyramid_bit_exact(pkg, orc, shape):
                 assert np.array_equal(ctx.download(s, l, 1), gpl[l]), ("gradient", s, l)
 
 
+@pytest.mark.parametrize("shape", [(376, 1241), (375, 1240), (188, 621), (97, 257), (64, 64), (66, 131), (129, 70), (200, 1024),
+                                   (41, 1237), (8, 65)])
+def test_pyramid_batch_path_bit_exact(pkg, orc, shape):
+    """Batches of four frames and more take the streaming gradient kernel + the register-marching pyrDown kernel (csrc/pyramid.cu,
+    k_pyrdown_march) instead of the fused tile kernel of a single frame: widths around every word / strip / pitch boundary
+    (w % 4 = 0..3, w % 16 = 0, one strip, strips that end in the padding), odd and even heights, saturating gradients;
+    every level of both stacks against the oracle, and against the single-frame path."""
+    h, w = shape
+    rng = np.random.default_rng(h * 7919 + w)
+    levels = 4 if min(h, w) >= 64 else 2
+    n = 6
+    imgs = rng.integers(0, 256, (n, h, w), dtype=np.uint8)
+    imgs[1] = 255 * (rng.random((h, w)) > 0.5)
+    imgs[2] = np.add.outer(np.arange(h), np.arange(w)) % 256
+    with pkg.Context(w, h, (500, 500, w / 2, h / 2), levels=levels, max_frames=n + 1, max_jobs=1, max_features=16,
+                     max_fa_items=16) as ctx:
+        ctx.upload(0, imgs)            # batch path
+        ctx.upload(n, imgs[3])         # single-frame path
+        for s in range(n):
+            ip, gp = orc.build_pyramid(imgs[s], levels)
+            ipl, gpl = orc.unpack_pyramid(ip, w, h, levels), orc.unpack_pyramid(gp, w, h, levels)
+            for l in range(levels):
+                assert np.array_equal(ctx.download(s, l, 0), ipl[l]), ("image", s, l)
+                assert np.array_equal(ctx.download(s, l, 1), gpl[l]), ("gradient", s, l)
+        for l in range(levels):
+            assert np.array_equal(ctx.download(n, l, 0), ctx.download(3, l, 0)) and np.array_equal(ctx.download(n, l, 1), ctx.download(3, l, 1))
+
+
 def test_pyramid_strided_and_pinned_upload(pkg, orc):
     h, w = 376, 1241
     rng = np.random.default_rng(5)
