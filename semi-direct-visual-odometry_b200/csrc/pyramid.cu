@@ -288,17 +288,17 @@ __global__ void __launch_bounds__(256) k_pyr_level(const uint8_t* __restrict__ s
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// cv::pyrDown of both stacks for BATCHES of frames, register-marching: a warp owns a strip of 32 source words (128
-// columns, 2 words of overlap on either side: the inner 28 words give 56 output columns) and walks down the rows of its
-// row segment.  Per source row and lane: one coalesced 32-bit load per stack, the neighbour words by shuffle, the
-// horizontal [1 4 6 4 1] of the lane's two outputs as three dp4a; the last four rows of horizontal sums stay in
-// registers (two 16-bit lanes per register), every second row emits one output row: (sum + 128) >> 8, two bytes per lane,
-// paired by shuffle into 32-bit stores.  No shared memory, no barrier, no index arithmetic beyond a row pointer.
-// BORDER_REFLECT_101: rows by mapping the row index, columns by one byte permute whose selector depends on the lane only.
-// The tile kernel above needs ~760 instructions per thread and tile (index arithmetic of five staged loops); this one ~30
-// per lane and source row for both stacks.  grid: (strips, row segments / 4, frames), block (32, 4).
+// cv::pyrDown of both stacks for BATCHES of frames, register-marching: a warp (= one CTA) owns a strip of 256 source columns
+// (a lane holds eight: two words; one lane of overlap on either side, the inner 30 lanes give 120 output columns) and walks
+// down the rows of its row segment.  Per source row and lane: one coalesced 64-bit load per stack (issued two output rows
+// ahead), the two neighbour words by shuffle, the horizontal [1 4 6 4 1] of the lane's four outputs as six dp4a; the last
+// four rows of horizontal sums stay in registers (two 16-bit lanes per register), every second row emits one output row:
+// (sum + 128) >> 8, four bytes per lane, one aligned 32-bit store.  No shared memory, no barrier, no index arithmetic beyond
+// row pointers.  BORDER_REFLECT_101: rows by folding the row index (border segments only), columns by one byte permute per
+// word whose selector depends on the lane only (border strips only).  The tile kernel above needs ~190 instructions per
+// source word of both stacks; this one ~40.  grid: (strips, row segments, frames), block 32.
 // ------------------------------------------------------------------------------------------------------------
-constexpr int PM_INNER = 28;   // inner words of a strip
+constexpr int PM_INNER = 30;   // inner lanes of a strip (8 source columns, 4 output columns each)
 
 __device__ __forceinline__ uint32_t pm_hsum(uint32_t wl, uint32_t w, uint32_t wr)
 {
@@ -315,42 +315,50 @@ __device__ __forceinline__ uint32_t pm_hsum(uint32_t wl, uint32_t w, uint32_t wr
 // reflection; the strips in between (launched separately: nothing but the blockIdx differs) carry none of that code.  A CTA is
 // ONE warp and every loop bound derives from blockIdx: the compiler sees warp-uniform control flow around the shuffles.
 template <bool BASE, bool EDGE>
-__global__ void __launch_bounds__(32) k_pyr_march(const uint8_t* __restrict__ src_img, const uint8_t* __restrict__ src_grad,
-                                                  uint8_t* __restrict__ dst_img, uint8_t* __restrict__ dst_grad,
-                                                  uint8_t* __restrict__ grad0, int sw, int sh, int spitch, long long sstride,
-                                                  int dw, int dh, int dpitch, long long dstride, int edge0, int rows)
+__device__ __forceinline__ void pyr_march_strip(const uint8_t* __restrict__ src_img, const uint8_t* __restrict__ src_grad,
+                                                uint8_t* __restrict__ dst_img, uint8_t* __restrict__ dst_grad,
+                                                uint8_t* __restrict__ grad0, int sw, int sh, int spitch, long long sstride, int dw,
+                                                int dh, int dpitch, long long dstride, int rows)
 {
     constexpr unsigned FULL = 0xffffffffu;
     const int lane = threadIdx.x, frame = blockIdx.z;
-    const int strip = EDGE ? (blockIdx.x == 0 ? 0 : edge0 + (int)blockIdx.x - 1) : 1 + (int)blockIdx.x;
-    const int wi    = strip * PM_INNER - 2 + lane;  // source word of this lane (columns 4 wi .. 4 wi + 3)
-    const int oy0   = blockIdx.y * rows;
-    const int oy1   = min(oy0 + rows, dh);
+    const int strip = blockIdx.x;
+    // a lane holds EIGHT source columns (two words): columns 8 L .. 8 L + 7 with L = strip * PM_INNER - 1 + lane; lanes 1 .. 30
+    // are the inner ones: four outputs each (columns 4 L .. 4 L + 3 of the next level), one aligned 32-bit store
+    const int L   = strip * PM_INNER - 1 + lane;
+    const int oy0 = blockIdx.y * rows;
+    const int oy1 = min(oy0 + rows, dh);
     const uint8_t* sI = src_img + (long long)frame * sstride;
     const uint8_t* sG = BASE ? nullptr : src_grad + (long long)frame * sstride;
-    const bool ld     = wi >= 0 && 4 * wi < spitch;
-    const bool inner  = lane >= 2 && lane < 2 + PM_INNER;
-    // column reflection: byte k of this lane's word is column c = 4 wi + k; columns sw, sw + 1 (the only ones beyond the image
-    // a tap can reach) are columns sw - 2, sw - 3, which live in this word or the one to the left; columns -2, -1 (word -1) are
-    // columns 2, 1 of word 0.  gmask (BASE): the columns where the gradient is defined as 0 (first, last, beyond).
-    uint32_t sel = 0x7654u, gmask = 0xffffffffu;
-    bool fixR    = false;
+    const bool ld     = L >= 0 && 8 * L < spitch;  // (the pitch is a multiple of 16)
+    const bool inner  = lane >= 1 && lane <= PM_INNER;
+    // column reflection, per word (k = 0 .. 3: the low word, 4 .. 7: the high word): column c = 8 L + k.  Columns sw, sw + 1 (the
+    // only ones beyond the image a tap can reach) are columns sw - 2, sw - 3, which live in the same word or the one to its left;
+    // columns -2, -1 (high word of L = -1) are columns 2, 1 (low word of L = 0).  gmask (BASE): the columns where the
+    // gradient is defined as 0 (first, last, beyond).
+    uint32_t selLo = 0x7654u, selHi = 0x7654u, gmLo = 0xffffffffu, gmHi = 0xffffffffu;
 #pragma unroll
-    for (int k = 0; k < 4; k++) {
-        const int c = 4 * wi + k;
+    for (int k = 0; k < 8; k++) {
+        const int c = 8 * L + k, word = 2 * L + (k >> 2), kk = k & 3;
         if (c >= sw && c <= sw + 1) {
             const int sc = 2 * (sw - 1) - c;
-            const int nb = (sc >> 2) == wi ? 4 + (sc & 3) : (sc & 3);
-            sel          = (sel & ~(0xfu << (4 * k))) | ((uint32_t)nb << (4 * k));
-            fixR         = true;
+            const int nb = (sc >> 2) == word ? 4 + (sc & 3) : (sc & 3);
+            if (k < 4)
+                selLo = (selLo & ~(0xfu << (4 * kk))) | ((uint32_t)nb << (4 * kk));
+            else
+                selHi = (selHi & ~(0xfu << (4 * kk))) | ((uint32_t)nb << (4 * kk));
         }
-        if (c <= 0 || c >= sw - 1) gmask &= ~(0xffu << (8 * k));
+        if (c <= 0 || c >= sw - 1) {
+            if (k < 4)
+                gmLo &= ~(0xffu << (8 * kk));
+            else
+                gmHi &= ~(0xffu << (8 * kk));
+        }
     }
-    (void)fixR;
-    const bool fixL = strip == 0;  // lane 1 holds word -1
+    const bool fixL = strip == 0;  // lane 0 holds L = -1
     // rows: a segment away from the first / last rows of the image walks a pointer; the others fold the row index
     const int y0        = 2 * oy0 - 2;  // first virtual source row of this segment
-    const bool interior = y0 - 1 >= 0 && 2 * oy1 + 2 < sh;
+    const bool interior = y0 - 1 >= 0 && 2 * oy1 + 6 < sh;  // (rows y0 - 1 .. 2 oy1 + 6 are touched: taps, gradient halo, loads ahead)
     auto run = [&](auto interiorTag) {
     constexpr bool INTERIOR = decltype(interiorTag)::value;
     auto rowOf = [&](int y) {  // BORDER_REFLECT_101 of a row index (|y| small: one fold)
@@ -358,98 +366,125 @@ __global__ void __launch_bounds__(32) k_pyr_march(const uint8_t* __restrict__ sr
         int yy = y < 0 ? -y : y;
         return yy >= sh ? 2 * sh - 2 - yy : yy;
     };
-    const long long wofs = ld ? 4ll * wi : 0ll;  // (lanes outside the pitched row read word 0 and discard it)
-    auto ldraw = [&](const uint8_t* base, int y) -> uint32_t {
-        const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(base + (long long)rowOf(y) * spitch + wofs));
-        return ld ? v : 0u;
+    const long long wofs = ld ? 8ll * L : 0ll;  // (lanes outside the pitched row read the first 8 bytes and discard them)
+    auto ldraw = [&](const uint8_t* base, int y) -> uint2 {
+        const uint2 v = __ldg(reinterpret_cast<const uint2*>(base + (long long)rowOf(y) * spitch + wofs));
+        return ld ? v : make_uint2(0u, 0u);
     };
-    auto fixcols = [&](uint32_t w) -> uint32_t {  // (all lanes; the selector of a lane that needs no fix is the identity)
+    auto fixcols = [&](uint2 w) -> uint2 {  // (all lanes; the selector of a word that needs no fix is the identity)
         if (EDGE) {
-            w                 = __byte_perm(__shfl_up_sync(FULL, w, 1), w, sel);
-            const uint32_t w0 = __shfl_sync(FULL, w, 2);
-            if (fixL && lane == 1) w = __byte_perm(w0, 0u, 0x1200u);
+            const uint32_t ph = __shfl_up_sync(FULL, w.y, 1);
+            const uint32_t lo = __byte_perm(ph, w.x, selLo);
+            w.y               = __byte_perm(w.x, w.y, selHi);  // (its left word is the RAW low word: columns below sw)
+            w.x               = lo;
+            const uint32_t n0 = __shfl_down_sync(FULL, w.x, 1);
+            if (fixL && lane == 0) w.y = __byte_perm(n0, 0u, 0x1200u);
         }
         return w;
     };
-    auto hsumOf = [&](uint32_t w) -> uint32_t {
-        return pm_hsum(__shfl_up_sync(FULL, w, 1), w, __shfl_down_sync(FULL, w, 1));
+    // horizontal sums of the lane's four outputs (two registers of two 16-bit lanes) and the neighbour words they need
+    auto hsumOf = [&](uint2 w, uint32_t& h01, uint32_t& h23) {
+        const uint32_t ph = __shfl_up_sync(FULL, w.y, 1), nl = __shfl_down_sync(FULL, w.x, 1);
+        h01 = pm_hsum(ph, w.x, w.y);
+        h23 = pm_hsum(w.x, w.y, nl);
     };
-    // output words: even inner lanes store bytes 2 wi .. 2 wi + 3; what lies beyond the image width is written as zeros
-    const int ox        = 2 * wi;
-    const bool ostore   = inner && !(lane & 1) && ox < dpitch;
+    const int ox        = 4 * L;
+    const bool ostore   = inner && ox >= 0 && ox < dpitch;
     const int orem      = dw - ox;
     const uint32_t omsk = orem <= 0 ? 0u : (orem < 4 ? (1u << (8 * orem)) - 1u : 0xffffffffu);
     uint8_t* oI = dst_img + (long long)frame * dstride + (long long)oy0 * dpitch + (ostore ? ox : 0);
     uint8_t* oG = dst_grad + (long long)frame * dstride + (long long)oy0 * dpitch + (ostore ? ox : 0);
-    auto emit = [&](uint8_t* dst, uint32_t a, uint32_t b, uint32_t c, uint32_t d, uint32_t e) {
-        const uint32_t acc = a + 4u * b + 6u * c + 4u * d + e + 0x00800080u;  // two 16-bit lanes, <= 65,408 each
-        const uint32_t two = __byte_perm(acc, 0u, 0x4431u);                   // bytes: out(2 wi), out(2 wi + 1), 0, 0
-        const uint32_t nxt = __shfl_down_sync(FULL, two, 1);
-        if (ostore) *reinterpret_cast<uint32_t*>(dst) = (two | (nxt << 16)) & omsk;
+    auto emit = [&](uint8_t* dst, const uint32_t (&a)[2], const uint32_t (&b)[2], const uint32_t (&c)[2], const uint32_t (&d)[2], uint32_t e0,
+                    uint32_t e1) {
+        const uint32_t acc0 = a[0] + 4u * b[0] + 6u * c[0] + 4u * d[0] + e0 + 0x00800080u;  // two 16-bit lanes, <= 65,408 each
+        const uint32_t acc1 = a[1] + 4u * b[1] + 6u * c[1] + 4u * d[1] + e1 + 0x00800080u;
+        if (ostore) *reinterpret_cast<uint32_t*>(dst) = __byte_perm(acc0, acc1, 0x7531u) & omsk;  // the high byte of each lane
     };
     if (!BASE) {
-        // both stacks are read; the loads of the NEXT output row are issued before the arithmetic of this one
-        uint32_t i1 = hsumOf(fixcols(ldraw(sI, y0))), i2 = hsumOf(fixcols(ldraw(sI, y0 + 1)));
-        uint32_t i3 = hsumOf(fixcols(ldraw(sI, y0 + 2))), i4 = hsumOf(fixcols(ldraw(sI, y0 + 3)));
-        uint32_t g1 = hsumOf(fixcols(ldraw(sG, y0))), g2 = hsumOf(fixcols(ldraw(sG, y0 + 1)));
-        uint32_t g3 = hsumOf(fixcols(ldraw(sG, y0 + 2))), g4 = hsumOf(fixcols(ldraw(sG, y0 + 3)));
-        uint32_t ra = ldraw(sI, y0 + 4), rb = ldraw(sI, y0 + 5), rc = ldraw(sG, y0 + 4), rd = ldraw(sG, y0 + 5);
+        uint32_t i1[2], i2[2], i3[2], i4[2], g1[2], g2[2], g3[2], g4[2];
+        hsumOf(fixcols(ldraw(sI, y0)), i1[0], i1[1]);
+        hsumOf(fixcols(ldraw(sI, y0 + 1)), i2[0], i2[1]);
+        hsumOf(fixcols(ldraw(sI, y0 + 2)), i3[0], i3[1]);
+        hsumOf(fixcols(ldraw(sI, y0 + 3)), i4[0], i4[1]);
+        hsumOf(fixcols(ldraw(sG, y0)), g1[0], g1[1]);
+        hsumOf(fixcols(ldraw(sG, y0 + 1)), g2[0], g2[1]);
+        hsumOf(fixcols(ldraw(sG, y0 + 2)), g3[0], g3[1]);
+        hsumOf(fixcols(ldraw(sG, y0 + 3)), g4[0], g4[1]);
+        // (loads run TWO output rows ahead of the arithmetic: with 32 warps per SM that is what it takes to keep HBM busy)
+        uint2 ra = ldraw(sI, y0 + 4), rb = ldraw(sI, y0 + 5), rc = ldraw(sG, y0 + 4), rd = ldraw(sG, y0 + 5);
+        uint2 pa = ldraw(sI, y0 + 6), pb = ldraw(sI, y0 + 7), pc = ldraw(sG, y0 + 6), pd = ldraw(sG, y0 + 7);
 #pragma unroll 1
         for (int oy = oy0; oy < oy1; oy++) {
-            const uint32_t na = ldraw(sI, 2 * oy + 4), nb = ldraw(sI, 2 * oy + 5), nc = ldraw(sG, 2 * oy + 4), nd = ldraw(sG, 2 * oy + 5);
-            const uint32_t in1 = hsumOf(fixcols(ra)), gn1 = hsumOf(fixcols(rc));
-            emit(oI, i1, i2, i3, i4, in1);
-            emit(oG, g1, g2, g3, g4, gn1);
+            const uint2 na = pa, nb = pb, nc = pc, nd = pd;
+            pa = ldraw(sI, 2 * oy + 6), pb = ldraw(sI, 2 * oy + 7), pc = ldraw(sG, 2 * oy + 6), pd = ldraw(sG, 2 * oy + 7);
+            uint32_t in1[2], gn1[2], in2[2], gn2[2];
+            hsumOf(fixcols(ra), in1[0], in1[1]);
+            hsumOf(fixcols(rc), gn1[0], gn1[1]);
+            emit(oI, i1, i2, i3, i4, in1[0], in1[1]);
+            emit(oG, g1, g2, g3, g4, gn1[0], gn1[1]);
             oI += dpitch, oG += dpitch;
-            const uint32_t in2 = hsumOf(fixcols(rb)), gn2 = hsumOf(fixcols(rd));
-            i1 = i3, i2 = i4, i3 = in1, i4 = in2;
-            g1 = g3, g2 = g4, g3 = gn1, g4 = gn2;
+            hsumOf(fixcols(rb), in2[0], in2[1]);
+            hsumOf(fixcols(rd), gn2[0], gn2[1]);
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                i1[q] = i3[q], i2[q] = i4[q], i3[q] = in1[q], i4[q] = in2[q];
+                g1[q] = g3[q], g2[q] = g4[q], g3[q] = gn1[q], g4[q] = gn2[q];
+            }
             ra = na, rb = nb, rc = nc, rd = nd;
         }
     } else {
-        // image rows y - 1, y, y + 1 in registers: up, cur (with its neighbour words), dn.  Gradient rows [2 oy0, 2 oy1) of
-        // the image belong to this segment: its first two and last two virtual rows are the halo of the taps.
+        // image rows y - 1, y, y + 1 in registers: up, cur, dn.  Gradient rows [2 oy0, 2 oy1) of the image belong to this
+        // segment: its first two and last two virtual rows are the halo of the taps.
         const bool gstore = inner && ld;
         uint8_t* pG0      = grad0 + (long long)frame * sstride + (long long)(2 * oy0) * spitch + wofs;
-        uint32_t up = fixcols(ldraw(sI, y0 - 1)), cur = fixcols(ldraw(sI, y0));
-        uint32_t r1 = ldraw(sI, y0 + 1), r2 = ldraw(sI, y0 + 2), r3 = ldraw(sI, y0 + 3), r4 = ldraw(sI, y0 + 4);
-        auto step = [&](int y, bool own, uint32_t rawDn, uint32_t& hi, uint32_t& hg) {  // virtual row y: its two horizontal sums
-            const uint32_t dn = fixcols(rawDn);
-            const uint32_t wl = __shfl_up_sync(FULL, cur, 1), wr = __shfl_down_sync(FULL, cur, 1);
-            hi                = pm_hsum(wl, cur, wr);
-            const uint32_t left = __funnelshift_r(wl, cur, 24), right = __funnelshift_r(cur, wr, 8);  // columns x - 1 / x + 1
-            uint32_t g          = __vaddus4(__vabsdiffu4(right, left), __vabsdiffu4(dn, up)) & gmask;
+        uint2 up = fixcols(ldraw(sI, y0 - 1)), cur = fixcols(ldraw(sI, y0));
+        uint2 r1 = ldraw(sI, y0 + 1), r2 = ldraw(sI, y0 + 2), r3 = ldraw(sI, y0 + 3), r4 = ldraw(sI, y0 + 4);
+        auto step = [&](int y, bool own, uint2 rawDn, uint32_t (&hi)[2], uint32_t (&hg)[2]) {  // virtual row y: its horizontal sums
+            const uint2 dn    = fixcols(rawDn);
+            const uint32_t ph = __shfl_up_sync(FULL, cur.y, 1), nl = __shfl_down_sync(FULL, cur.x, 1);
+            hi[0]             = pm_hsum(ph, cur.x, cur.y);
+            hi[1]             = pm_hsum(cur.x, cur.y, nl);
+            // columns x - 1 / x + 1 of the two words
+            const uint32_t l0 = __funnelshift_r(ph, cur.x, 24), q0 = __funnelshift_r(cur.x, cur.y, 8);
+            const uint32_t l1 = __funnelshift_r(cur.x, cur.y, 24), q1 = __funnelshift_r(cur.y, nl, 8);
+            uint2 g;
+            g.x = __vaddus4(__vabsdiffu4(q0, l0), __vabsdiffu4(dn.x, up.x)) & gmLo;
+            g.y = __vaddus4(__vabsdiffu4(q1, l1), __vabsdiffu4(dn.y, up.y)) & gmHi;
             if (!INTERIOR) {
                 const int yr = rowOf(y);
-                if (yr == 0 || yr == sh - 1) g = 0u;  // SimdLib.h:856-884: first / last row
+                if (yr == 0 || yr == sh - 1) g = make_uint2(0u, 0u);  // SimdLib.h:856-884: first / last row
                 own = own && y >= 0 && y < sh;
             }
             if (own) {
-                if (gstore) *reinterpret_cast<uint32_t*>(pG0) = g;
+                if (gstore) *reinterpret_cast<uint2*>(pG0) = g;
                 pG0 += spitch;
             }
-            hg  = hsumOf(fixcols(g));
+            hsumOf(fixcols(g), hg[0], hg[1]);
             up  = cur;
             cur = dn;
         };
-        uint32_t i1, i2, i3, i4, g1, g2, g3, g4;
+        uint32_t i1[2], i2[2], i3[2], i4[2], g1[2], g2[2], g3[2], g4[2];
         step(y0, false, r1, i1, g1);
         step(y0 + 1, false, r2, i2, g2);
         step(y0 + 2, true, r3, i3, g3);
         step(y0 + 3, true, r4, i4, g4);
-        uint32_t ra = ldraw(sI, y0 + 5), rb = ldraw(sI, y0 + 6);
+        uint2 ra = ldraw(sI, y0 + 5), rb = ldraw(sI, y0 + 6), pa = ldraw(sI, y0 + 7), pb = ldraw(sI, y0 + 8);
 #pragma unroll 1
         for (int oy = oy0; oy < oy1; oy++) {
-            const uint32_t na = ldraw(sI, 2 * oy + 5), nb = ldraw(sI, 2 * oy + 6);  // (rows y0 + 7, y0 + 8 at the first pass)
+            const uint2 na = pa, nb = pb;  // (loads run two output rows ahead)
+            pa = ldraw(sI, 2 * oy + 7), pb = ldraw(sI, 2 * oy + 8);  // (rows y0 + 9, y0 + 10 at the first pass)
             const bool own = oy + 1 < oy1;  // (the last output row's two new rows are the halo below the segment)
-            uint32_t in1, gn1, in2, gn2;
+            uint32_t in1[2], gn1[2], in2[2], gn2[2];
             step(2 * oy + 2, own, ra, in1, gn1);
-            emit(oI, i1, i2, i3, i4, in1);
-            emit(oG, g1, g2, g3, g4, gn1);
+            emit(oI, i1, i2, i3, i4, in1[0], in1[1]);
+            emit(oG, g1, g2, g3, g4, gn1[0], gn1[1]);
             oI += dpitch, oG += dpitch;
             step(2 * oy + 3, own, rb, in2, gn2);
-            i1 = i3, i2 = i4, i3 = in1, i4 = in2;
-            g1 = g3, g2 = g4, g3 = gn1, g4 = gn2;
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                i1[q] = i3[q], i2[q] = i4[q], i3[q] = in1[q], i4[q] = in2[q];
+                g1[q] = g3[q], g2[q] = g4[q], g3[q] = gn1[q], g4[q] = gn2[q];
+            }
             ra = na, rb = nb;
         }
     }
@@ -458,6 +493,19 @@ __global__ void __launch_bounds__(32) k_pyr_march(const uint8_t* __restrict__ sr
         run(std::true_type{});
     else
         run(std::false_type{});
+}
+
+// strips 1 .. edge0 - 1 hold no border column (blockIdx-uniform choice of the instantiation)
+template <bool BASE>
+__global__ void __launch_bounds__(32) k_pyr_march(const uint8_t* __restrict__ src_img, const uint8_t* __restrict__ src_grad,
+                                                  uint8_t* __restrict__ dst_img, uint8_t* __restrict__ dst_grad,
+                                                  uint8_t* __restrict__ grad0, int sw, int sh, int spitch, long long sstride,
+                                                  int dw, int dh, int dpitch, long long dstride, int edge0, int rows)
+{
+    if (blockIdx.x == 0 || (int)blockIdx.x >= edge0)
+        pyr_march_strip<BASE, true>(src_img, src_grad, dst_img, dst_grad, grad0, sw, sh, spitch, sstride, dw, dh, dpitch, dstride, rows);
+    else
+        pyr_march_strip<BASE, false>(src_img, src_grad, dst_img, dst_grad, grad0, sw, sh, spitch, sstride, dw, dh, dpitch, dstride, rows);
 }
 
 // cv::pyrDown, one level, both stacks, byte-wise: only for levels smaller than 8 x 8, where the reflection can wrap
@@ -526,27 +574,24 @@ svo_status launch_pyramid_build(svo_ctx* ctx, int first_slot, int n)
                 if (s.w >= 64 && s.h >= 8) {
                     // strips 1 .. edge0 - 1 need no column reflection; strip 0 and the strips from edge0 on (the first whose
                     // words reach column sw) do.  Row segments: long (less halo) when the batch fills the device anyway.
-                    const int strips = (d.w + 2 * PM_INNER - 1) / (2 * PM_INNER);
+                    const int strips = (d.w + 4 * PM_INNER - 1) / (4 * PM_INNER);
                     int edge0        = 1;
-                    while (edge0 < strips && 4 * (PM_INNER * edge0 + 30) <= s.w) edge0++;
-                    const int rows = (long long)strips * ((d.h + 23) / 24) * m >= 148 * 32 ? 24 : ((long long)strips * ((d.h + 11) / 12) * m >= 148 * 16 ? 12 : 6);
+                    while (edge0 < strips && 8 * (PM_INNER * edge0 + 31) <= s.w) edge0++;  // (the strip's last column is below sw)
+                    // row segments: as long as possible (less halo) while the batch still fills the device
+                    int rows = 48;
+                    while (rows > 6 && (long long)strips * ((d.h + rows - 1) / rows) * m < 148 * 32) rows /= 2;
                     const int segs = (d.h + rows - 1) / rows;
                     const uint8_t* sg = l == 1 ? nullptr : a.grad[l - 1] + fs * s.plane_stride;
                     uint8_t* g0w      = l == 1 ? a.grad[0] + fs * s.plane_stride : nullptr;
-                    const dim3 gEdge(1 + (strips - edge0), segs, m), gMid(std::max(edge0 - 1, 0), segs, m);
-#define SVO_MARCH(BASE, EDGE, GRID)                                                                                                   \
-    k_pyr_march<BASE, EDGE><<<GRID, 32, 0, ctx->pyr_stream>>>(a.img[l - 1] + fs * s.plane_stride, sg, a.img[l] + fs * d.plane_stride,   \
-                                                            a.grad[l] + fs * d.plane_stride, g0w, s.w, s.h, s.pitch, s.plane_stride,  \
-                                                            d.w, d.h, d.pitch, d.plane_stride, edge0, rows)
-                    if (l == 1) {
-                        SVO_MARCH(true, true, gEdge);
-                        if (gMid.x) SVO_MARCH(true, false, gMid);
-                    } else {
-                        SVO_MARCH(false, true, gEdge);
-                        if (gMid.x) SVO_MARCH(false, false, gMid);
-                    }
-#undef SVO_MARCH
-                    if (gMid.x) ctx->launches++;
+                    const dim3 grid(strips, segs, m);
+                    if (l == 1)
+                        k_pyr_march<true><<<grid, 32, 0, ctx->pyr_stream>>>(a.img[0] + fs * s.plane_stride, sg, a.img[1] + fs * d.plane_stride,
+                                                                           a.grad[1] + fs * d.plane_stride, g0w, s.w, s.h, s.pitch, s.plane_stride,
+                                                                           d.w, d.h, d.pitch, d.plane_stride, edge0, rows);
+                    else
+                        k_pyr_march<false><<<grid, 32, 0, ctx->pyr_stream>>>(a.img[l - 1] + fs * s.plane_stride, sg, a.img[l] + fs * d.plane_stride,
+                                                                            a.grad[l] + fs * d.plane_stride, g0w, s.w, s.h, s.pitch, s.plane_stride,
+                                                                            d.w, d.h, d.pitch, d.plane_stride, edge0, rows);
                 } else if (s.w >= 8 && s.h >= 8) {
                     dim3 grid((d.w + PT_X - 1) / PT_X, (d.h + PT_Y - 1) / PT_Y, m);
                     k_pyr_level<false><<<grid, 256, 0, ctx->pyr_stream>>>(

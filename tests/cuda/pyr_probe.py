@@ -21,7 +21,7 @@ with torch.cuda.stream(stream):
         ctx.sync()
         for chunk in sys.argv[1:] or ["48"]:
             os.environ["SVO_PYR_CHUNK"] = chunk
-            for n in (1, 3, 16, 64, 256, 1024):
+            for n in ([int(os.environ["PYR_N"])] if "PYR_N" in os.environ else (1, 3, 16, 64, 256, 1024)):
                 for _ in range(3):
                     ctx.rebuild(0, n)
                 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
