@@ -138,7 +138,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_align_v5(const V5Args a)
     sel.rp = 0;
 #ifdef SVO_PROFILE
     if (a.dbg && job == 0 && tid == 0)
-        for (int i = 48; i < 52; i++) a.dbg[i] = 0;
+        for (int i = 48; i < 56; i++) a.dbg[i] = 0;
 #endif
     if (tid == 0) {
 #pragma unroll
@@ -515,7 +515,13 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_align_v5(const V5Args a)
                         if (ctrl->first) ctrl->first_sigma = ctrl->sigma;
                         const bool wasFirst = ctrl->first;
                         record_first(ctrl->E, chi2, 0.0, ctrl->n_eval);
+#ifdef SVO_PROFILE
+                        const long long tq0 = clock64();
+#endif
                         solve6_inline(ctrl->E, 0.0, dx);
+#ifdef SVO_PROFILE
+                        if (a.dbg && job == 0) a.dbg[52] += clock64() - tq0;
+#endif
                         if (wasFirst && statsOut)
                             for (int i = 0; i < 6; i++) statsOut[(size_t)job * nLevels + si].dx[i] = dx[i];
                         ctrl->iters_level++;
@@ -540,7 +546,13 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_align_v5(const V5Args a)
                             ctrl->preChi2  = chi2;
                             double step    = 0;
                             for (int i = 0; i < 6; i++) step += dx[i] * dx[i];
+#ifdef SVO_PROFILE
+                            const long long tq1 = clock64();
+#endif
                             svo::pose_update_right_exp_neg_fast(ctrl->pose, dx);
+#ifdef SVO_PROFILE
+                            if (a.dbg && job == 0) a.dbg[53] += clock64() - tq1;
+#endif
                             if (step < 1e-16 || chi2 < 1e-1) {
                                 int st = ctrl->status;
                                 st     = step < 1e-16 ? SVO_ST_SMALL_STEP : st;
@@ -616,8 +628,12 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_align_v5(const V5Args a)
                         }
                         if (ctrl->done) ctrl->rmse = sqrt(ctrl->curE[27] / (double)ctrl->cur_n);
                     }
+#ifdef SVO_PROFILE
+                    const long long tq2 = clock64();
+#endif
                     set_Rt(ctrl);
 #ifdef SVO_PROFILE
+                    if (a.dbg && job == 0) a.dbg[54] += clock64() - tq2;
                     if (a.dbg && job == 0) a.dbg[48 + si] += clock64() - ts0;
 #endif
                 }
@@ -690,7 +706,16 @@ svo_status launch_v5(svo_ctx* ctx, int maxF)
     args.results = ctx->d_results;
     args.stats   = ctx->staged_want_stats ? ctx->d_stats : nullptr;
     args.prm     = ctx->staged_params;
-    args.dbg     = ctx->d_dbg;
+    // the per-evaluation trace of job 0 (svo_debug_cycles) costs that job a global-memory round trip per evaluation on the serial
+    // path of its solver: only on request (probes set SVO_ALIGN_TRACE=1; the instrumented twin of the library always traces)
+#ifdef SVO_PROFILE
+    args.dbg = ctx->d_dbg;
+#else
+    {
+        const char* te = getenv("SVO_ALIGN_TRACE");
+        args.dbg       = (te && te[0] == '1') ? ctx->d_dbg : nullptr;
+    }
+#endif
     {
         const char* fe = getenv("SVO_S5_FORCE");
         args.force     = fe ? atoi(fe) : 0;

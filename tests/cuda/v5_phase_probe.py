@@ -24,5 +24,5 @@ for idx in (0, 3):
             tot = d[:, :6].sum(0); tot[5] = 0; n = d[:, 6].sum()
             print("cycles per evaluation:", (tot / n).round(0), "total", (tot.sum() / n).round(0), "=> us/eval %.2f" % (tot.sum() / n / 1965))
             sel = dd.reshape(-1)[32:45]
-            print("solve cycles per level (thread 0):", dd.reshape(-1)[48:52], "per evaluation %.0f" % (dd.reshape(-1)[48:52].sum() / n))
+            print("solve cycles per level (thread 0):", dd.reshape(-1)[48:52], "per evaluation %.0f" % (dd.reshape(-1)[48:52].sum() / n), "| of which LDLT %.0f, exp map + pose %.0f, quaternion -> R %.0f" % tuple(dd.reshape(-1)[52:55] / n))
             print("selection cycles (total over the pair):", ", ".join("%s %d" % (nm, v) for nm, v in zip(NAMES, sel)))

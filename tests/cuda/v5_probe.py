@@ -10,6 +10,7 @@ import sys
 import time
 
 import numpy as np
+os.environ["SVO_ALIGN_TRACE"] = "1"   # the per-evaluation sigma trace of job 0
 
 sys.path.insert(0, "/root/repo")
 sys.path.insert(0, "/root/repo/oracle")

@@ -2,6 +2,7 @@
 batch alone as job 0 with SVO_S5_FORCE=0 / 1 / 2 and prints the per-evaluation sigma traces of the pairs that differ."""
 import importlib, os, sys
 import numpy as np
+os.environ["SVO_ALIGN_TRACE"] = "1"   # the per-evaluation sigma trace of job 0
 sys.path.insert(0, "/root/repo")
 pkg = importlib.import_module("semi-direct-visual-odometry_b200")
 capi, synth = pkg.capi, pkg.synth
