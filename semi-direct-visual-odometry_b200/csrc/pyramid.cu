@@ -563,7 +563,9 @@ svo_status launch_pyramid_build(svo_ctx* ctx, int first_slot, int n)
     // batch: chunking the batch so that L2 holds what a level hands to the next saves 19 % of the DRAM reads and loses more than
     // that to the extra launches (measured, tests/cuda/pyr_probe.py).  A single frame (the per-frame front end) keeps the fused
     // tile kernel: a handful of CTAs either way, and one launch instead of two.
-    if (n >= 4 && a.levels >= 2 && g0.w >= 64 && g0.h >= 8) {
+    const char* me   = getenv("SVO_PYR_MARCH_MIN");  // (measurements) smallest batch that takes the marching kernels
+    const int nMarch = me ? atoi(me) : 4;
+    if (n >= nMarch && a.levels >= 2 && g0.w >= 64 && g0.h >= 8) {
         const char* ce  = getenv("SVO_PYR_CHUNK");  // (measurements) frames per chunk
         const int chunk = ce ? std::max(1, atoi(ce)) : 1 << 30;
         for (int c0 = 0; c0 < n; c0 += chunk) {
