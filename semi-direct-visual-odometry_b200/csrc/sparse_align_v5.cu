@@ -4,16 +4,16 @@
 //
 //   level set-up   computeJacobian (:69-192) fused into the kernel: every thread reads the (P+3)^2 reference bytes of its
 //                  feature, builds the (P+2)^2 bilinear template grid in FP64 and keeps, feature-minor in shared memory,
-//                  the template T and twice the central differences (gx, gy) of every patch pixel; the 2x6 image
-//                  Jacobian (computeImageJac, :194-248) stays in registers.  Nothing is staged through global memory.
+//                  the template T and twice the central differences (gx, gy) of every patch pixel, the 2x6 image
+//                  Jacobian (computeImageJac, :194-248) and the world point.  Nothing is staged through global memory.
 //   evaluation     computeResiduals (:251-370) + tukeyWeighting + normal equations:
 //       warp       p_cur = R p_W + t, project, scale (FP64)
-//       sample     the (P+1)^2 footprint of the current image lives in REGISTERS (8-byte row windows), re-fetched from
-//                  L2 only when the feature's integer position leaves the window; bilinear in FP32
-//       sigma      1.4826 MAD: median and median absolute deviation found together (select5.cuh)
+//       sample     the (P+1)^2 footprint of the current image lives in REGISTERS (8-byte row windows, one spare row and
+//                  column on either side), re-fetched from L2 only when the feature leaves them; bilinear in FP32
+//       sigma      1.4826 MAD: exact median and median absolute deviation, no shared-memory atomics per key (select5.cuh)
 //       reduce     per-feature patch sums sxx sxy syy bx by chi2 -> 28 entries of J^T W J, J^T W r, chi2 through the
 //                  factorisation J_row = gx A + gy B; transposed warp-shuffle reduction, FP64 across warps
-//       solve      damping, LDLT 6x6, pose <- pose exp(-dx) in FP64 by warp 0; accept / reject on device
+//       solve      damping, LDLT 6x6 in registers, pose <- pose exp(-dx) in FP64 by one thread; accept / reject on device
 #include <float.h>
 #include <stdlib.h>
 
@@ -182,7 +182,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_align_v5(const V5Args a)
     const double fx0 = a.K[0], fy0 = a.K[1], cx0 = a.K[2], cy0 = a.K[3];
     const int border = P / 2 + 2;
     const int refSlot = f < J->n_ref ? J->ref_slot : J->kf_slot;
-    uint32_t tierCount = 0;  // diagnostics: hot | cold << 8 | generic << 16 evaluations
+    uint32_t tierCount = 0;  // diagnostics, evaluations by selection route: prediction + count passes | no prediction << 8 | bisection << 16 | predicted brackets alone << 24
     int parity         = 0;
     S5Pred pred;
     s5_pred_init(pred);
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(NT, 512 / NT) k_align_v5(const V5Args a)
             ctrl->pre_pose    = ctrl->pose;
         }
         __syncthreads();  // ctrl init visible
-        pred.haveMove = false;  // the deviation changes with the level: no hot attempt at its first evaluation
+        pred.haveMove = false;  // the deviation changes with the level: no predicted bracket at its first evaluation
 
         // current-image window of this feature: FW + 1 rows x 8 bytes starting at column wx, row wy -- one column of slack on
         // either side and one row: a warp re-fetches (an L2 round trip for all its lanes) only when one of its features moves
